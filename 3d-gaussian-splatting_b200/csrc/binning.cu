@@ -1,0 +1,206 @@
+// Tile binning.  (1) the reference's legacy dense-list API (calc_tile_list / gather_gaussians);
+// (2) the fused path: (tile | depth) key emission, and the post-sort pass that derives the
+// per-tile ranges and packs the sorted per-instance record streams the blend kernels stream.
+#include "internal.h"
+
+namespace {
+
+constexpr int kBlock = 256;
+
+// ---- legacy: reference gaussian.cu:101-250 ---------------------------------------------
+__device__ __forceinline__ void append_to_tile(int* tile_n_point, int* list, int max_per_tile, uint32_t tid,
+                                               uint32_t pid) {
+  // The reference checks capacity non-atomically and then appends at the atomic's old value
+  // (gaussian.cu:244-247), which can overrun a row.  Here the count always increases and only
+  // in-capacity slots are written; the caller clamps the count (splatter.py:586).
+  int old = atomicAdd(tile_n_point + tid, 1);
+  if (old < max_per_tile) list[(size_t)max_per_tile * tid + old] = (int)pid;
+}
+
+__global__ void tile_list_dist_kernel(const float* __restrict__ pos, const float* __restrict__ top,
+                                      const float* __restrict__ bottom, const float* __restrict__ left,
+                                      const float* __restrict__ right, int* tile_n_point, int* list, uint32_t n,
+                                      uint32_t n_tiles, int max_per_tile, float thresh) {
+  uint32_t pid = blockDim.x * blockIdx.x + threadIdx.x;
+  uint32_t tid = blockDim.y * blockIdx.y + threadIdx.y;
+  if (pid >= n || tid >= n_tiles) return;
+  float cy = (top[tid] + bottom[tid]) / 2;                   // :124-128
+  float cx = (left[tid] + right[tid]) / 2;
+  float d1 = pos[3 * pid] - cx, d2 = pos[3 * pid + 1] - cy;
+  if (d1 * d1 + d2 * d2 < thresh) append_to_tile(tile_n_point, list, max_per_tile, tid, pid);
+}
+
+__device__ __forceinline__ bool bbox_of(float cx, float cy, float a, float b, float c, float d, float t2,
+                                        float& l, float& r, float& tp, float& bt) {
+  float det = a * d - b * c;
+  if (det <= 0.f) return false;
+  float ai = (float)((double)d / ((double)det + 1e-14));
+  float di = (float)((double)a / ((double)det + 1e-14));
+  float sx = sqrtf(di * t2 * det), sy = sqrtf(ai * t2 * det);
+  r = cx + sx;
+  l = cx - sx;
+  tp = cy - sy;
+  bt = cy + sy;
+  return true;
+}
+
+__global__ void tile_list_prob_kernel(const float* __restrict__ pos, const float* __restrict__ cov,
+                                      const float* __restrict__ top, const float* __restrict__ bottom,
+                                      const float* __restrict__ left, const float* __restrict__ right,
+                                      int* tile_n_point, int* list, uint32_t n, uint32_t n_tiles, int max_per_tile,
+                                      float thresh) {
+  uint32_t pid = blockDim.x * blockIdx.x + threadIdx.x;
+  uint32_t tid = blockDim.y * blockIdx.y + threadIdx.y;
+  if (pid >= n || tid >= n_tiles) return;
+  float4 cv = reinterpret_cast<const float4*>(cov)[pid];
+  float l, r, tp, bt;
+  if (!bbox_of(pos[3 * pid], pos[3 * pid + 1], cv.x, cv.y, cv.z, cv.w, -2.f * logf(thresh), l, r, tp, bt)) return;
+  if (!(right[tid] < l || r < left[tid] || bottom[tid] < tp || bt < top[tid]))   // :187
+    append_to_tile(tile_n_point, list, max_per_tile, tid, pid);
+}
+
+__global__ void __launch_bounds__(kBlock) tile_list_prob2_kernel(const float* __restrict__ pos,
+                                                                  const float* __restrict__ cov, GsTileGrid grid,
+                                                                  int* tile_n_point, int* list, uint32_t n,
+                                                                  int max_per_tile, float thresh) {
+  uint32_t pid = blockDim.x * blockIdx.x + threadIdx.x;
+  if (pid >= n) return;
+  grid.t2 = -2.f * logf(thresh);                              // :233
+  float4 cv = reinterpret_cast<const float4*>(cov)[pid];
+  uint32_t tx0, tx1, ty0, ty1;
+  if (!gs_tile_rect(grid, pos[3 * pid], pos[3 * pid + 1], cv.x, cv.y, cv.z, cv.w, tx0, tx1, ty0, ty1)) return;
+  for (uint32_t ty = ty0; ty < ty1; ++ty)
+    for (uint32_t tx = tx0; tx < tx1; ++tx) append_to_tile(tile_n_point, list, max_per_tile, tx + ty * grid.ntx, pid);
+}
+
+__global__ void gather_kernel(const int* __restrict__ accum, const int* __restrict__ list, int n_tiles,
+                              int list_stride, int* __restrict__ gathered, int* __restrict__ tile_ids) {
+  // one warp per tile; lanes stride over the tile's entries (coalesced both ways)
+  int tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (tile >= n_tiles) return;
+  int s = accum[tile], e = accum[tile + 1];
+  const int* src = list + (size_t)tile * list_stride;
+  for (int i = (threadIdx.x & 31); i < e - s; i += 32) {
+    gathered[s + i] = src[i];
+    tile_ids[s + i] = tile;
+  }
+}
+
+// ---- fused path ------------------------------------------------------------------------
+// key = tile id << 32 | float bits of depth (depth > 0 => bit order == numeric order)
+// value = Gaussian id.  Instance `rank` of Gaussian g (row-major over its tile rectangle) is
+// written at offsets[g] + rank: that row index doubles as the "slot" the backward pass writes
+// this instance's gradient record to, so a Gaussian's records are contiguous.
+__global__ void __launch_bounds__(kBlock) emit_keys_kernel(const ushort4* __restrict__ rect,
+                                                            const float* __restrict__ depth,
+                                                            const uint32_t* __restrict__ offsets, int n, int ntx,
+                                                            uint64_t* __restrict__ keys,
+                                                            uint32_t* __restrict__ vals) {
+  int i = blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n) return;
+  uint32_t o0 = offsets[i], o1 = offsets[i + 1];
+  if (o1 == o0) return;
+  ushort4 rc = rect[i];
+  uint32_t dbits = __float_as_uint(depth[i]);
+  uint32_t r = o0;
+  for (uint32_t ty = rc.y; ty < (uint32_t)rc.y + rc.w; ++ty)
+    for (uint32_t tx = rc.x; tx < (uint32_t)rc.x + rc.z; ++tx, ++r) {
+      keys[r] = ((uint64_t)(ty * ntx + tx) << 32) | dbits;
+      vals[r] = (uint32_t)i;
+    }
+}
+
+__global__ void __launch_bounds__(kBlock) pack_sorted_kernel(
+    const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, long long m, int n_tiles, int ntx,
+    const float4* __restrict__ gA, const float2* __restrict__ gB, const float4* __restrict__ gC,
+    const ushort4* __restrict__ rect, const uint32_t* __restrict__ offsets, float4* __restrict__ pA,
+    float2* __restrict__ pB, float4* __restrict__ pC, int* __restrict__ tile_accum) {
+  long long i = (long long)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= m) return;
+  uint32_t tile = (uint32_t)(keys[i] >> 32);
+  // tile range boundaries (tile_n_point_accum semantics: accum[t] = first sorted index of tile t)
+  if (i == 0) {
+    for (uint32_t t = 0; t <= tile; ++t) tile_accum[t] = 0;
+  } else {
+    uint32_t prev = (uint32_t)(keys[i - 1] >> 32);
+    for (uint32_t t = prev + 1; t <= tile; ++t) tile_accum[t] = (int)i;
+  }
+  if (i == m - 1)
+    for (uint32_t t = tile + 1; t <= (uint32_t)n_tiles; ++t) tile_accum[t] = (int)m;
+
+  uint32_t g = vals[i];
+  ushort4 rc = rect[g];
+  uint32_t tx = tile % ntx, ty = tile / ntx;
+  uint32_t slot = offsets[g] + (ty - rc.y) * rc.z + (tx - rc.x);
+  float4 c = gC[g];
+  c.w = __uint_as_float(slot);
+  pA[i] = gA[g];
+  pB[i] = gB[g];
+  pC[i] = c;
+}
+
+}  // namespace
+
+extern "C" int gs_tile_list(const float* pos, const float* cov, int n, const float* tile_top,
+                            const float* tile_bottom, const float* tile_left, const float* tile_right, int n_tiles,
+                            int* tile_n_point, int* tile_gaussian_list, int max_per_tile, float thresh, int method,
+                            float tile_length_x, float tile_length_y, int n_tiles_x, int n_tiles_y, float leftmost,
+                            float topmost, gs_stream_t stream) {
+  if (n < 0 || n_tiles < 0 || max_per_tile < 0) return gs_set_error_msg(GS_ERR_INVALID_ARG, "gs_tile_list: negative size");
+  if (n == 0 || n_tiles == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (method == 0 || method == 1) {
+    dim3 block(32, 8), grid((n + 31) / 32, (n_tiles + 7) / 8);
+    if (grid.y > 65535) return gs_set_error_msg(GS_ERR_INVALID_ARG, "gs_tile_list: too many tiles for method 0/1");
+    if (method == 0)
+      tile_list_dist_kernel<<<grid, block, 0, st>>>(pos, tile_top, tile_bottom, tile_left, tile_right, tile_n_point,
+                                                    tile_gaussian_list, n, n_tiles, max_per_tile, thresh);
+    else
+      tile_list_prob_kernel<<<grid, block, 0, st>>>(pos, cov, tile_top, tile_bottom, tile_left, tile_right,
+                                                    tile_n_point, tile_gaussian_list, n, n_tiles, max_per_tile,
+                                                    thresh);
+  } else {
+    GsTileGrid g;
+    g.lx = tile_length_x;
+    g.ly = tile_length_y;
+    g.leftmost = leftmost;
+    g.topmost = topmost;
+    g.t2 = 0.f;
+    g.ntx = n_tiles_x;
+    g.nty = n_tiles_y;
+    tile_list_prob2_kernel<<<(n + kBlock - 1) / kBlock, kBlock, 0, st>>>(pos, cov, g, tile_n_point,
+                                                                        tile_gaussian_list, n, max_per_tile, thresh);
+  }
+  GS_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gs_gather(const int* tile_n_point_accum, const int* tile_gaussian_list, int n_tiles, int list_stride,
+                         int max_points_for_tile, int* gathered_list, int* tile_ids_for_points,
+                         gs_stream_t stream) {
+  (void)max_points_for_tile;   // only sized the reference's grid (gaussian.cu:367)
+  if (n_tiles < 0) return gs_set_error_msg(GS_ERR_INVALID_ARG, "gs_gather: n_tiles < 0");
+  if (n_tiles == 0) return 0;
+  int warps = kBlock / 32;
+  gather_kernel<<<(n_tiles + warps - 1) / warps, kBlock, 0, (cudaStream_t)stream>>>(
+      tile_n_point_accum, tile_gaussian_list, n_tiles, list_stride, gathered_list, tile_ids_for_points);
+  GS_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+cudaError_t gs_launch_emit_keys(const ushort4* rect, const float* depth, const uint32_t* offsets, int n, int ntx,
+                                uint64_t* keys, uint32_t* vals, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  emit_keys_kernel<<<(n + kBlock - 1) / kBlock, kBlock, 0, st>>>(rect, depth, offsets, n, ntx, keys, vals);
+  return cudaGetLastError();
+}
+
+cudaError_t gs_launch_pack_sorted(const uint64_t* keys, const uint32_t* vals, long long m, int n_tiles, int ntx,
+                                  const float4* gA, const float2* gB, const float4* gC, const ushort4* rect,
+                                  const uint32_t* offsets, float4* pA, float2* pB, float4* pC, int* tile_accum,
+                                  cudaStream_t st) {
+  if (m == 0) return cudaMemsetAsync(tile_accum, 0, sizeof(int) * (size_t)(n_tiles + 1), st);
+  pack_sorted_kernel<<<(unsigned)((m + kBlock - 1) / kBlock), kBlock, 0, st>>>(
+      keys, vals, m, n_tiles, ntx, gA, gB, gC, rect, offsets, pA, pB, pC, tile_accum);
+  return cudaGetLastError();
+}

@@ -1,0 +1,486 @@
+// Per-tile front-to-back alpha compositing, forward and backward (the hot kernels).
+//
+// Semantics: reference gaussian.cu:806-970 (draw_kernel) and :440-803 (draw_backward_kernel):
+// 16x16 pixel tiles, each tile blends its (depth-sorted) instance range front to back,
+// a pixel stops before an instance once its transmittance is < 1e-4, no alpha clamp, no
+// 1/255 skip, black background.  Design (not the reference's):
+//   * each tile's range is contiguous in three packed record streams (see gs_common.cuh) and is
+//     staged into shared memory by 1-D bulk async copies (cp.async.bulk -> UBLKCP, mbarrier
+//     complete_tx), double buffered; one elected thread issues, nobody spends LSU slots on it;
+//   * per (pixel, instance): one ex2 (opacity folded into the exponent) and ~15 FP32 ops;
+//     no FP64, no division in the forward loop;
+//   * whole-warp and whole-CTA early exit once every pixel is saturated, so a tile's tail is
+//     never read (M_eff accounting);
+//   * backward: 64 threads x 4 pixels per tile; 9 moment sums per instance are reduced with a
+//     recursive-halving shuffle network (14 SHFL instead of 45), combined across the two warps
+//     through shared memory and written as ONE record per instance (no atomics, deterministic).
+#include "internal.h"
+
+namespace {
+
+// =======================================================================================
+// forward
+// =======================================================================================
+constexpr int FWD_THREADS = 256;
+constexpr int FWD_CH = 256;
+constexpr int FWD_STAGES = 2;
+
+struct FwdSmem {
+  float4 A[FWD_STAGES][FWD_CH];
+  float4 C[FWD_STAGES][FWD_CH];
+  float2 B[FWD_STAGES][FWD_CH + 2];
+  uint64_t full[FWD_STAGES];
+};
+
+template <typename SM, int CH>
+__device__ __forceinline__ void issue_chunk(SM& sm, int stage, const float4* __restrict__ pA,
+                                            const float2* __restrict__ pB, const float4* __restrict__ pC,
+                                            int base, int n, int shift) {
+  uint32_t bytes_a = (uint32_t)n * 16u;
+  uint32_t nb = (uint32_t)(n + shift + 1) & ~1u;
+  uint32_t bytes_b = nb * 8u;
+  gs_mbar_expect_tx(&sm.full[stage], 2u * bytes_a + bytes_b);
+  gs_bulk_g2s(sm.A[stage], pA + base, bytes_a, &sm.full[stage]);
+  gs_bulk_g2s(sm.C[stage], pC + base, bytes_a, &sm.full[stage]);
+  gs_bulk_g2s(sm.B[stage], pB + (base - shift), bytes_b, &sm.full[stage]);
+}
+
+__global__ void __launch_bounds__(FWD_THREADS) blend_fwd_kernel(const float4* __restrict__ pA,
+                                                                 const float2* __restrict__ pB,
+                                                                 const float4* __restrict__ pC,
+                                                                 const int* __restrict__ tile_accum, int wp, int hp,
+                                                                 int ntx, float fx, float fy,
+                                                                 float* __restrict__ image,
+                                                                 int* __restrict__ tile_neff) {
+  __shared__ __align__(16) FwdSmem sm;
+  const int tile = blockIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tx = tile % ntx, ty = tile / ntx;
+  // warp = 8x4 pixel block of the 16x16 tile
+  const int ix = tx * GS_TILE + (warp & 1) * 8 + (lane & 7);
+  const int iy = ty * GS_TILE + (warp >> 1) * 4 + (lane >> 3);
+  const float px = gs_pixel_coord(ix, wp, fx);
+  const float py = gs_pixel_coord(iy, hp, fy);
+
+  const int start = tile_accum[tile];
+  const int cnt = tile_accum[tile + 1] - start;
+  const int shift = start & 1;
+  const int nchunks = (cnt + FWD_CH - 1) / FWD_CH;
+
+  if (tid == 0) {
+    for (int s = 0; s < FWD_STAGES; ++s) gs_mbar_init(&sm.full[s], 1);
+    gs_fence_barrier_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int k = 0; k < FWD_STAGES && k < nchunks; ++k)
+      issue_chunk<FwdSmem, FWD_CH>(sm, k, pA, pB, pC, start + k * FWD_CH, min(FWD_CH, cnt - k * FWD_CH), shift);
+  }
+
+  float T = 1.f, cr = 0.f, cg = 0.f, cb = 0.f;
+  int consumed = cnt;
+  int k = 0;
+  for (; k < nchunks; ++k) {
+    const int stage = k % FWD_STAGES;
+    gs_mbar_wait(&sm.full[stage], (uint32_t)((k / FWD_STAGES) & 1));
+    const int n = min(FWD_CH, cnt - k * FWD_CH);
+    const float4* __restrict__ sA = sm.A[stage];
+    const float4* __restrict__ sC = sm.C[stage];
+    const float2* __restrict__ sB = sm.B[stage] + shift;
+
+#define GS_FWD_BODY(J)                                                        \
+  {                                                                           \
+    const float4 a = sA[J];                                                   \
+    const float2 b = sB[J];                                                   \
+    const float4 c = sC[J];                                                   \
+    const float dx = px - a.x, dy = py - a.y;                                 \
+    const float q = fmaf(a.z * dx, dx, fmaf(-a.w * dx, dy, b.x * dy * dy));   \
+    const float alpha = gs_ex2(b.y - q);                                      \
+    const float w = (T > GS_T_STOP) ? alpha * T : 0.f;                        \
+    cr = fmaf(c.x, w, cr);                                                    \
+    cg = fmaf(c.y, w, cg);                                                    \
+    cb = fmaf(c.z, w, cb);                                                    \
+    T -= w;                                                                   \
+  }
+    int j = 0;
+    bool warp_dead = false;
+    for (; j + 8 <= n; j += 8) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) GS_FWD_BODY(j + u)
+      if (__all_sync(0xffffffffu, !(T > GS_T_STOP))) {
+        warp_dead = true;
+        break;
+      }
+    }
+    if (!warp_dead)
+      for (; j < n; ++j) GS_FWD_BODY(j)
+#undef GS_FWD_BODY
+
+    const int all_dead = __syncthreads_and(!(T > GS_T_STOP));
+    if (all_dead) {
+      consumed = min(cnt, (k + 1) * FWD_CH);
+      break;
+    }
+    if (tid == 0 && k + FWD_STAGES < nchunks) {
+      const int kn = k + FWD_STAGES;
+      issue_chunk<FwdSmem, FWD_CH>(sm, stage, pA, pB, pC, start + kn * FWD_CH, min(FWD_CH, cnt - kn * FWD_CH), shift);
+    }
+  }
+  // drain copies that were issued but never consumed (early exit) before the CTA retires
+  if (tid == 0 && k < nchunks) {
+    for (int kk = k + 1; kk < nchunks && kk < k + FWD_STAGES; ++kk)
+      gs_mbar_wait(&sm.full[kk % FWD_STAGES], (uint32_t)((kk / FWD_STAGES) & 1));
+  }
+  float* o = image + ((size_t)iy * wp + ix) * 3;
+  o[0] = cr;
+  o[1] = cg;
+  o[2] = cb;
+  if (tile_neff && tid == 0) tile_neff[tile] = consumed;
+}
+
+// =======================================================================================
+// backward
+// =======================================================================================
+constexpr int BWD_THREADS = 64;
+constexpr int BWD_CH = 64;
+constexpr int BWD_STAGES = 2;
+constexpr int BWD_NV = 9;   // Sx Sy Sxx Sxy Syy S0 Cr Cg | Cb
+
+struct BwdSmem {
+  float4 A[BWD_STAGES][BWD_CH];
+  float4 C[BWD_STAGES][BWD_CH];
+  float2 B[BWD_STAGES][BWD_CH + 2];
+  uint64_t full[BWD_STAGES];
+  float partial[2][BWD_CH * BWD_NV];
+};
+
+__global__ void __launch_bounds__(BWD_THREADS) blend_bwd_kernel(const float4* __restrict__ pA,
+                                                                 const float2* __restrict__ pB,
+                                                                 const float4* __restrict__ pC,
+                                                                 const int* __restrict__ tile_accum, int wp, int hp,
+                                                                 int ntx, float fx, float fy,
+                                                                 const float* __restrict__ image,
+                                                                 const float* __restrict__ grad_image,
+                                                                 float* __restrict__ grad_inst) {
+  __shared__ __align__(16) BwdSmem sm;
+  const int tile = blockIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tx = tile % ntx, ty = tile / ntx;
+  const int start = tile_accum[tile];
+  const int cnt = tile_accum[tile + 1] - start;
+  if (cnt == 0) return;
+  const int shift = start & 1;
+  const int nchunks = (cnt + BWD_CH - 1) / BWD_CH;
+
+  // thread -> 2x2 pixel block
+  const int ix0 = tx * GS_TILE + (tid & 7) * 2;
+  const int iy0 = ty * GS_TILE + (tid >> 3) * 2;
+  float px[2], py[2];
+  px[0] = gs_pixel_coord(ix0, wp, fx);
+  px[1] = gs_pixel_coord(ix0 + 1, wp, fx);
+  py[0] = gs_pixel_coord(iy0, hp, fy);
+  py[1] = gs_pixel_coord(iy0 + 1, hp, fy);
+
+  float T[4], R[4], gr[4], gg[4], gb[4];
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    const size_t off = ((size_t)(iy0 + (p >> 1)) * wp + (ix0 + (p & 1))) * 3;
+    gr[p] = grad_image[off];
+    gg[p] = grad_image[off + 1];
+    gb[p] = grad_image[off + 2];
+    R[p] = gr[p] * image[off] + gg[p] * image[off + 1] + gb[p] * image[off + 2];
+    T[p] = 1.f;
+  }
+
+  if (tid == 0) {
+    for (int s = 0; s < BWD_STAGES; ++s) gs_mbar_init(&sm.full[s], 1);
+    gs_fence_barrier_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int k = 0; k < BWD_STAGES && k < nchunks; ++k)
+      issue_chunk<BwdSmem, BWD_CH>(sm, k, pA, pB, pC, start + k * BWD_CH, min(BWD_CH, cnt - k * BWD_CH), shift);
+  }
+
+  int consumed = cnt;
+  int k = 0;
+  for (; k < nchunks; ++k) {
+    const int stage = k % BWD_STAGES;
+    gs_mbar_wait(&sm.full[stage], (uint32_t)((k / BWD_STAGES) & 1));
+    const int n = min(BWD_CH, cnt - k * BWD_CH);
+    const float4* __restrict__ sA = sm.A[stage];
+    const float4* __restrict__ sC = sm.C[stage];
+    const float2* __restrict__ sB = sm.B[stage] + shift;
+    float* __restrict__ part = sm.partial[warp];
+
+    int j = 0;
+    for (; j < n; ++j) {
+      if ((j & 3) == 0) {
+        const bool dead = !(T[0] > GS_T_STOP) && !(T[1] > GS_T_STOP) && !(T[2] > GS_T_STOP) && !(T[3] > GS_T_STOP);
+        if (__all_sync(0xffffffffu, dead)) break;
+      }
+      const float4 a = sA[j];
+      const float2 b = sB[j];
+      const float4 c = sC[j];
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = 0.f;
+      float v8 = 0.f;
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const float dx = px[p & 1] - a.x, dy = py[p >> 1] - a.y;
+        const float q = fmaf(a.z * dx, dx, fmaf(-a.w * dx, dy, b.x * dy * dy));
+        const float alpha = gs_ex2(b.y - q);
+        const bool live = T[p] > GS_T_STOP;
+        const float w = live ? alpha * T[p] : 0.f;
+        const float gc = fmaf(gr[p], c.x, fmaf(gg[p], c.y, gb[p] * c.z));
+        R[p] = fmaf(-gc, w, R[p]);                                   // sum_c g_c (out_c - C_c^{<=i})
+        const float rc = gs_rcp(1.0000001f - alpha);                 // 1/(1 - alpha + 1e-7)  (:721)
+        const float dal = fmaf(T[p], gc, -R[p] * rc);                // d L / d alpha            (:710-722)
+        const float e = live ? dal * alpha : 0.f;
+        T[p] -= w;
+        const float ex = e * dx, ey = e * dy;
+        v[0] += ex;
+        v[1] += ey;
+        v[2] = fmaf(ex, dx, v[2]);
+        v[3] = fmaf(ex, dy, v[3]);
+        v[4] = fmaf(ey, dy, v[4]);
+        v[5] += e;
+        v[6] = fmaf(gr[p], w, v[6]);
+        v[7] = fmaf(gg[p], w, v[7]);
+        v8 = fmaf(gb[p], w, v8);
+      }
+      // recursive-halving reduction of v[0..7] over the warp, plain butterfly for v8
+      {
+        const bool up = (lane & 16) != 0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float keep = up ? v[u + 4] : v[u];
+          const float send = up ? v[u] : v[u + 4];
+          v[u] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+      }
+      {
+        const bool up = (lane & 8) != 0;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const float keep = up ? v[u + 2] : v[u];
+          const float send = up ? v[u] : v[u + 2];
+          v[u] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+      }
+      {
+        const bool up = (lane & 4) != 0;
+        const float keep = up ? v[1] : v[0];
+        const float send = up ? v[0] : v[1];
+        v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+      }
+      v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
+      v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v8 += __shfl_xor_sync(0xffffffffu, v8, o);
+      // lane L now holds the warp total of value index ((L>>4)&1)*4 + ((L>>3)&1)*2 + ((L>>2)&1)
+      if ((lane & 3) == 0) part[j * BWD_NV + (((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1))] = v[0];
+      if (lane == 0) part[j * BWD_NV + 8] = v8;
+    }
+    // instances this warp skipped because all of its pixels are saturated
+    for (int z = j * BWD_NV + lane; z < n * BWD_NV; z += 32) part[z] = 0.f;
+    __syncthreads();
+
+    for (int t = tid; t < n; t += BWD_THREADS) {
+      float s[BWD_NV];
+#pragma unroll
+      for (int u = 0; u < BWD_NV; ++u) s[u] = sm.partial[0][t * BWD_NV + u] + sm.partial[1][t * BWD_NV + u];
+      const float4 a = sA[t];
+      const float2 b = sB[t];
+      const uint32_t slot = __float_as_uint(sC[t].w);
+      float4* out = reinterpret_cast<float4*>(grad_inst + (size_t)slot * GS_GREC);
+      // d/dx, d/dy, d/dca, d/dcb  |  d/dcc, d/dl2o, d/dr, d/dg  |  d/db
+      out[0] = make_float4(GS_LN2 * (2.f * a.z * s[0] - a.w * s[1]), GS_LN2 * (2.f * b.x * s[1] - a.w * s[0]),
+                           -GS_LN2 * s[2], GS_LN2 * s[3]);
+      out[1] = make_float4(-GS_LN2 * s[4], GS_LN2 * s[5], s[6], s[7]);
+      out[2] = make_float4(s[8], 0.f, 0.f, 0.f);
+    }
+    const bool dead = !(T[0] > GS_T_STOP) && !(T[1] > GS_T_STOP) && !(T[2] > GS_T_STOP) && !(T[3] > GS_T_STOP);
+    const int all_dead = __syncthreads_and(dead);
+    if (all_dead) {
+      consumed = min(cnt, (k + 1) * BWD_CH);
+      break;
+    }
+    if (tid == 0 && k + BWD_STAGES < nchunks) {
+      const int kn = k + BWD_STAGES;
+      issue_chunk<BwdSmem, BWD_CH>(sm, stage, pA, pB, pC, start + kn * BWD_CH, min(BWD_CH, cnt - kn * BWD_CH), shift);
+    }
+  }
+  if (tid == 0 && k < nchunks) {
+    for (int kk = k + 1; kk < nchunks && kk < k + BWD_STAGES; ++kk)
+      gs_mbar_wait(&sm.full[kk % BWD_STAGES], (uint32_t)((kk / BWD_STAGES) & 1));
+  }
+  // the unread tail of a saturated tile has zero gradient
+  for (int t = consumed + tid; t < cnt; t += BWD_THREADS) {
+    const uint32_t slot = __float_as_uint(pC[start + t].w);
+    float4* out = reinterpret_cast<float4*>(grad_inst + (size_t)slot * GS_GREC);
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    out[0] = z;
+    out[1] = z;
+    out[2] = z;
+  }
+}
+
+// =======================================================================================
+// legacy boundary helpers: per-instance tensors <-> packed record streams
+// =======================================================================================
+__global__ void __launch_bounds__(256) legacy_pack_kernel(const float* __restrict__ pos, const float* __restrict__ rgb,
+                                                           const float* __restrict__ opa,
+                                                           const float* __restrict__ cov, int m,
+                                                           float4* __restrict__ pA, float2* __restrict__ pB,
+                                                           float4* __restrict__ pC) {
+  int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= m) return;
+  float4 cv = reinterpret_cast<const float4*>(cov)[i];
+  GsConic k = gs_make_conic(cv.x, cv.y, cv.z, cv.w);
+  pA[i] = make_float4(pos[3 * i], pos[3 * i + 1], k.ca, k.cb);
+  pB[i] = make_float2(k.cc, log2f(opa[i]));
+  pC[i] = make_float4(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2], __uint_as_float((uint32_t)i));
+}
+
+__global__ void __launch_bounds__(256) legacy_unpack_grads_kernel(const float* __restrict__ grad_inst,
+                                                                   const float* __restrict__ opa,
+                                                                   const float* __restrict__ cov, int m,
+                                                                   float* __restrict__ g_pos,
+                                                                   float* __restrict__ g_rgb,
+                                                                   float* __restrict__ g_opa,
+                                                                   float* __restrict__ g_cov) {
+  int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= m) return;
+  const float4* row = reinterpret_cast<const float4*>(grad_inst + (size_t)i * GS_GREC);
+  float4 v0 = row[0], v1 = row[1], v2 = row[2];
+  float4 cv = reinterpret_cast<const float4*>(cov)[i];
+  float det = cv.x * cv.w - cv.y * cv.z;
+  double pn = 2.0 * (double)det + 1e-14;
+  float sc = (float)((double)GS_LOG2E / pn);
+  float kk = 2.f * sc * sc / GS_LOG2E;
+  float gsc = v0.z * cv.w + v0.w * (cv.y + cv.z) + v1.x * cv.x;
+  g_pos[3 * i] = v0.x;
+  g_pos[3 * i + 1] = v0.y;                                    // z column untouched (gaussian.cu:785-786)
+  reinterpret_cast<float4*>(g_cov)[i] = make_float4(v1.x * sc - gsc * kk * cv.w, v0.w * sc + gsc * kk * cv.z,
+                                                    v0.w * sc + gsc * kk * cv.y, v0.z * sc - gsc * kk * cv.x);
+  g_opa[i] = v1.y / (opa[i] * GS_LN2);
+  g_rgb[3 * i] = v1.z;
+  g_rgb[3 * i + 1] = v1.w;
+  g_rgb[3 * i + 2] = v2.x;
+}
+
+struct LegacyWs {
+  float4* pA;
+  float2* pB;
+  float4* pC;
+  float* grad_inst;
+};
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+inline size_t legacy_ws_layout(int m, LegacyWs* ws, char* base) {
+  size_t off = 0;
+  size_t mm = (size_t)(m > 0 ? m : 0);
+  if (ws) ws->pA = reinterpret_cast<float4*>(base + off);
+  off += align_up(mm * 16, 256);
+  if (ws) ws->pC = reinterpret_cast<float4*>(base + off);
+  off += align_up(mm * 16, 256);
+  if (ws) ws->pB = reinterpret_cast<float2*>(base + off);
+  off += align_up((mm + 2) * 8, 256);
+  if (ws) ws->grad_inst = reinterpret_cast<float*>(base + off);
+  off += align_up(mm * GS_GREC * 4, 256);
+  return off;
+}
+
+}  // namespace
+
+cudaError_t gs_launch_blend_fwd(const float4* pA, const float2* pB, const float4* pC, const int* tile_accum,
+                                const GsFrameGeom& g, float* image, int* tile_neff, cudaStream_t st) {
+  blend_fwd_kernel<<<g.n_tiles, FWD_THREADS, 0, st>>>(pA, pB, pC, tile_accum, g.wp, g.hp, g.ntx, g.fx, g.fy, image,
+                                                      tile_neff);
+  return cudaGetLastError();
+}
+
+cudaError_t gs_launch_blend_bwd(const float4* pA, const float2* pB, const float4* pC, const int* tile_accum,
+                                const GsFrameGeom& g, const float* image, const float* grad_image, float* grad_inst,
+                                cudaStream_t st) {
+  blend_bwd_kernel<<<g.n_tiles, BWD_THREADS, 0, st>>>(pA, pB, pC, tile_accum, g.wp, g.hp, g.ntx, g.fx, g.fy, image,
+                                                      grad_image, grad_inst);
+  return cudaGetLastError();
+}
+
+extern "C" size_t gs_draw_workspace_bytes(int m, int d) {
+  (void)d;
+  return legacy_ws_layout(m, nullptr, nullptr);
+}
+
+static int check_draw_args(const char* fn, int m, int d, int wp, int hp, int weight_normalize, int sigmoid,
+                           size_t ws_bytes, void* ws) {
+  if (m < 0 || wp <= 0 || hp <= 0 || (wp % GS_TILE) || (hp % GS_TILE))
+    return gs_set_error_msg(GS_ERR_INVALID_ARG, fn);
+  if (weight_normalize || sigmoid || d != 3) return gs_set_error_msg(GS_ERR_UNSUPPORTED, fn);
+  if (m > 0 && (ws == nullptr || ws_bytes < gs_draw_workspace_bytes(m, d)))
+    return gs_set_error_msg(GS_ERR_INVALID_ARG, fn);
+  return 0;
+}
+
+extern "C" int gs_draw_fwd(const float* pos, const float* rgb, const float* opa, const float* cov,
+                           const int* tile_n_point_accum, int m, int d, int width_padded, int height_padded,
+                           float focal_x, float focal_y, int weight_normalize, int sigmoid, const float* rays_o,
+                           const float* lefttop, const float* vec_dx, const float* vec_dy, float* image,
+                           void* workspace, size_t workspace_bytes, gs_stream_t stream) {
+  (void)rays_o; (void)lefttop; (void)vec_dx; (void)vec_dy;
+  int rc = check_draw_args("gs_draw_fwd: bad/unsupported arguments", m, d, width_padded, height_padded,
+                           weight_normalize, sigmoid, workspace_bytes, workspace);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  LegacyWs ws{};
+  legacy_ws_layout(m, &ws, static_cast<char*>(workspace));
+  if (m > 0) {
+    legacy_pack_kernel<<<(m + 255) / 256, 256, 0, st>>>(pos, rgb, opa, cov, m, ws.pA, ws.pB, ws.pC);
+    GS_CUDA_TRY(cudaGetLastError());
+  }
+  GsFrameGeom g{};
+  g.wp = width_padded;
+  g.hp = height_padded;
+  g.ntx = width_padded / GS_TILE;
+  g.nty = height_padded / GS_TILE;
+  g.n_tiles = g.ntx * g.nty;
+  g.fx = focal_x;
+  g.fy = focal_y;
+  GS_CUDA_TRY(gs_launch_blend_fwd(ws.pA, ws.pB, ws.pC, tile_n_point_accum, g, image, nullptr, st));
+  return 0;
+}
+
+extern "C" int gs_draw_bwd(const float* pos, const float* rgb, const float* opa, const float* cov,
+                           const int* tile_n_point_accum, int m, int d, int width_padded, int height_padded,
+                           float focal_x, float focal_y, int weight_normalize, int sigmoid, const float* rays_o,
+                           const float* lefttop, const float* vec_dx, const float* vec_dy, const float* image,
+                           const float* grad_image, float* grad_pos, float* grad_rgb, float* grad_opa,
+                           float* grad_cov, void* workspace, size_t workspace_bytes, gs_stream_t stream) {
+  (void)rays_o; (void)lefttop; (void)vec_dx; (void)vec_dy;
+  int rc = check_draw_args("gs_draw_bwd: bad/unsupported arguments", m, d, width_padded, height_padded,
+                           weight_normalize, sigmoid, workspace_bytes, workspace);
+  if (rc) return rc;
+  if (m == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  LegacyWs ws{};
+  legacy_ws_layout(m, &ws, static_cast<char*>(workspace));
+  legacy_pack_kernel<<<(m + 255) / 256, 256, 0, st>>>(pos, rgb, opa, cov, m, ws.pA, ws.pB, ws.pC);
+  GS_CUDA_TRY(cudaGetLastError());
+  GsFrameGeom g{};
+  g.wp = width_padded;
+  g.hp = height_padded;
+  g.ntx = width_padded / GS_TILE;
+  g.nty = height_padded / GS_TILE;
+  g.n_tiles = g.ntx * g.nty;
+  g.fx = focal_x;
+  g.fy = focal_y;
+  GS_CUDA_TRY(gs_launch_blend_bwd(ws.pA, ws.pB, ws.pC, tile_n_point_accum, g, image, grad_image, ws.grad_inst, st));
+  legacy_unpack_grads_kernel<<<(m + 255) / 256, 256, 0, st>>>(ws.grad_inst, opa, cov, m, grad_pos, grad_rgb, grad_opa,
+                                                            grad_cov);
+  GS_CUDA_TRY(cudaGetLastError());
+  return 0;
+}

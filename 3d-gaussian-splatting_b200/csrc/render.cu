@@ -1,0 +1,322 @@
+// Frame orchestration for the fused path: owns device workspaces and strings the stages
+//   project -> exclusive scan -> key emit -> CUB radix sort (onesweep) -> range+pack -> blend
+// and the backward  blend_bwd -> project_bwd (segment-sum + chain rule).
+// Replaces the PyTorch glue of reference splatter.py:513-655 (4 boolean-mask compactions, the
+// dense [T, N/20] tile list, cumsum, two 4-tensor gathers, fp32-key torch.sort, >= 7 host
+// syncs) with 7 launches and ONE 8-byte readback (the instance count M sizes the sort).
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "internal.h"
+
+// ---- error plumbing ---------------------------------------------------------------------
+static thread_local char g_err[512] = {0};
+
+int gs_set_error(cudaError_t e, const char* what) {
+  snprintf(g_err, sizeof(g_err), "CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+  return (int)e;
+}
+int gs_set_error_msg(int code, const char* what) {
+  snprintf(g_err, sizeof(g_err), "%s", what);
+  return code;
+}
+extern "C" const char* gs_last_error(void) { return g_err; }
+extern "C" int gs_abi_version(void) { return 1; }
+
+// ---- growable device buffer -------------------------------------------------------------
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes, cudaStream_t st) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) {
+      cudaError_t e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) return e;
+      cudaFree(p);
+      p = nullptr;
+      cap = 0;
+    }
+    size_t want = bytes + bytes / 8 + 256;   // slack so M jitter between frames does not realloc
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) return e;
+    cap = want;
+    return cudaSuccess;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T>
+  T* as() const { return static_cast<T*>(p); }
+};
+
+struct gs_ctx {
+  int device = 0;
+  // per Gaussian
+  DevBuf gA, gB, gC, rect, depth, count, offsets;
+  // per instance
+  DevBuf keys_in, keys_out, vals_in, vals_out, pA, pB, pC, grad_inst;
+  // per tile / misc
+  DevBuf tile_accum, tile_neff, cub_tmp, counters, img_dev, gimg_dev;
+  unsigned long long* host_m = nullptr;   // pinned: {M}
+  // state of the last forward
+  bool have_forward = false;
+  int n = 0, d = 3, scale_act = 0;
+  long long m = 0;
+  GsCam cam{};
+  GsTileGrid grid{};
+  GsFrameGeom geom{};
+  float near_plane = 0.f, half_w = 0.f, half_h = 0.f;
+  int64_t* mask_ptr = nullptr;
+};
+
+extern "C" int gs_ctx_create(gs_ctx** out) {
+  if (!out) return gs_set_error_msg(GS_ERR_INVALID_ARG, "gs_ctx_create: null out");
+  gs_ctx* c = new (std::nothrow) gs_ctx();
+  if (!c) return gs_set_error_msg(GS_ERR_INVALID_ARG, "gs_ctx_create: out of host memory");
+  GS_CUDA_TRY(cudaGetDevice(&c->device));
+  cudaError_t e = cudaMallocHost(reinterpret_cast<void**>(&c->host_m), 64);
+  if (e != cudaSuccess) {
+    delete c;
+    return gs_set_error(e, "cudaMallocHost");
+  }
+  *out = c;
+  return 0;
+}
+
+extern "C" void gs_ctx_destroy(gs_ctx* c) {
+  if (!c) return;
+  cudaDeviceSynchronize();
+  DevBuf* bufs[] = {&c->gA, &c->gB, &c->gC, &c->rect, &c->depth, &c->count, &c->offsets, &c->keys_in, &c->keys_out,
+                    &c->vals_in, &c->vals_out, &c->pA, &c->pB, &c->pC, &c->grad_inst, &c->tile_accum, &c->tile_neff,
+                    &c->cub_tmp, &c->counters, &c->img_dev, &c->gimg_dev};
+  for (DevBuf* b : bufs) b->release();
+  if (c->host_m) cudaFreeHost(c->host_m);
+  delete c;
+}
+
+static int ceil_log2(unsigned v) {
+  int b = 0;
+  while ((1u << b) < v) ++b;
+  return b;
+}
+
+extern "C" int gs_render_forward(gs_ctx* c, const float* pos, const float* rgb, const float* opa, const float* quat,
+                                 const float* scale, int n, int d, int scale_activation, const gs_camera* cam,
+                                 float* image, int64_t* culling_mask, gs_stream_t stream) {
+  if (!c || !cam || n < 0) return gs_set_error_msg(GS_ERR_INVALID_ARG, "gs_render_forward: bad arguments");
+  if (d != 3) return gs_set_error_msg(GS_ERR_UNSUPPORTED, "gs_render_forward: only d == 3 (RGB) is implemented");
+  if (cam->width <= 0 || cam->height <= 0 || !(cam->focal_x > 0.f) || !(cam->focal_y > 0.f))
+    return gs_set_error_msg(GS_ERR_INVALID_ARG, "gs_render_forward: bad camera");
+  cudaStream_t st = (cudaStream_t)stream;
+  c->have_forward = false;
+
+  GsFrameGeom g{};
+  g.width = cam->width;
+  g.height = cam->height;
+  g.wp = (cam->width + GS_TILE - 1) / GS_TILE * GS_TILE;     // splatter.py:259-260
+  g.hp = (cam->height + GS_TILE - 1) / GS_TILE * GS_TILE;
+  g.ntx = g.wp / GS_TILE;
+  g.nty = g.hp / GS_TILE;
+  g.n_tiles = g.ntx * g.nty;
+  g.fx = cam->focal_x;
+  g.fy = cam->focal_y;
+  if (g.ntx > 65535 || g.nty > 65535) return gs_set_error_msg(GS_ERR_INVALID_ARG, "gs_render_forward: image too large");
+
+  // Host scalars are formed in double then narrowed, like the Python floats that the reference
+  // passes through pybind (splatter.py:279-282, :532-533).
+  GsTileGrid grid{};
+  grid.lx = (float)(16.0 / (double)cam->focal_x);
+  grid.ly = (float)(16.0 / (double)cam->focal_y);
+  grid.leftmost = (float)(-(double)g.wp / 2.0 / (double)cam->focal_x);
+  grid.topmost = (float)(-(double)g.hp / 2.0 / (double)cam->focal_y);
+  grid.t2 = -2.f * logf(cam->tile_thresh);
+  grid.ntx = g.ntx;
+  grid.nty = g.nty;
+  GsCam dc{};
+  memcpy(dc.r, cam->rot, sizeof(dc.r));
+  memcpy(dc.t, cam->tran, sizeof(dc.t));
+  float half_w = (float)((double)cam->width * 1.2 / 2.0 / (double)cam->focal_x);
+  float half_h = (float)((double)cam->height * 1.2 / 2.0 / (double)cam->focal_y);
+
+  size_t N = (size_t)n;
+  GS_CUDA_TRY(c->gA.reserve(N * 16, st));
+  GS_CUDA_TRY(c->gB.reserve(N * 8, st));
+  GS_CUDA_TRY(c->gC.reserve(N * 16, st));
+  GS_CUDA_TRY(c->rect.reserve(N * 8, st));
+  GS_CUDA_TRY(c->depth.reserve(N * 4, st));
+  GS_CUDA_TRY(c->count.reserve((N + 1) * 4, st));
+  GS_CUDA_TRY(c->offsets.reserve((N + 1) * 4, st));
+  GS_CUDA_TRY(c->tile_accum.reserve((size_t)(g.n_tiles + 1) * 4, st));
+  GS_CUDA_TRY(c->tile_neff.reserve((size_t)g.n_tiles * 4, st));
+  GS_CUDA_TRY(c->counters.reserve(64, st));
+
+  // 1. projection + activations + tile rectangle
+  GS_CUDA_TRY(cudaMemsetAsync(c->counters.p, 0, 64, st));
+  GS_CUDA_TRY(cudaMemsetAsync(c->count.as<uint32_t>() + N, 0, 4, st));
+  GS_CUDA_TRY(gs_launch_fused_project(pos, rgb, opa, quat, scale, n, scale_activation, dc, grid, cam->near_plane,
+                                      half_w, half_h, c->gA.as<float4>(), c->gB.as<float2>(), c->gC.as<float4>(),
+                                      c->rect.as<ushort4>(), c->depth.as<float>(), c->count.as<uint32_t>(),
+                                      culling_mask, c->counters.as<unsigned int>(), st));
+  // 2. exclusive scan of the per-Gaussian tile counts (N+1 items: offsets[N] = M)
+  size_t scan_tmp = 0;
+  GS_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp, c->count.as<uint32_t>(), c->offsets.as<uint32_t>(),
+                                            n + 1, st));
+  GS_CUDA_TRY(c->cub_tmp.reserve(scan_tmp, st));
+  GS_CUDA_TRY(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, scan_tmp, c->count.as<uint32_t>(),
+                                            c->offsets.as<uint32_t>(), n + 1, st));
+  // the one host round trip of the frame
+  *c->host_m = 0;
+  GS_CUDA_TRY(cudaMemcpyAsync(c->host_m, c->offsets.as<uint32_t>() + N, 4, cudaMemcpyDeviceToHost, st));
+  GS_CUDA_TRY(cudaStreamSynchronize(st));
+  long long m = (long long)(*c->host_m & 0xffffffffull);
+  if (m >= (1ll << 31)) return gs_set_error_msg(GS_ERR_UNSUPPORTED, "gs_render_forward: more than 2^31 tile instances");
+  size_t M = (size_t)m;
+
+  GS_CUDA_TRY(c->pA.reserve(M * 16 + 16, st));
+  GS_CUDA_TRY(c->pC.reserve(M * 16 + 16, st));
+  GS_CUDA_TRY(c->pB.reserve((M + 2) * 8, st));
+  if (m > 0) {
+    GS_CUDA_TRY(c->keys_in.reserve(M * 8, st));
+    GS_CUDA_TRY(c->keys_out.reserve(M * 8, st));
+    GS_CUDA_TRY(c->vals_in.reserve(M * 4, st));
+    GS_CUDA_TRY(c->vals_out.reserve(M * 4, st));
+    // 3. keys
+    GS_CUDA_TRY(gs_launch_emit_keys(c->rect.as<ushort4>(), c->depth.as<float>(), c->offsets.as<uint32_t>(), n, g.ntx,
+                                    c->keys_in.as<uint64_t>(), c->vals_in.as<uint32_t>(), st));
+    // 4. (tile | depth) radix sort — only the significant key bits
+    int end_bit = 32 + ceil_log2((unsigned)g.n_tiles);
+    if (end_bit < 33) end_bit = 33;
+    size_t sort_tmp = 0;
+    GS_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, c->keys_in.as<uint64_t>(),
+                                                c->keys_out.as<uint64_t>(), c->vals_in.as<uint32_t>(),
+                                                c->vals_out.as<uint32_t>(), (int)m, 0, end_bit, st));
+    GS_CUDA_TRY(c->cub_tmp.reserve(sort_tmp, st));
+    GS_CUDA_TRY(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, sort_tmp, c->keys_in.as<uint64_t>(),
+                                                c->keys_out.as<uint64_t>(), c->vals_in.as<uint32_t>(),
+                                                c->vals_out.as<uint32_t>(), (int)m, 0, end_bit, st));
+  }
+  // 5. tile ranges + packed sorted record streams
+  GS_CUDA_TRY(gs_launch_pack_sorted(c->keys_out.as<uint64_t>(), c->vals_out.as<uint32_t>(), m, g.n_tiles, g.ntx,
+                                    c->gA.as<float4>(), c->gB.as<float2>(), c->gC.as<float4>(),
+                                    c->rect.as<ushort4>(), c->offsets.as<uint32_t>(), c->pA.as<float4>(),
+                                    c->pB.as<float2>(), c->pC.as<float4>(), c->tile_accum.as<int>(), st));
+  // 6. blend
+  GS_CUDA_TRY(gs_launch_blend_fwd(c->pA.as<float4>(), c->pB.as<float2>(), c->pC.as<float4>(), c->tile_accum.as<int>(),
+                                  g, image, c->tile_neff.as<int>(), st));
+
+  c->have_forward = true;
+  c->n = n;
+  c->d = d;
+  c->scale_act = scale_activation;
+  c->m = m;
+  c->cam = dc;
+  c->grid = grid;
+  c->geom = g;
+  c->near_plane = cam->near_plane;
+  c->half_w = half_w;
+  c->half_h = half_h;
+  return 0;
+}
+
+extern "C" int gs_render_backward(gs_ctx* c, const float* pos, const float* rgb, const float* opa, const float* quat,
+                                  const float* scale, const float* image, const float* grad_image, float* grad_pos,
+                                  float* grad_rgb, float* grad_opa, float* grad_quat, float* grad_scale,
+                                  gs_stream_t stream) {
+  if (!c) return gs_set_error_msg(GS_ERR_INVALID_ARG, "gs_render_backward: null ctx");
+  if (!c->have_forward) return gs_set_error_msg(GS_ERR_NO_FORWARD, "gs_render_backward: no forward on this ctx");
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t M = (size_t)c->m;
+  GS_CUDA_TRY(c->grad_inst.reserve(M * GS_GREC * 4 + 16, st));
+  if (c->m > 0)
+    GS_CUDA_TRY(gs_launch_blend_bwd(c->pA.as<float4>(), c->pB.as<float2>(), c->pC.as<float4>(),
+                                    c->tile_accum.as<int>(), c->geom, image, grad_image, c->grad_inst.as<float>(),
+                                    st));
+  GS_CUDA_TRY(gs_launch_fused_project_bwd(pos, rgb, opa, quat, scale, c->n, c->scale_act, c->cam, c->near_plane,
+                                          c->half_w, c->half_h, c->offsets.as<uint32_t>(), c->grad_inst.as<float>(),
+                                          grad_pos, grad_rgb, grad_opa, grad_quat, grad_scale, st));
+  return 0;
+}
+
+extern "C" int gs_frame_stats(gs_ctx* c, gs_frame_info* out, gs_stream_t stream) {
+  if (!c || !out) return gs_set_error_msg(GS_ERR_INVALID_ARG, "gs_frame_stats: null argument");
+  if (!c->have_forward) return gs_set_error_msg(GS_ERR_NO_FORWARD, "gs_frame_stats: no forward on this ctx");
+  cudaStream_t st = (cudaStream_t)stream;
+  int T = c->geom.n_tiles;
+  int* h = static_cast<int*>(malloc(sizeof(int) * (size_t)(2 * T + 1)));
+  if (!h) return gs_set_error_msg(GS_ERR_INVALID_ARG, "gs_frame_stats: out of host memory");
+  unsigned int nvis = 0;
+  cudaError_t e = cudaMemcpyAsync(h, c->tile_accum.p, sizeof(int) * (size_t)(T + 1), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(h + T + 1, c->tile_neff.p, sizeof(int) * (size_t)T, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&nvis, c->counters.p, 4, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) {
+    free(h);
+    return gs_set_error(e, "gs_frame_stats copy");
+  }
+  long long meff = 0;
+  int mx = 0;
+  for (int t = 0; t < T; ++t) {
+    int cnt = h[t + 1] - h[t];
+    if (cnt > mx) mx = cnt;
+    meff += h[T + 1 + t];
+  }
+  free(h);
+  out->n_gaussians = c->n;
+  out->n_visible = (int)nvis;
+  out->n_instances = c->m;
+  out->n_instances_eff = meff;
+  out->width_padded = c->geom.wp;
+  out->height_padded = c->geom.hp;
+  out->n_tiles = T;
+  out->max_tile_count = mx;
+  return 0;
+}
+
+extern "C" int gs_frame_sorted(gs_ctx* c, int* gauss_idx, long long capacity, int* tile_accum, gs_stream_t stream) {
+  if (!c) return gs_set_error_msg(GS_ERR_INVALID_ARG, "gs_frame_sorted: null ctx");
+  if (!c->have_forward) return gs_set_error_msg(GS_ERR_NO_FORWARD, "gs_frame_sorted: no forward on this ctx");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (gauss_idx && c->m > 0) {
+    long long k = capacity < c->m ? capacity : c->m;
+    if (k > 0)
+      GS_CUDA_TRY(cudaMemcpyAsync(gauss_idx, c->vals_out.p, sizeof(int) * (size_t)k, cudaMemcpyDeviceToDevice, st));
+  }
+  if (tile_accum)
+    GS_CUDA_TRY(cudaMemcpyAsync(tile_accum, c->tile_accum.p, sizeof(int) * (size_t)(c->geom.n_tiles + 1),
+                                cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+extern "C" int gs_render_forward_backward_host(gs_ctx* c, const float* pos, const float* rgb, const float* opa,
+                                               const float* quat, const float* scale, int n, int d,
+                                               int scale_activation, const gs_camera* cam,
+                                               const float* grad_image_host, float* image_host, float* grad_pos,
+                                               float* grad_rgb, float* grad_opa, float* grad_quat, float* grad_scale,
+                                               gs_stream_t stream) {
+  if (!c || !cam) return gs_set_error_msg(GS_ERR_INVALID_ARG, "gs_render_forward_backward_host: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  int wp = (cam->width + GS_TILE - 1) / GS_TILE * GS_TILE, hp = (cam->height + GS_TILE - 1) / GS_TILE * GS_TILE;
+  size_t img_bytes = (size_t)wp * hp * 3 * sizeof(float);
+  DevBuf& img_dev = c->img_dev;
+  DevBuf& gimg_dev = c->gimg_dev;
+  GS_CUDA_TRY(img_dev.reserve(img_bytes, st));
+  GS_CUDA_TRY(gimg_dev.reserve(img_bytes, st));
+  GS_CUDA_TRY(cudaMemcpyAsync(gimg_dev.p, grad_image_host, img_bytes, cudaMemcpyHostToDevice, st));
+  int rc = gs_render_forward(c, pos, rgb, opa, quat, scale, n, d, scale_activation, cam, img_dev.as<float>(), nullptr,
+                             stream);
+  if (rc) return rc;
+  rc = gs_render_backward(c, pos, rgb, opa, quat, scale, img_dev.as<float>(), gimg_dev.as<float>(), grad_pos, grad_rgb,
+                          grad_opa, grad_quat, grad_scale, stream);
+  if (rc) return rc;
+  GS_CUDA_TRY(cudaMemcpyAsync(image_host, img_dev.p, img_bytes, cudaMemcpyDeviceToHost, st));
+  GS_CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}

@@ -1,0 +1,168 @@
+"""Autograd operator boundary — host-side mirror of the reference's renderer.py.
+
+Same public names, positional argument order, return values and zero-fill/ownership
+conventions as reference renderer.py (`draw` :89, `trunc_exp` :102,
+`world2camera_func` :119, `global_culling` :158), so code written against the
+reference keeps working; underneath, every op calls the sm_100a kernels of
+libgs_b200 through the `gaussian` extension in this directory.  Additive:
+`render_frame`, one autograd node for the whole frame (fused path).
+
+The product path never falls back to PyTorch/CPU math: importing this module
+without the built extension raises.
+"""
+from __future__ import annotations
+
+import torch
+
+try:
+    import gaussian
+except ImportError as e:  # pragma: no cover - fail loudly, never fall back
+    raise ImportError(
+        "the `gaussian` CUDA extension is not built; run "
+        "`python 3d-gaussian-splatting_b200/build.py` (needs nvcc, sm_100a)") from e
+
+
+def _f32(t):
+    return t.contiguous() if t.dtype == torch.float32 else t.float().contiguous()
+
+
+class _Drawer(torch.autograd.Function):
+    """Tile blend of sorted per-instance tensors (reference renderer.py:6-87)."""
+
+    @staticmethod
+    def forward(ctx, gaussians_pos, gaussians_rgb, gaussians_opa, gaussians_cov, tile_n_point_accum,
+                padded_height, padded_width, focal_x, focal_y, render_weight_normalize=False,
+                sigmoid=False, use_sh_coeff=False, fast=False, rays_o=None, lefttop_pos=None,
+                vec_dx=None, vec_dy=None):
+        pos, rgb, opa, cov = (_f32(gaussians_pos), _f32(gaussians_rgb), _f32(gaussians_opa), _f32(gaussians_cov))
+        accum = tile_n_point_accum.contiguous()
+        image = torch.empty(padded_height, padded_width, 3, device=pos.device, dtype=torch.float32)
+        dummy = pos.new_zeros(3)
+        rays = [dummy if r is None else _f32(r) for r in (rays_o, lefttop_pos, vec_dx, vec_dy)]
+        gaussian.draw(pos, rgb, opa, cov, accum, image, focal_x, focal_y, render_weight_normalize, sigmoid,
+                      fast, rays[0], rays[1], rays[2], rays[3], use_sh_coeff)
+        ctx.save_for_backward(pos, rgb, opa, cov, accum, image, *rays)
+        ctx.cfg = (focal_x, focal_y, render_weight_normalize, sigmoid, fast, use_sh_coeff)
+        return image
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        pos, rgb, opa, cov, accum, image, rays_o, lefttop_pos, vec_dx, vec_dy = ctx.saved_tensors
+        focal_x, focal_y, weight_normalize, sigmoid, fast, use_sh_coeff = ctx.cfg
+        g_pos = torch.zeros_like(pos)          # z column stays 0 (depth is only a sort key)
+        g_rgb = torch.empty_like(rgb)
+        g_opa = torch.empty_like(opa)
+        g_cov = torch.empty_like(cov)
+        gaussian.draw_backward(pos, rgb, opa, cov, accum, image, _f32(grad_output), g_pos, g_rgb, g_opa, g_cov,
+                               focal_x, focal_y, weight_normalize, sigmoid, fast, rays_o, lefttop_pos, vec_dx,
+                               vec_dy, use_sh_coeff)
+        return (g_pos, g_rgb, g_opa, g_cov) + (None,) * 13
+
+
+draw = _Drawer.apply
+
+
+class _trunc_exp(torch.autograd.Function):
+    """exp with a clamped-gradient backward (reference renderer.py:91-100)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        return torch.exp(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        return g * torch.exp(x.clamp(-1, 1))
+
+
+trunc_exp = _trunc_exp.apply
+
+
+class _world2camera(torch.autograd.Function):
+    """p @ R^T + t and its adjoint (reference renderer.py:104-117; deprecated path)."""
+
+    @staticmethod
+    def forward(ctx, pos, rot, tran):
+        pos, rot, tran = _f32(pos), _f32(rot), _f32(tran)
+        ctx.save_for_backward(rot)
+        res = torch.empty_like(pos)
+        gaussian.world2camera(pos, rot, tran, res)
+        return res
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (rot,) = ctx.saved_tensors
+        grad_out = _f32(grad_out)
+        grad_inp = torch.empty_like(grad_out)
+        gaussian.world2camera_backward(grad_out, rot, grad_inp)
+        return grad_inp, None, None
+
+
+world2camera_func = _world2camera.apply
+
+
+class _GlobalCulling(torch.autograd.Function):
+    """Projection + near/frustum cull + 2-D covariance (reference renderer.py:121-156)."""
+
+    @staticmethod
+    def forward(ctx, pos, quat, scale, current_rot, current_tran, near, half_width, half_height):
+        pos, quat, scale = _f32(pos), _f32(quat), _f32(scale)
+        rot, tran = _f32(current_rot), _f32(current_tran)
+        n = pos.shape[0]
+        res_pos = torch.zeros_like(pos)                       # culled rows must read 0
+        res_cov = torch.zeros((n, 2, 2), device=pos.device, dtype=torch.float32)
+        culling_mask = torch.zeros(n, dtype=torch.long, device=pos.device)
+        gaussian.global_culling(pos, quat, scale, rot, tran, res_pos, res_cov, culling_mask,
+                                near, half_width, half_height)
+        ctx.save_for_backward(culling_mask, pos, quat, scale, rot, tran)
+        ctx.mark_non_differentiable(culling_mask)
+        return res_pos, res_cov, culling_mask
+
+    @staticmethod
+    def backward(ctx, gradout_pos, gradout_cov, _grad_mask):
+        culling_mask, pos, quat, scale, rot, tran = ctx.saved_tensors
+        g_pos = torch.zeros_like(pos)
+        g_quat = torch.zeros_like(quat)
+        g_scale = torch.zeros_like(scale)
+        gaussian.global_culling_backward(pos, quat, scale, rot, tran, _f32(gradout_pos), _f32(gradout_cov),
+                                         culling_mask, g_pos, g_quat, g_scale)
+        return g_pos, g_quat, g_scale, None, None, None, None, None
+
+
+global_culling = _GlobalCulling.apply
+
+
+# ----------------------------------------------------------------------------------------
+# additive: the whole frame as one autograd node (fused path)
+# ----------------------------------------------------------------------------------------
+SCALE_ACTIVATIONS = {"abs": 0, "exp": 1}
+
+
+class _RenderFrame(torch.autograd.Function):
+    """raw parameters -> padded un-clamped image, replacing splatter.py:513-634's glue.
+
+    `rctx` is a `gaussian.RenderContext` (owns device workspaces; holds the state of
+    the latest forward, so backward must run before the next forward on the same ctx).
+    """
+
+    @staticmethod
+    def forward(ctx, rctx, pos, rgb, opa, quat, scale, width, height, focal_x, focal_y, rot, tran,
+                near, tile_thresh, scale_activation):
+        pos, rgb, opa, quat, scale = (_f32(t.detach()) for t in (pos, rgb, opa, quat, scale))
+        image, mask = rctx.forward(pos, rgb, opa, quat, scale, int(width), int(height), float(focal_x),
+                                   float(focal_y), rot.detach().cpu(), tran.detach().cpu(), float(near),
+                                   float(tile_thresh), SCALE_ACTIVATIONS[scale_activation])
+        ctx.rctx = rctx
+        ctx.save_for_backward(pos, rgb, opa, quat, scale, image)
+        ctx.mark_non_differentiable(mask)
+        return image, mask
+
+    @staticmethod
+    def backward(ctx, grad_image, _grad_mask):
+        pos, rgb, opa, quat, scale, image = ctx.saved_tensors
+        g = ctx.rctx.backward(pos, rgb, opa, quat, scale, image, _f32(grad_image))
+        return (None, g[0], g[1], g[2], g[3], g[4]) + (None,) * 9
+
+
+render_frame = _RenderFrame.apply

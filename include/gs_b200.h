@@ -1,0 +1,177 @@
+/*
+ * gs_b200.h — C ABI of libgs_b200.so: B200-native (sm_100a) differentiable tile rasterizer.
+ *
+ * This is the drop-in boundary for the hot path of WangFeng18/3d-gaussian-splatting
+ * (projection + 3D->2D covariance, (tile|depth) sort, front-to-back alpha blend, and the
+ * backward of all of it).  The reference exposes that path as a torch/pybind11 module
+ * named `gaussian` (reference src/bindings.cpp:21-50); our pybind shim
+ * (3d-gaussian-splatting_b200/csrc/bindings.cpp) keeps that Python-visible surface and
+ * forwards every call to the functions below.  Everything here is plain C:
+ *   - raw DEVICE pointers (unless a name ends in `_host`), explicit sizes,
+ *   - a trailing `gs_stream_t` (a `cudaStream_t`; NULL = legacy default stream),
+ *   - return value: 0 on success, otherwise a `cudaError_t` code (or GS_ERR_* < 0),
+ *   - no function allocates or synchronises unless its comment says so.
+ * All tensors are dense row-major float32 unless stated; indices int32; mask int64.
+ */
+#ifndef GS_B200_H
+#define GS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* gs_stream_t; /* cudaStream_t */
+
+#define GS_ERR_INVALID_ARG (-1)
+#define GS_ERR_UNSUPPORTED (-2)
+#define GS_ERR_NO_FORWARD (-3)
+
+/* ABI version of this header (bumped on any signature change). */
+int gs_abi_version(void);
+/* Human-readable text of the last error on this host thread ("" if none). */
+const char* gs_last_error(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Legacy per-stage entry points == the reference's `gaussian` module functions.
+ * ------------------------------------------------------------------------------------- */
+
+/* global_culling — reference bindings.cpp:48, gaussian.cu:1338-1369 (kernel :1182-1336).
+ * quat/scale are PRE-activated (splatter.py:519-524).  res_pos[n,3]=(x/z,y/z,|p_c|),
+ * res_cov[n,2,2], mask[n] int64; outputs must be zero-filled by the caller (culled rows
+ * are left untouched, like the reference). */
+int gs_project_fwd(const float* pos, const float* quat, const float* scale, const float* rot,
+                   const float* tran, int n, float near_plane, float half_width, float half_height,
+                   float* res_pos, float* res_cov, int64_t* mask, gs_stream_t stream);
+
+/* global_culling_backward — bindings.cpp:49, gaussian.cu:1578-1609 (kernel :1371-1576).
+ * The projection Jacobian is treated as constant (no d cov2d / d pos), as in the reference. */
+int gs_project_bwd(const float* pos, const float* quat, const float* scale, const float* rot,
+                   const float* tran, const float* gradout_pos, const float* gradout_cov,
+                   const int64_t* mask, int n, float* gradin_pos, float* gradin_quat,
+                   float* gradin_scale, gs_stream_t stream);
+
+/* calc_tile_list — bindings.cpp:44, gaussian.cu:254-335.  method 0 "dist" (:101-136),
+ * 1 "prob" (:138-195), 2 "prob2" (:197-250).  tile_top/bottom/left/right[n_tiles] are only
+ * read by methods 0/1.  tile_n_point[T] is incremented (may exceed max_per_tile; entries
+ * beyond capacity are dropped, caller clamps — splatter.py:586). */
+int gs_tile_list(const float* pos /*[n,3]*/, const float* cov /*[n,4]*/, int n,
+                 const float* tile_top, const float* tile_bottom, const float* tile_left,
+                 const float* tile_right, int n_tiles, int* tile_n_point, int* tile_gaussian_list,
+                 int max_per_tile, float thresh, int method, float tile_length_x, float tile_length_y,
+                 int n_tiles_x, int n_tiles_y, float leftmost, float topmost, gs_stream_t stream);
+
+/* gather_gaussians — bindings.cpp:45, gaussian.cu:359-381. */
+int gs_gather(const int* tile_n_point_accum /*[T+1]*/, const int* tile_gaussian_list /*[T,list_stride]*/,
+              int n_tiles, int list_stride, int max_points_for_tile, int* gathered_list /*[M]*/,
+              int* tile_ids_for_points /*[M]*/, gs_stream_t stream);
+
+/* Scratch bytes needed by gs_draw_fwd / gs_draw_bwd for m tile-instances with colour width
+ * d (3 = RGB, 27 = SH degree 2). */
+size_t gs_draw_workspace_bytes(int m, int d);
+
+/* draw — bindings.cpp:46, gaussian.cu:973-1043 (kernel :806-970).  Inputs are the already
+ * (tile, depth)-sorted per-instance tensors pos[m,3], rgb[m,d], opa[m], cov[m,2,2] and
+ * tile_n_point_accum[T+1]; image[Hp,Wp,3] is fully overwritten.  d = 3 or 27
+ * (use_sh_coeff).  `weight_normalize` / `sigmoid` must be 0 (GS_ERR_UNSUPPORTED
+ * otherwise: the reference never enables them, splatter.py:627, train.py:377).
+ * rays_o/lefttop/vec_dx/vec_dy[3] are only read when d == 27 (splatter.py:305-321). */
+int gs_draw_fwd(const float* pos, const float* rgb, const float* opa, const float* cov,
+                const int* tile_n_point_accum, int m, int d, int width_padded, int height_padded,
+                float focal_x, float focal_y, int weight_normalize, int sigmoid,
+                const float* rays_o, const float* lefttop, const float* vec_dx, const float* vec_dy,
+                float* image, void* workspace, size_t workspace_bytes, gs_stream_t stream);
+
+/* draw_backward — bindings.cpp:47, gaussian.cu:1045-1129 (kernel :440-803).
+ * grad_pos[m,3] (z column untouched), grad_rgb[m,d], grad_opa[m], grad_cov[m,2,2] receive the
+ * per-instance gradients (every row of the listed columns is written). */
+int gs_draw_bwd(const float* pos, const float* rgb, const float* opa, const float* cov,
+                const int* tile_n_point_accum, int m, int d, int width_padded, int height_padded,
+                float focal_x, float focal_y, int weight_normalize, int sigmoid,
+                const float* rays_o, const float* lefttop, const float* vec_dx, const float* vec_dy,
+                const float* image, const float* grad_image,
+                float* grad_pos, float* grad_rgb, float* grad_opa, float* grad_cov,
+                void* workspace, size_t workspace_bytes, gs_stream_t stream);
+
+/* world2camera / world2camera_backward / jacobian — bindings.cpp:24-26,
+ * gaussian.cu:71-76, :95-99, :41-47 (deprecated cudaculling=0 path). */
+int gs_w2c_fwd(const float* pos, const float* rot, const float* tran, int n, float* res, gs_stream_t stream);
+int gs_w2c_bwd(const float* grad_out, const float* rot, int n, float* grad_in, gs_stream_t stream);
+int gs_jacobian(const float* pos_cam, int n, float* jac /*[n,3,3]*/, gs_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Fused frame path (additive; replaces the PyTorch glue of splatter.py:513-655 and the
+ * autograd glue around it): parameters -> image, grad_image -> parameter gradients.
+ * ------------------------------------------------------------------------------------- */
+
+typedef struct gs_ctx gs_ctx; /* owns device workspaces; one per (device, in-flight frame) */
+
+typedef struct gs_camera {
+  int width, height;          /* un-padded image size; render target is padded to x16 */
+  float focal_x, focal_y;     /* principal point = image centre (splatter.py:499-500)  */
+  float rot[9];               /* world->camera rotation, row-major                      */
+  float tran[3];
+  float near_plane;           /* splatter.py: near=0.3                                   */
+  float tile_thresh;          /* bbox probability threshold, train.py:310 (0.05)         */
+} gs_camera;
+
+typedef struct gs_frame_info {
+  int n_gaussians;            /* N                                                       */
+  int n_visible;              /* Nc: passed near + 1.2x frustum cull                     */
+  long long n_instances;      /* M : tile-instances binned                               */
+  long long n_instances_eff;  /* M_eff: instances actually consumed before every pixel   */
+                              /*        of their tile saturated (filled by forward)      */
+  int width_padded, height_padded, n_tiles;
+  int max_tile_count;
+} gs_frame_info;
+
+/* scale_activation: 0 = abs()+1e-4 (splatter.py:521), 1 = trunc_exp (splatter.py:524). */
+#define GS_SCALE_ABS 0
+#define GS_SCALE_EXP 1
+
+int gs_ctx_create(gs_ctx** out);           /* binds to the current CUDA device            */
+void gs_ctx_destroy(gs_ctx* ctx);          /* frees workspaces (synchronises the device)  */
+
+/* Raw parameters (splatter.py:399-406): pos[n,3], rgb[n,d] (logits if d==3, SH coefficients
+ * channel-major [c*K+k] if d==27), opa[n] logits, quat[n,4] wxyz un-normalised, scale[n,3]
+ * raw.  Writes image[Hp,Wp,3] (un-clamped, padded; black background) and, if non-NULL,
+ * culling_mask[n] int64 (train.py:150).  Performs ONE host synchronisation on `stream`
+ * (reads back the instance count M to size the sort). */
+int gs_render_forward(gs_ctx* ctx, const float* pos, const float* rgb, const float* opa,
+                      const float* quat, const float* scale, int n, int d, int scale_activation,
+                      const gs_camera* cam_host, float* image, int64_t* culling_mask,
+                      gs_stream_t stream);
+
+/* Backward of the most recent gs_render_forward on `ctx` (same parameter pointers).
+ * grad_image[Hp,Wp,3]; `image` is the forward output.  Writes (overwrites, all n rows)
+ * grad_pos[n,3], grad_rgb[n,d], grad_opa[n], grad_quat[n,4], grad_scale[n,3]:
+ * gradients wrt the RAW parameters (activation backward included).  No synchronisation. */
+int gs_render_backward(gs_ctx* ctx, const float* pos, const float* rgb, const float* opa,
+                       const float* quat, const float* scale, const float* image,
+                       const float* grad_image, float* grad_pos, float* grad_rgb, float* grad_opa,
+                       float* grad_quat, float* grad_scale, gs_stream_t stream);
+
+/* Statistics of the last forward on ctx (host struct; synchronises `stream` for M_eff). */
+int gs_frame_stats(gs_ctx* ctx, gs_frame_info* out_host, gs_stream_t stream);
+
+/* Exposes the last frame's sorted instance list for parity tests: copies
+ * min(capacity, M) entries of the sorted Gaussian ids into gauss_idx (device int32) and
+ * T+1 entries into tile_accum (device int32).  Either pointer may be NULL. */
+int gs_frame_sorted(gs_ctx* ctx, int* gauss_idx, long long capacity, int* tile_accum, gs_stream_t stream);
+
+/* End-to-end convenience with HOST buffers (bench `e2e` leg and plain-C callers): copies
+ * the camera + grad_image from host, runs forward + backward on device-resident parameters,
+ * copies the padded image back.  Host buffers should be pinned.  Synchronises. */
+int gs_render_forward_backward_host(gs_ctx* ctx, const float* pos, const float* rgb, const float* opa,
+                                    const float* quat, const float* scale, int n, int d,
+                                    int scale_activation, const gs_camera* cam_host,
+                                    const float* grad_image_host, float* image_host,
+                                    float* grad_pos, float* grad_rgb, float* grad_opa,
+                                    float* grad_quat, float* grad_scale, gs_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GS_B200_H */
