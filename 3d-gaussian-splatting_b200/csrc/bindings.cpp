@@ -10,6 +10,7 @@
 #include <torch/extension.h>
 
 #include <string>
+#include <vector>
 
 #include "../../include/gs_b200.h"
 
@@ -283,6 +284,13 @@ struct RenderContext {
     return {g_pos, g_rgb, g_opa, g_quat, g_scale};
   }
 
+  void set_timing(bool on) { check_rc(gs_ctx_set_timing(ctx, on ? 1 : 0), "gs_ctx_set_timing"); }
+  std::vector<float> stage_ms() {
+    std::vector<float> v(GS_N_STAGES, -1.f);
+    check_rc(gs_frame_stage_ms(ctx, v.data(), cur_stream()), "gs_frame_stage_ms");
+    return v;
+  }
+
   py::dict stats() {
     gs_frame_info fi{};
     check_rc(gs_frame_stats(ctx, &fi, cur_stream()), "gs_frame_stats");
@@ -349,6 +357,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def("forward", &RenderContext::forward)
       .def("backward", &RenderContext::backward)
       .def("stats", &RenderContext::stats)
+      .def("set_timing", &RenderContext::set_timing)
+      .def("stage_ms", &RenderContext::stage_ms)
       .def("sorted_instances", &RenderContext::sorted_instances);
   m.attr("abi_version") = gs_abi_version();
 }

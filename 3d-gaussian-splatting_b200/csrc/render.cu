@@ -74,7 +74,19 @@ struct gs_ctx {
   GsFrameGeom geom{};
   float near_plane = 0.f, half_w = 0.f, half_h = 0.f;
   int64_t* mask_ptr = nullptr;
+  // optional per-stage timing (CUDA events on the frame's stream)
+  bool timing = false;
+  cudaEvent_t ev[GS_N_STAGES + 2] = {};
+  bool ev_ok = false;
+  bool ev_fwd_valid = false, ev_bwd_valid = false;
 };
+
+// stage boundaries: event i is recorded BEFORE stage i; stage i lasts ev[i+1]-ev[i]
+//  forward : 0 project | 1 scan+readback | 2 emit keys | 3 radix sort | 4 pack | 5 blend fwd | (6 end)
+//  backward: 7 blend bwd | 8 project bwd | (9 end)
+static inline void gs_mark(gs_ctx* c, int i, cudaStream_t st) {
+  if (c->timing && c->ev_ok) cudaEventRecord(c->ev[i], st);
+}
 
 extern "C" int gs_ctx_create(gs_ctx** out) {
   if (!out) return gs_set_error_msg(GS_ERR_INVALID_ARG, "gs_ctx_create: null out");
@@ -98,6 +110,8 @@ extern "C" void gs_ctx_destroy(gs_ctx* c) {
                     &c->cub_tmp, &c->counters, &c->img_dev, &c->gimg_dev};
   for (DevBuf* b : bufs) b->release();
   if (c->host_m) cudaFreeHost(c->host_m);
+  if (c->ev_ok)
+    for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
   delete c;
 }
 
@@ -158,6 +172,8 @@ extern "C" int gs_render_forward(gs_ctx* c, const float* pos, const float* rgb, 
   GS_CUDA_TRY(c->counters.reserve(64, st));
 
   // 1. projection + activations + tile rectangle
+  c->ev_fwd_valid = false;
+  gs_mark(c, 0, st);
   GS_CUDA_TRY(cudaMemsetAsync(c->counters.p, 0, 64, st));
   GS_CUDA_TRY(cudaMemsetAsync(c->count.as<uint32_t>() + N, 0, 4, st));
   GS_CUDA_TRY(gs_launch_fused_project(pos, rgb, opa, quat, scale, n, scale_activation, dc, grid, cam->near_plane,
@@ -165,6 +181,7 @@ extern "C" int gs_render_forward(gs_ctx* c, const float* pos, const float* rgb, 
                                       c->rect.as<ushort4>(), c->depth.as<float>(), c->count.as<uint32_t>(),
                                       culling_mask, c->counters.as<unsigned int>(), st));
   // 2. exclusive scan of the per-Gaussian tile counts (N+1 items: offsets[N] = M)
+  gs_mark(c, 1, st);
   size_t scan_tmp = 0;
   GS_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp, c->count.as<uint32_t>(), c->offsets.as<uint32_t>(),
                                             n + 1, st));
@@ -179,6 +196,7 @@ extern "C" int gs_render_forward(gs_ctx* c, const float* pos, const float* rgb, 
   if (m >= (1ll << 31)) return gs_set_error_msg(GS_ERR_UNSUPPORTED, "gs_render_forward: more than 2^31 tile instances");
   size_t M = (size_t)m;
 
+  gs_mark(c, 2, st);
   GS_CUDA_TRY(c->pA.reserve(M * 16 + 16, st));
   GS_CUDA_TRY(c->pC.reserve(M * 16 + 16, st));
   GS_CUDA_TRY(c->pB.reserve((M + 2) * 8, st));
@@ -191,6 +209,7 @@ extern "C" int gs_render_forward(gs_ctx* c, const float* pos, const float* rgb, 
     GS_CUDA_TRY(gs_launch_emit_keys(c->rect.as<ushort4>(), c->depth.as<float>(), c->offsets.as<uint32_t>(), n, g.ntx,
                                     c->keys_in.as<uint64_t>(), c->vals_in.as<uint32_t>(), st));
     // 4. (tile | depth) radix sort — only the significant key bits
+    gs_mark(c, 3, st);
     int end_bit = 32 + ceil_log2((unsigned)g.n_tiles);
     if (end_bit < 33) end_bit = 33;
     size_t sort_tmp = 0;
@@ -203,13 +222,18 @@ extern "C" int gs_render_forward(gs_ctx* c, const float* pos, const float* rgb, 
                                                 c->vals_out.as<uint32_t>(), (int)m, 0, end_bit, st));
   }
   // 5. tile ranges + packed sorted record streams
+  if (m == 0) gs_mark(c, 3, st);
+  gs_mark(c, 4, st);
   GS_CUDA_TRY(gs_launch_pack_sorted(c->keys_out.as<uint64_t>(), c->vals_out.as<uint32_t>(), m, g.n_tiles, g.ntx,
                                     c->gA.as<float4>(), c->gB.as<float2>(), c->gC.as<float4>(),
                                     c->rect.as<ushort4>(), c->offsets.as<uint32_t>(), c->pA.as<float4>(),
                                     c->pB.as<float2>(), c->pC.as<float4>(), c->tile_accum.as<int>(), st));
   // 6. blend
+  gs_mark(c, 5, st);
   GS_CUDA_TRY(gs_launch_blend_fwd(c->pA.as<float4>(), c->pB.as<float2>(), c->pC.as<float4>(), c->tile_accum.as<int>(),
                                   g, image, c->tile_neff.as<int>(), st));
+  gs_mark(c, 6, st);
+  c->ev_fwd_valid = c->timing && c->ev_ok;
 
   c->have_forward = true;
   c->n = n;
@@ -234,13 +258,18 @@ extern "C" int gs_render_backward(gs_ctx* c, const float* pos, const float* rgb,
   cudaStream_t st = (cudaStream_t)stream;
   size_t M = (size_t)c->m;
   GS_CUDA_TRY(c->grad_inst.reserve(M * GS_GREC * 4 + 16, st));
+  c->ev_bwd_valid = false;
+  gs_mark(c, 7, st);
   if (c->m > 0)
     GS_CUDA_TRY(gs_launch_blend_bwd(c->pA.as<float4>(), c->pB.as<float2>(), c->pC.as<float4>(),
                                     c->tile_accum.as<int>(), c->geom, image, grad_image, c->grad_inst.as<float>(),
                                     st));
+  gs_mark(c, 8, st);
   GS_CUDA_TRY(gs_launch_fused_project_bwd(pos, rgb, opa, quat, scale, c->n, c->scale_act, c->cam, c->near_plane,
                                           c->half_w, c->half_h, c->offsets.as<uint32_t>(), c->grad_inst.as<float>(),
                                           grad_pos, grad_rgb, grad_opa, grad_quat, grad_scale, st));
+  gs_mark(c, 9, st);
+  c->ev_bwd_valid = c->timing && c->ev_ok;
   return 0;
 }
 
@@ -318,5 +347,28 @@ extern "C" int gs_render_forward_backward_host(gs_ctx* c, const float* pos, cons
   if (rc) return rc;
   GS_CUDA_TRY(cudaMemcpyAsync(image_host, img_dev.p, img_bytes, cudaMemcpyDeviceToHost, st));
   GS_CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" int gs_ctx_set_timing(gs_ctx* c, int enable) {
+  if (!c) return gs_set_error_msg(GS_ERR_INVALID_ARG, "gs_ctx_set_timing: null ctx");
+  if (enable && !c->ev_ok) {
+    for (cudaEvent_t& e : c->ev) GS_CUDA_TRY(cudaEventCreate(&e));
+    c->ev_ok = true;
+  }
+  c->timing = enable != 0;
+  c->ev_fwd_valid = c->ev_bwd_valid = false;
+  return 0;
+}
+
+extern "C" int gs_frame_stage_ms(gs_ctx* c, float* out, gs_stream_t stream) {
+  if (!c || !out) return gs_set_error_msg(GS_ERR_INVALID_ARG, "gs_frame_stage_ms: null argument");
+  for (int i = 0; i < GS_N_STAGES; ++i) out[i] = -1.f;
+  if (!c->ev_ok) return 0;
+  GS_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  if (c->ev_fwd_valid)
+    for (int i = 0; i < 6; ++i) GS_CUDA_TRY(cudaEventElapsedTime(&out[i], c->ev[i], c->ev[i + 1]));
+  if (c->ev_bwd_valid)
+    for (int i = 6; i < 8; ++i) GS_CUDA_TRY(cudaEventElapsedTime(&out[i], c->ev[i + 1], c->ev[i + 2]));
   return 0;
 }

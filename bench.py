@@ -1,0 +1,404 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: render + backward FPS at 1080p, 2.4M Gaussians.
+
+  python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload C2|C3|C5]
+
+One "step" = one forward + backward of one 1920x1080 view per GPU: raw parameters ->
+image -> gradients of all five parameter tensors for a fixed upstream image gradient
+(SURVEY.md §8d FPS_fb; no loss / optimizer inside), followed at N > 1 by the NCCL
+all-reduce of the gradient bucket (views are sharded one per GPU, Gaussians replicated:
+weak scaling).  `value` = N views / max-over-ranks step time, inputs resident in HBM.
+`e2e`   = the same through the public `Splatter` API with the upstream gradient coming
+from pinned HOST memory and the rendered image read back to the host every step.
+
+--impl reference times the reference's own CUDA build (oracle/_ref: unmodified
+gaussian.cu + bindings.cpp + renderer.py) driven with the reference's per-frame call
+sequence (oracle/ref_pipeline.py) on the same scene, rank 0 only.  If oracle/_ref is
+absent it falls back to the CPU oracle port on a tile sub-sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in ("3d-gaussian-splatting_b200", "oracle"):
+    sys.path.insert(0, os.path.join(ROOT, _p))
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (N gaussians, width, height, forward_only)
+    "C2": (500_000, 1920, 1080, False),
+    "C3": (2_400_000, 1920, 1080, False),
+    "C5": (5_000_000, 3840, 2160, True),
+    "tiny": (20_000, 320, 192, False),
+}
+METRIC = "render+backward FPS @1080p (2.4M Gaussians)"
+
+
+# ------------------------------------------------------------------------------------------
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for nm, val in zip(names, r[3:7]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def dist_setup(n_gpus):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(0)
+    return world, rank, local
+
+
+def barrier(world):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(x, world, dev):
+    if world == 1:
+        return x
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def allreduce_grads(params, world):
+    """One NCCL all-reduce (SUM) over a single flat bucket of the five gradients."""
+    if world == 1:
+        return
+    import torch.distributed as dist
+    from torch._utils import _flatten_dense_tensors, _unflatten_dense_tensors
+    grads = [p.grad for p in params]
+    flat = _flatten_dense_tensors(grads)
+    dist.all_reduce(flat)
+    for g, f in zip(grads, _unflatten_dense_tensors(flat, grads)):
+        g.copy_(f)
+
+
+# ------------------------------------------------------------------------------------------
+def timed_loop(step_fn, steps, warmup, world, dev):
+    for _ in range(warmup):
+        step_fn()
+    barrier(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step_fn()
+    e1.record()
+    barrier(world)
+    ms = e0.elapsed_time(e1) / steps
+    return max_over_ranks(ms, world, dev)
+
+
+def cpu_baseline(workload, n_tiles_sample=48):
+    """The CPU oracle (pure PyTorch) on the box's host cores: full projection + binning +
+    exact sort of the frame, then blend forward + autograd backward on a tile sub-sample,
+    extrapolated to all tiles (labelled as such)."""
+    import gs_oracle as O
+    import synthetic as S
+    n, w, h, fwd_only = WORKLOADS[workload]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    v = S.make_view(w, h, 0)
+    g = S.make_gaussians(n, w, h, 0)
+    cam = O.Camera(w, h, v.fx, v.fy, v.rot, v.tran)
+    T = cam.ntx * cam.nty
+    tiles = torch.linspace(0, T - 1, n_tiles_sample).long()
+    go = S.make_grad_output(h, w, 0)
+    t0 = time.time()
+    p = {k: t.clone().requires_grad_(not fwd_only) for k, t in g.items()}
+    with torch.set_grad_enabled(not fwd_only):
+        img, aux = O.render(p["pos"], p["rgb"], p["opa"], p["quat"], p["scale"], cam, tiles=tiles, return_aux=True)
+        t_front_blend = time.time() - t0
+        if not fwd_only:
+            img.backward(go)
+    t_total = time.time() - t0
+    # split: the blend part scales with the number of tiles, the front end does not
+    t1 = time.time()
+    with torch.no_grad():
+        O.render(g["pos"], g["rgb"], g["opa"], g["quat"], g["scale"], cam, tiles=tiles[:1])
+    t_front = time.time() - t1                       # ~ projection + binning + sort (+1 tile)
+    t_blend = max(t_total - t_front, 1e-6)
+    est = t_front + t_blend * (T / n_tiles_sample)
+    return {"value": 1.0 / est, "unit": "frames/s", "cores": cores, "kind": "port",
+            "sample": f"{workload}: full projection+binning+sort of {n} gaussians, blend fwd"
+                      f"{'' if fwd_only else '+bwd'} on {n_tiles_sample}/{T} tiles, extrapolated "
+                      f"({t_front:.1f}s front end + {t_blend:.1f}s sampled blend)"}
+
+
+# ------------------------------------------------------------------------------------------
+def run_ours(args, world, rank, local):
+    import splatter
+    import synthetic as S
+    dev = torch.device("cuda", local)
+    n, w, h, fwd_only = WORKLOADS[args.workload]
+    g = S.make_gaussians(n, w, h, 0)
+    views = [S.make_view(w, h, k) for k in range(8)]
+    vd = [dict(width=v.width, height=v.height, focal_x=v.fx, focal_y=v.fy, rot=v.rot, tran=v.tran) for v in views]
+    sp = splatter.Splatter(g, vd, device=dev)
+    params = list(sp.gaussian_3ds.parameters())
+    view_id = rank % 8
+    go_host = S.make_grad_output(h, w, 0).pin_memory()
+    go_dev = go_host.to(dev)
+    sp._rctx.set_timing(True)
+
+    def step_resident():
+        for p in params:
+            p.grad = None
+        if fwd_only:
+            with torch.no_grad():
+                sp(view_id)
+        else:
+            img = sp(view_id)
+            img.backward(go_dev)
+            allreduce_grads(params, world)
+
+    ms = timed_loop(step_resident, args.steps, args.warmup, world, dev)
+
+    # clocks are sampled during a second identical timed region so that nvidia-smi polling
+    # cannot perturb the headline number
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_b = timed_loop(step_resident, args.steps, 0, world, dev)
+    clocks = sampler.stop() if rank == 0 else {}
+    ms = min(ms, ms_b)
+
+    # per-stage device times of the last frame (CUDA events on the launching stream)
+    stage = sp._rctx.stage_ms()
+    st = sp.frame_stats()
+
+    # ---- e2e: host buffers in the timed region -------------------------------------------
+    img_host = torch.empty(h, w, 3, dtype=torch.float32).pin_memory()
+    copy_stream = torch.cuda.Stream(device=dev)
+    go_stage = torch.empty_like(go_dev)
+
+    def step_e2e():
+        for p in params:
+            p.grad = None
+        main = torch.cuda.current_stream(dev)
+        with torch.cuda.stream(copy_stream):
+            go_stage.copy_(go_host, non_blocking=True)          # H2D: this step's upstream gradient
+            h2d_done = torch.cuda.Event()
+            h2d_done.record(copy_stream)
+        if fwd_only:
+            with torch.no_grad():
+                img = sp(view_id)
+        else:
+            img = sp(view_id)                                    # camera (48 B) goes host->device inside
+        fwd_done = torch.cuda.Event()
+        fwd_done.record(main)
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(fwd_done)
+            img_host.copy_(img.detach(), non_blocking=True)      # D2H: the rendered image
+        if not fwd_only:
+            main.wait_event(h2d_done)
+            img.backward(go_stage)
+            allreduce_grads(params, world)
+        copy_stream.synchronize()
+
+    ms_e2e = timed_loop(step_e2e, args.steps, max(1, args.warmup // 2), world, dev)
+
+    if rank != 0:
+        return None
+    M, Meff = int(st["n_instances"]), int(st["n_instances_eff"])
+    T = int(st["n_tiles"])
+    P = int(st["width_padded"]) * int(st["height_padded"])
+    D = 3
+    peak, peak_src = measured_peak_gbs()
+    bf = 4 * (7 + D) * Meff + 12 * P + 4 * (T + 1)
+    bb = 8 * (7 + D) * Meff + 24 * P + 4 * (T + 1)
+    blend_f_ms, blend_b_ms = stage[5], stage[6]
+    roof_kernel = "blend_bwd_kernel" if not fwd_only else "blend_fwd_kernel"
+    alg_bytes, k_ms = (bb, blend_b_ms) if not fwd_only else (bf, blend_f_ms)
+    achieved = alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms and k_ms > 0 else None
+    pairs = Meff * 256
+    out = {
+        "metric": METRIC if args.workload == "C3" else f"render{'' if fwd_only else '+backward'} FPS ({args.workload})",
+        "value": world * 1000.0 / ms, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {n} gaussians, {w}x{h}, RGB colour (D=3), "
+                               f"{'forward only' if fwd_only else 'forward+backward'}, one view per GPU "
+                               f"(view k = rank mod 8), seed 0 (SURVEY.md §8d generator)",
+                   "tile_instances_M": M, "tile_instances_consumed_M_eff": Meff, "max_tile_count": st["max_tile_count"],
+                   "n_visible": st["n_visible"], "l2": "inputs larger than L2 (per-frame working set "
+                                                       f"{(M * 112 + n * 56) / 1e6:.0f} MB >> 126 MB)",
+                   "parallelism": f"dp{world} over views, NCCL all-reduce of the gradient bucket"},
+        "clocks": clocks,
+        "e2e": {"value": world * 1000.0 / ms_e2e, "unit": "frames/s", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": int(go_host.numel() * 4 + 48), "d2h_bytes_per_step": int(img_host.numel() * 4),
+                "api": "Splatter.forward(camera_id) + image.backward(grad) with pinned host grad / image buffers"},
+        "gpu_launches": int((4 if fwd_only else 6) * args.steps),
+        "gpu_launches_note": "our kernels per step: fused_project, emit_keys, pack_sorted, blend_fwd"
+                             + ("" if fwd_only else ", blend_bwd, fused_project_bwd") +
+                             "; plus CUB scan (2) and onesweep radix sort (8) library kernels",
+        "stage_ms": dict(zip(["project", "scan+readback", "emit_keys", "radix_sort", "pack", "blend_fwd",
+                              "blend_bwd", "project_bwd"], [round(x, 4) for x in stage])),
+        "roofline": {"bound": "hbm", "kernel": roof_kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg_bytes,
+                     "note": "blend is FP32/MUFU-issue bound, not HBM bound (SURVEY.md §8d): "
+                             f"{pairs / 1e9:.2f} G pixel-instance pairs upper bound per launch",
+                     "blend_fwd": {"ms": blend_f_ms, "algorithmic_bytes": bf,
+                                   "achieved": bf / (blend_f_ms * 1e-3) / 1e9 if blend_f_ms > 0 else None},
+                     "blend_bwd": {"ms": blend_b_ms, "algorithmic_bytes": bb,
+                                   "achieved": bb / (blend_b_ms * 1e-3) / 1e9 if blend_b_ms > 0 else None}},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(args.workload)
+    return out
+
+
+def run_reference(args, world, rank, local):
+    """Reference arm: rank 0 only, one GPU (the reference has no multi-GPU path)."""
+    if rank != 0:
+        return None
+    import ref_pipeline
+    import synthetic as S
+    n, w, h, fwd_only = WORKLOADS[args.workload]
+    gref, rref = ref_pipeline.load_reference()
+    if gref is None:
+        cb = cpu_baseline(args.workload)
+        return {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "frames/s", "n_gpus": 1,
+                "steps": 1, "warmup": 0, "ms_per_step": 1000.0 / cb["value"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": args.workload, "note": "oracle/_ref absent: CPU oracle port"},
+                "cpu_baseline": cb,
+                "e2e": {"value": cb["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    dev = torch.device("cuda", local)
+    g = S.make_gaussians(n, w, h, 0)
+    v = S.make_view(w, h, 0)
+    frame = ref_pipeline.LegacyFrame(gref, rref, w, h, v.fx, v.fy, v.rot.to(dev), v.tran.to(dev))
+    p = {k: t.to(dev).clone().requires_grad_(True) for k, t in g.items()}
+    go = S.make_grad_output(h, w, 0).to(dev)
+
+    def step():
+        for t in p.values():
+            t.grad = None
+        if fwd_only:
+            with torch.no_grad():
+                frame(p["pos"], p["rgb"], p["opa"], p["quat"], p["scale"])
+        else:
+            img = frame(p["pos"], p["rgb"], p["opa"], p["quat"], p["scale"])
+            img.backward(go)
+
+    sampler = ClockSampler(local)
+    ms = timed_loop(step, args.steps, args.warmup, 1, dev)
+    sampler.start()
+    ms2 = timed_loop(step, args.steps, 0, 1, dev)
+    clocks = sampler.stop()
+    ms = min(ms, ms2)
+    fps = 1000.0 / ms
+    return {"impl": "reference", "metric": METRIC if args.workload == "C3" else f"FPS ({args.workload})",
+            "value": fps, "unit": "frames/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {n} gaussians, {w}x{h}, RGB, "
+                                   f"{'forward only' if fwd_only else 'forward+backward'}, view 0",
+                       "impl": "reference CUDA build (oracle/_ref: unmodified gaussian.cu + bindings.cpp + renderer.py, "
+                               "-std=c++17 flag only) driven with the call sequence of reference splatter.py:513-655",
+                       "tile_instances_M": frame.aux.get("n_instances"), "max_tile_count": frame.aux.get("max_tile"),
+                       "note": "reference backward is only valid for <= 500 instances per tile (SURVEY.md hazard 1); "
+                               "timing is still that of its stock code path"},
+            "clocks": clocks,
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": 0, "kind": "reference",
+                             "sample": "the reference has no CPU implementation of this path; this arm is its own "
+                                       "CUDA build on the same GPU (the stronger baseline)"},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
+    world, rank, local = dist_setup(args.gpus)
+    if args.impl == "reference":
+        out = run_reference(args, world, rank, local)
+    else:
+        out = run_ours(args, world, rank, local)
+    if rank == 0 and out is not None:
+        print(json.dumps(out))
+    if world > 1:
+        import torch.distributed as dist
+        if args.impl != "reference":
+            dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

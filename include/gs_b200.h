@@ -153,6 +153,14 @@ int gs_render_backward(gs_ctx* ctx, const float* pos, const float* rgb, const fl
                        const float* grad_image, float* grad_pos, float* grad_rgb, float* grad_opa,
                        float* grad_quat, float* grad_scale, gs_stream_t stream);
 
+/* Per-stage device timing with CUDA events recorded on the frame's stream (off by default).
+ * gs_frame_stage_ms fills out[GS_N_STAGES] with the milliseconds of the last frame's stages:
+ * 0 project, 1 scan + M readback, 2 key emit, 3 radix sort, 4 range + pack, 5 blend forward,
+ * 6 blend backward, 7 project backward (-1 where not available).  Synchronises `stream`. */
+#define GS_N_STAGES 8
+int gs_ctx_set_timing(gs_ctx* ctx, int enable);
+int gs_frame_stage_ms(gs_ctx* ctx, float* out_host, gs_stream_t stream);
+
 /* Statistics of the last forward on ctx (host struct; synchronises `stream` for M_eff). */
 int gs_frame_stats(gs_ctx* ctx, gs_frame_info* out_host, gs_stream_t stream);
 

@@ -77,9 +77,11 @@ def main(out_dir):
     pr = {k: x.to(dev).clone().requires_grad_(True) for k, x in g.items()}
     img = frame(pr["pos"], pr["rgb"], pr["opa"], pr["quat"], pr["scale"])
     img.backward(go.to(dev))
-    assert frame.aux["max_tile"] <= 500
+    # inside the reference's own limits: dense-list capacity MAXP = Nc//20 (splatter.py:569) and the
+    # backward's 500-instance chunk (SURVEY.md hazards 1, 4)
+    assert frame.aux["max_tile"] <= min(500, frame.aux["MAXP"]), frame.aux["max_tile"]
     np.savez_compressed(os.path.join(out_dir, "frame_c1.npz"), n=c["n"], w=c["w"], h=c["h"], image=cpu(img),
-                        grad_output=cpu(go), **{"grad_" + k: cpu(pr[k].grad) for k in pr})
+                        **{"grad_" + k: cpu(pr[k].grad) for k in pr})
     print("golden fixtures written to", out_dir, sorted(os.listdir(out_dir)))
 
 

@@ -12,7 +12,7 @@ CASES = {
     "project.npz": dict(n=2000, w=256, h=256, k=1),
     "tiles.npz": dict(n=3000, w=320, h=200, k=0),
     "draw_rgb.npz": dict(n=1500, w=128, h=96, opa=(0.005, 0.05)),
-    "frame_c1.npz": dict(n=2000, w=128, h=128, opa=(0.005, 0.05)),
+    "frame_c1.npz": dict(n=4000, w=256, h=192, opa=(0.005, 0.05)),   # max tile 159 <= MAXP = n//20
 }
 
 

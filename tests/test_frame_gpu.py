@@ -54,7 +54,17 @@ def test_fused_frame_vs_oracle(gs, cuda, n, w, h, k, opa):
     assert st["n_instances"] == int(aux["accum"][-1])
     idx, accum = sp._rctx.sorted_instances()
     assert torch.equal(accum.cpu(), aux["accum"])
-    assert torch.equal(idx.cpu().long(), aux["gauss_idx"])
+    # same per-tile sets; the order may differ from the fp64 oracle's only between Gaussians whose
+    # fp32 depths are within rounding of each other (any such order is a valid refinement)
+    ours, want = idx.cpu().long(), aux["gauss_idx"]
+    acc = aux["accum"].long()
+    depth = aux["res_pos"][:, 2]
+    for t in range(acc.numel() - 1):
+        s, e = int(acc[t]), int(acc[t + 1])
+        assert torch.equal(torch.sort(ours[s:e])[0], torch.sort(want[s:e])[0])
+        d = depth[ours[s:e]]
+        assert bool((d[1:] >= d[:-1] - 1e-5).all())
+    assert float((ours != want).float().mean()) < 0.01
 
 
 def test_fused_frame_vs_reference_pipeline(gs, ref, cuda):
@@ -69,7 +79,7 @@ def test_fused_frame_vs_reference_pipeline(gs, ref, cuda):
     p = {k: t.to(cuda).clone().requires_grad_(True) for k, t in g.items()}
     rimg = frame(p["pos"], p["rgb"], p["opa"], p["quat"], p["scale"])
     rimg.backward(go)
-    assert frame.aux["max_tile"] <= 500
+    assert frame.aux["max_tile"] <= min(500, frame.aux["MAXP"])
     sp = _splatter(g, [v], cuda)
     img = sp(0)
     img.backward(go)
@@ -103,12 +113,13 @@ def test_fused_frame_vs_golden(gs, cuda):
     gold = load_golden("frame_c1.npz")
     if gold is None:
         pytest.skip("tests/golden/frame_c1.npz not generated yet")
-    n, w, h = int(gold["n"]), int(gold["w"]), int(gold["h"])
-    g, v, cam = scene(n, w, h, k=0, opa_range=(0.005, 0.05))
+    import golden_cases as GC
+    g, v, cam, go = GC.frame_inputs()
+    assert (int(gold["n"]), int(gold["w"]), int(gold["h"])) == (g["pos"].shape[0], v.width, v.height)
     sp = _splatter(g, [v], cuda)
     img = sp(0)
     assert abs_err(img, gold["image"]) < IMG_ATOL
-    img.backward(gold["grad_output"].to(cuda))
+    img.backward(go.to(cuda))
     for name in ("pos", "rgb", "opa", "quat", "scale"):
         assert rel_err(getattr(sp.gaussian_3ds, name).grad, gold["grad_" + name]) < GRAD_RTOL, name
 
