@@ -66,9 +66,13 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
+            t0 = time.time()
+            while not self.rows and time.time() - t0 < 5.0:      # first sample before the timed region
+                time.sleep(0.01)
+            self.rows.clear()
         except Exception:
             self.proc = None
 
@@ -127,19 +131,6 @@ def max_over_ranks(x, world, dev):
     t = torch.tensor([x], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
-
-
-def allreduce_grads(params, world):
-    """One NCCL all-reduce (SUM) over a single flat bucket of the five gradients."""
-    if world == 1:
-        return
-    import torch.distributed as dist
-    from torch._utils import _flatten_dense_tensors, _unflatten_dense_tensors
-    grads = [p.grad for p in params]
-    flat = _flatten_dense_tensors(grads)
-    dist.all_reduce(flat)
-    for g, f in zip(grads, _unflatten_dense_tensors(flat, grads)):
-        g.copy_(f)
 
 
 # ------------------------------------------------------------------------------------------
@@ -204,6 +195,8 @@ def run_ours(args, world, rank, local):
     vd = [dict(width=v.width, height=v.height, focal_x=v.fx, focal_y=v.fy, rot=v.rot, tran=v.tran) for v in views]
     sp = splatter.Splatter(g, vd, device=dev)
     params = list(sp.gaussian_3ds.parameters())
+    import dp
+    bucket = dp.GradBucket(params)          # one NCCL all-reduce over one flat bucket (no-op at N=1)
     view_id = rank % 8
     go_host = S.make_grad_output(h, w, 0).pin_memory()
     go_dev = go_host.to(dev)
@@ -218,7 +211,7 @@ def run_ours(args, world, rank, local):
         else:
             img = sp(view_id)
             img.backward(go_dev)
-            allreduce_grads(params, world)
+            bucket.allreduce()
 
     ms = timed_loop(step_resident, args.steps, args.warmup, world, dev)
 
@@ -261,7 +254,7 @@ def run_ours(args, world, rank, local):
         if not fwd_only:
             main.wait_event(h2d_done)
             img.backward(go_stage)
-            allreduce_grads(params, world)
+            bucket.allreduce()
         copy_stream.synchronize()
 
     ms_e2e = timed_loop(step_e2e, args.steps, max(1, args.warmup // 2), world, dev)
@@ -378,8 +371,8 @@ def run_reference(args, world, rank, local):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -73,6 +73,8 @@ def main(out_dir):
     # ---- frame_c1.npz : the reference's whole per-frame pipeline ---------------------------
     g, v, cam, go = GC.frame_inputs()
     c = GC.CASES["frame_c1.npz"]
+    bad, mx, maxp = GC.reference_key_collisions(g, cam)
+    assert bad == 0 and mx <= maxp, (bad, mx, maxp)
     frame = ref_pipeline.LegacyFrame(gref, rref, c["w"], c["h"], v.fx, v.fy, v.rot.to(dev), v.tran.to(dev))
     pr = {k: x.to(dev).clone().requires_grad_(True) for k, x in g.items()}
     img = frame(pr["pos"], pr["rgb"], pr["opa"], pr["quat"], pr["scale"])

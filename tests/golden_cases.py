@@ -12,7 +12,10 @@ CASES = {
     "project.npz": dict(n=2000, w=256, h=256, k=1),
     "tiles.npz": dict(n=3000, w=320, h=200, k=0),
     "draw_rgb.npz": dict(n=1500, w=128, h=96, opa=(0.005, 0.05)),
-    "frame_c1.npz": dict(n=4000, w=256, h=192, opa=(0.005, 0.05)),   # max tile 159 <= MAXP = n//20
+    # whole-pipeline case: must sit inside the reference's own limits (SURVEY.md hazards 1, 4):
+    # max tile count 86 <= MAXP = n//20 = 100 (dense-list capacity, splatter.py:569) and NO two
+    # instances of a tile collide in the reference's quantised fp32 sort key (splatter.py:610-612)
+    "frame_c1.npz": dict(n=2000, w=192, h=128, opa=(0.005, 0.05), sigma=(0.4, 1.5), seed=0),
 }
 
 
@@ -46,9 +49,26 @@ def draw_inputs():
 
 def frame_inputs():
     c = CASES["frame_c1.npz"]
-    g, v, cam = scene(c["n"], c["w"], c["h"], opa_range=c["opa"])
-    go = S.make_grad_output(c["h"], c["w"], 0) * (c["h"] * c["w"])
+    return frame_case(c["n"], c["w"], c["h"], c["opa"], c["sigma"], c["seed"])
+
+
+def frame_case(n, w, h, opa, sigma, seed):
+    g, v, cam = scene(n, w, h, seed=seed, opa_range=opa, sigma_px=sigma)
+    go = S.make_grad_output(h, w, seed) * (h * w)
     return g, v, cam, go
+
+
+def reference_key_collisions(g, cam):
+    """(# same-tile neighbours that tie/invert under the reference's fp32 composite key,
+    max tile count, MAXP) for a scene - emulated on the CPU with the oracle front end."""
+    inst = sorted_instances_cpu(g, cam)
+    acc = inst["accum"].long()
+    cnt = acc[1:] - acc[:-1]
+    depth = inst["pos"][:, 2].float()
+    tile = torch.repeat_interleave(torch.arange(cnt.numel()), cnt).float()
+    key = depth + tile * (depth.max() + 1)
+    bad = int(((key[1:] <= key[:-1]) & (tile[1:] == tile[:-1])).sum())
+    return bad, int(cnt.max()), g["pos"].shape[0] // 20
 
 
 def check_oracle_against(name, gold):

@@ -1,0 +1,69 @@
+"""N>1 host logic on CPU: world_size=2, gloo backend, 127.0.0.1 rendezvous."""
+import os
+import socket
+import sys
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "3d-gaussian-splatting_b200"))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import dp
+    torch.manual_seed(0)                       # replicas start identical
+    params = [torch.nn.Parameter(torch.randn(50, 3)), torch.nn.Parameter(torch.randn(50)),
+              torch.nn.Parameter(torch.randn(50, 4))]
+    # each rank "renders" its own view: a rank-dependent gradient
+    views = [dp.view_for_rank(s, rank, world, 8) for s in range(4)]
+    for p in params:
+        p.grad = torch.full_like(p, float(rank + 1))
+    params[1].grad = None                      # a parameter that got no gradient on this rank
+    bucket = dp.GradBucket(params)
+    bucket.allreduce()
+    stat = torch.tensor([float(rank + 1)])
+    dp.allreduce_stats([stat])
+    ok = (bool((params[0].grad == 3.0).all()) and bool((params[2].grad == 3.0).all())
+          and bool((params[1].grad == 0.0).all()) and float(stat) == 3.0)
+    # async variant + averaging
+    for p in params:
+        p.grad = torch.full_like(p, float(rank))
+    work, finish = dp.GradBucket(params, average=True).allreduce(async_op=True)
+    work.wait()
+    finish()
+    ok = ok and bool((params[0].grad == 0.5).all())
+    out[rank] = (ok, views, bucket.nbytes())
+    dist.destroy_process_group()
+
+
+def test_view_sharding_is_a_partition():
+    sys.path.insert(0, os.path.join(ROOT, "3d-gaussian-splatting_b200"))
+    import dp
+    for world in (1, 2, 4, 8):
+        seen = sorted(v for r in range(world) for v in dp.shard_views(8, r, world))
+        assert seen == list(range(8))
+        step_views = sorted(dp.view_for_rank(3, r, world, 8) for r in range(world))
+        assert len(set(step_views)) == world
+
+
+def test_gradient_bucket_allreduce_world2():
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+    assert all(out[r][0] for r in range(world))
+    assert out[0][1] == [0, 2, 4, 6] and out[1][1] == [1, 3, 5, 7]
+    assert out[0][2] == (150 + 50 + 200) * 4

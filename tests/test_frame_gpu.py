@@ -72,9 +72,12 @@ def test_fused_frame_vs_reference_pipeline(gs, ref, cuda):
     sequence) vs our fused path on a C1-class scene inside the reference's safe regime."""
     import ref_pipeline
     gref, rref = ref
-    n, w, h = 3000, 256, 256
-    g, v, cam = scene(n, w, h, k=0, opa_range=(0.005, 0.05))
-    go = (S.make_grad_output(h, w, 0) * (h * w)).to(cuda)
+    import golden_cases as GC
+    # a scene inside the reference's own limits (capacity MAXP = n//20, no fp32 sort-key ties)
+    n, w, h = 2000, 192, 128
+    g, v, cam, go = GC.frame_case(n, w, h, (0.005, 0.05), (0.4, 1.5), 2)
+    assert GC.reference_key_collisions(g, cam)[0] == 0
+    go = go.to(cuda)
     frame = ref_pipeline.LegacyFrame(gref, rref, w, h, v.fx, v.fy, v.rot.to(cuda), v.tran.to(cuda))
     p = {k: t.to(cuda).clone().requires_grad_(True) for k, t in g.items()}
     rimg = frame(p["pos"], p["rgb"], p["opa"], p["quat"], p["scale"])
@@ -93,9 +96,11 @@ def test_legacy_boundary_drop_in(gs, cuda):
     (+ our renderer.py) and agrees with the fused path."""
     import ref_pipeline
     gaussian, renderer = gs
-    n, w, h = 5000, 160, 128
-    g, v, cam = scene(n, w, h, k=0, opa_range=(0.02, 0.5))
-    go = (S.make_grad_output(h, w, 0) * (h * w)).to(cuda)
+    import golden_cases as GC
+    n, w, h = 2000, 192, 128
+    g, v, cam, go = GC.frame_case(n, w, h, (0.05, 0.6), (0.4, 1.5), 6)      # capacity n//20 respected
+    assert GC.reference_key_collisions(g, cam)[0] == 0
+    go = go.to(cuda)
     frame = ref_pipeline.LegacyFrame(gaussian, renderer, w, h, v.fx, v.fy, v.rot.to(cuda), v.tran.to(cuda))
     p = {k: t.to(cuda).clone().requires_grad_(True) for k, t in g.items()}
     limg = frame(p["pos"], p["rgb"], p["opa"], p["quat"], p["scale"])
@@ -103,10 +108,9 @@ def test_legacy_boundary_drop_in(gs, cuda):
     sp = _splatter(g, [v], cuda)
     img = sp(0)
     img.backward(go)
-    # the legacy glue sorts on a quantised fp32 key (SURVEY.md hazard 4): same set, ties may swap
-    assert abs_err(img, limg) < 5e-4
+    assert abs_err(img, limg) < IMG_ATOL
     for name in ("pos", "rgb", "opa", "quat", "scale"):
-        assert rel_err(getattr(sp.gaussian_3ds, name).grad, p[name].grad) < 5e-3, name
+        assert rel_err(getattr(sp.gaussian_3ds, name).grad, p[name].grad) < GRAD_RTOL, name
 
 
 def test_fused_frame_vs_golden(gs, cuda):
