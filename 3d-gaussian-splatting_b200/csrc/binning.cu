@@ -87,59 +87,78 @@ __global__ void gather_kernel(const int* __restrict__ accum, const int* __restri
 }
 
 // ---- fused path ------------------------------------------------------------------------
-// key = tile id << 32 | float bits of depth (depth > 0 => bit order == numeric order)
-// value = Gaussian id.  Instance `rank` of Gaussian g (row-major over its tile rectangle) is
-// written at offsets[g] + rank: that row index doubles as the "slot" the backward pass writes
-// this instance's gradient record to, so a Gaussian's records are contiguous.
-__global__ void __launch_bounds__(kBlock) emit_keys_kernel(const ushort4* __restrict__ rect,
-                                                            const float* __restrict__ depth,
-                                                            const uint32_t* __restrict__ offsets, int n, int ntx,
-                                                            uint64_t* __restrict__ keys,
+// Ordering scheme: the (tile, depth, id) order of all M tile-instances is obtained WITHOUT a
+// wide M-element sort.  (1) the N Gaussians are stably radix-sorted by depth (32-bit keys, N
+// items - cheap); (2) instances are emitted in that order (instance `rank` of the Gaussian at
+// sorted position i goes to row offsets_sorted[i] + rank, rank = row-major index inside its
+// tile rectangle), so the instance array is already ordered by (depth, id, rank);
+// (3) a STABLE radix sort of the M instances on the tile id alone (16-bit key, ceil(log2 T) bits
+// = 2 passes at 1080p, 6 B / item) yields exactly (tile, depth, id).
+// The pre-sort row index doubles as the "slot" the backward writes this instance's gradient
+// record to, so the records of one Gaussian are contiguous (rec[g].d.x .. + count[g]).
+__global__ void __launch_bounds__(kBlock) emit_keys_kernel(GsRec* __restrict__ rec, const uint32_t* __restrict__ perm,
+                                                            const uint32_t* __restrict__ offsets_sorted, int n,
+                                                            int ntx, uint16_t* __restrict__ keys,
                                                             uint32_t* __restrict__ vals) {
   int i = blockIdx.x * kBlock + threadIdx.x;
   if (i >= n) return;
-  uint32_t o0 = offsets[i], o1 = offsets[i + 1];
+  uint32_t o0 = offsets_sorted[i], o1 = offsets_sorted[i + 1];
   if (o1 == o0) return;
-  ushort4 rc = rect[i];
-  uint32_t dbits = __float_as_uint(depth[i]);
+  uint32_t g = perm[i];
+  float4 c = rec[g].c;
+  rec[g].d.x = o0;
+  uint32_t rxy = __float_as_uint(c.z), rwh = __float_as_uint(c.w);
+  uint32_t tx0 = rxy & 0xffffu, ty0 = rxy >> 16, w = rwh & 0xffffu, h = rwh >> 16;
   uint32_t r = o0;
-  for (uint32_t ty = rc.y; ty < (uint32_t)rc.y + rc.w; ++ty)
-    for (uint32_t tx = rc.x; tx < (uint32_t)rc.x + rc.z; ++tx, ++r) {
-      keys[r] = ((uint64_t)(ty * ntx + tx) << 32) | dbits;
-      vals[r] = (uint32_t)i;
+  for (uint32_t ty = ty0; ty < ty0 + h; ++ty)
+    for (uint32_t tx = tx0; tx < tx0 + w; ++tx, ++r) {
+      keys[r] = (uint16_t)(ty * ntx + tx);
+      vals[r] = g;
     }
 }
 
-__global__ void __launch_bounds__(kBlock) pack_sorted_kernel(
-    const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, long long m, int n_tiles, int ntx,
-    const float4* __restrict__ gA, const float2* __restrict__ gB, const float4* __restrict__ gC,
-    const ushort4* __restrict__ rect, const uint32_t* __restrict__ offsets, float4* __restrict__ pA,
-    float2* __restrict__ pB, float4* __restrict__ pC, int* __restrict__ tile_accum) {
+__global__ void __launch_bounds__(kBlock) pack_sorted_kernel(const uint16_t* __restrict__ keys,
+                                                              const uint32_t* __restrict__ vals, long long m,
+                                                              int n_tiles, int ntx, const GsRec* __restrict__ rec,
+                                                              float4* __restrict__ pA, float2* __restrict__ pB,
+                                                              float4* __restrict__ pC,
+                                                              int* __restrict__ tile_accum) {
   long long i = (long long)blockIdx.x * kBlock + threadIdx.x;
   if (i >= m) return;
-  uint32_t tile = (uint32_t)(keys[i] >> 32);
+  uint32_t tile = keys[i];
   // tile range boundaries (tile_n_point_accum semantics: accum[t] = first sorted index of tile t)
   if (i == 0) {
     for (uint32_t t = 0; t <= tile; ++t) tile_accum[t] = 0;
   } else {
-    uint32_t prev = (uint32_t)(keys[i - 1] >> 32);
+    uint32_t prev = keys[i - 1];
     for (uint32_t t = prev + 1; t <= tile; ++t) tile_accum[t] = (int)i;
   }
   if (i == m - 1)
     for (uint32_t t = tile + 1; t <= (uint32_t)n_tiles; ++t) tile_accum[t] = (int)m;
 
-  uint32_t g = vals[i];
-  ushort4 rc = rect[g];
+  const GsRec* r = rec + vals[i];
+  float4 a = r->a, b = r->b, c = r->c;
+  uint32_t off = r->d.x;
+  uint32_t rxy = __float_as_uint(c.z), rwh = __float_as_uint(c.w);
   uint32_t tx = tile % ntx, ty = tile / ntx;
-  uint32_t slot = offsets[g] + (ty - rc.y) * rc.z + (tx - rc.x);
-  float4 c = gC[g];
-  c.w = __uint_as_float(slot);
-  pA[i] = gA[g];
-  pB[i] = gB[g];
-  pC[i] = c;
+  uint32_t slot = off + (ty - (rxy >> 16)) * (rwh & 0xffffu) + (tx - (rxy & 0xffffu));
+  pA[i] = a;
+  pB[i] = make_float2(b.x, b.y);
+  pC[i] = make_float4(b.z, b.w, c.x, __uint_as_float(slot));
+}
+
+__global__ void __launch_bounds__(kBlock) iota_kernel(uint32_t* out, int n) {
+  int i = blockIdx.x * kBlock + threadIdx.x;
+  if (i < n) out[i] = (uint32_t)i;
 }
 
 }  // namespace
+
+cudaError_t gs_launch_iota(uint32_t* out, int n, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  iota_kernel<<<(n + kBlock - 1) / kBlock, kBlock, 0, st>>>(out, n);
+  return cudaGetLastError();
+}
 
 extern "C" int gs_tile_list(const float* pos, const float* cov, int n, const float* tile_top,
                             const float* tile_bottom, const float* tile_left, const float* tile_right, int n_tiles,
@@ -188,19 +207,18 @@ extern "C" int gs_gather(const int* tile_n_point_accum, const int* tile_gaussian
   return 0;
 }
 
-cudaError_t gs_launch_emit_keys(const ushort4* rect, const float* depth, const uint32_t* offsets, int n, int ntx,
-                                uint64_t* keys, uint32_t* vals, cudaStream_t st) {
+cudaError_t gs_launch_emit_keys(GsRec* rec, const uint32_t* perm, const uint32_t* offsets_sorted, int n, int ntx,
+                                uint16_t* keys, uint32_t* vals, cudaStream_t st) {
   if (n == 0) return cudaSuccess;
-  emit_keys_kernel<<<(n + kBlock - 1) / kBlock, kBlock, 0, st>>>(rect, depth, offsets, n, ntx, keys, vals);
+  emit_keys_kernel<<<(n + kBlock - 1) / kBlock, kBlock, 0, st>>>(rec, perm, offsets_sorted, n, ntx, keys, vals);
   return cudaGetLastError();
 }
 
-cudaError_t gs_launch_pack_sorted(const uint64_t* keys, const uint32_t* vals, long long m, int n_tiles, int ntx,
-                                  const float4* gA, const float2* gB, const float4* gC, const ushort4* rect,
-                                  const uint32_t* offsets, float4* pA, float2* pB, float4* pC, int* tile_accum,
+cudaError_t gs_launch_pack_sorted(const uint16_t* keys, const uint32_t* vals, long long m, int n_tiles, int ntx,
+                                  const GsRec* rec, float4* pA, float2* pB, float4* pC, int* tile_accum,
                                   cudaStream_t st) {
   if (m == 0) return cudaMemsetAsync(tile_accum, 0, sizeof(int) * (size_t)(n_tiles + 1), st);
   pack_sorted_kernel<<<(unsigned)((m + kBlock - 1) / kBlock), kBlock, 0, st>>>(
-      keys, vals, m, n_tiles, ntx, gA, gB, gC, rect, offsets, pA, pB, pC, tile_accum);
+      keys, vals, m, n_tiles, ntx, rec, pA, pB, pC, tile_accum);
   return cudaGetLastError();
 }

@@ -94,8 +94,9 @@ __global__ void __launch_bounds__(FWD_THREADS) blend_fwd_kernel(const float4* __
     const float2 b = sB[J];                                                   \
     const float4 c = sC[J];                                                   \
     const float dx = px - a.x, dy = py - a.y;                                 \
-    const float q = fmaf(a.z * dx, dx, fmaf(-a.w * dx, dy, b.x * dy * dy));   \
-    const float alpha = gs_ex2(b.y - q);                                      \
+    const float eu = fmaf(a.z, dx, -a.w * dy);                                \
+    const float ev = fmaf(-b.x * dy, dy, b.y);                                \
+    const float alpha = gs_ex2(fmaf(-dx, eu, ev)); /* l2o - (ca dx^2 - cb dx dy + cc dy^2) */ \
     const float w = (T > GS_T_STOP) ? alpha * T : 0.f;                        \
     cr = fmaf(c.x, w, cr);                                                    \
     cg = fmaf(c.y, w, cg);                                                    \
@@ -229,8 +230,9 @@ __global__ void __launch_bounds__(BWD_THREADS) blend_bwd_kernel(const float4* __
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
         const float dx = px[p & 1] - a.x, dy = py[p >> 1] - a.y;
-        const float q = fmaf(a.z * dx, dx, fmaf(-a.w * dx, dy, b.x * dy * dy));
-        const float alpha = gs_ex2(b.y - q);
+        const float eu = fmaf(a.z, dx, -a.w * dy);
+        const float ev = fmaf(-b.x * dy, dy, b.y);
+        const float alpha = gs_ex2(fmaf(-dx, eu, ev));   // l2o - (ca dx^2 - cb dx dy + cc dy^2)
         const bool live = T[p] > GS_T_STOP;
         const float w = live ? alpha * T[p] : 0.f;
         const float gc = fmaf(gr[p], c.x, fmaf(gg[p], c.y, gb[p] * c.z));

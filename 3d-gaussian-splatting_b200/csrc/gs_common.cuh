@@ -27,6 +27,15 @@ int gs_set_error_msg(int code, const char* what);
 //                             gradient record (int bits)
 // alpha(px,py) = exp2(l2o - (ca*dx*dx - cb*dx*dy + cc*dy*dy)),  dx = px-x, dy = py-y
 //   == opa * __expf(-(d*dx^2 - (b+c)*dx*dy + a*dy^2) / (2*det + 1e-14))   (gaussian.cu:920-926)
+// Per-Gaussian record produced by the fused projection (one 64-byte line = two sectors, so the
+// post-sort gather touches 2 sectors per instance instead of 5 separate arrays).
+struct __align__(64) GsRec {
+  float4 a;      // x, y, ca, cb
+  float4 b;      // cc, l2o, r, g
+  float4 c;      // b, depth, rect(tx0 | ty0<<16) bits, rect(w | h<<16) bits
+  uint4 d;       // offsets[g] (first instance row), unused x3
+};
+
 struct GsConic {
   float ca, cb, cc;
 };

@@ -19,23 +19,24 @@ struct GsFrameGeom {
 cudaError_t gs_launch_fused_project(const float* pos, const float* rgb, const float* opa, const float* quat,
                                     const float* scale, int n, int scale_act, const GsCam& cam,
                                     const GsTileGrid& grid, float near_plane, float half_w, float half_h,
-                                    float4* gA, float2* gB, float4* gC, ushort4* rect, float* depth,
-                                    uint32_t* count, int64_t* mask, unsigned int* n_visible, cudaStream_t st);
+                                    GsRec* rec, uint32_t* count, uint32_t* dkey, int64_t* mask,
+                                    unsigned int* n_visible, cudaStream_t st);
 
 cudaError_t gs_launch_fused_project_bwd(const float* pos, const float* rgb, const float* opa, const float* quat,
                                         const float* scale, int n, int scale_act, const GsCam& cam,
-                                        float near_plane, float half_w, float half_h, const uint32_t* offsets,
-                                        const float* grad_inst, float* g_pos, float* g_rgb, float* g_opa,
+                                        float near_plane, float half_w, float half_h, const GsRec* rec,
+                                        const uint32_t* count, const float* grad_inst, float* g_pos, float* g_rgb, float* g_opa,
                                         float* g_quat, float* g_scale, cudaStream_t st);
 
 // ---- binning.cu ------------------------------------------------------------------------
-cudaError_t gs_launch_emit_keys(const ushort4* rect, const float* depth, const uint32_t* offsets, int n, int ntx,
-                                uint64_t* keys, uint32_t* vals, cudaStream_t st);
+cudaError_t gs_launch_emit_keys(GsRec* rec, const uint32_t* perm, const uint32_t* offsets_sorted, int n, int ntx,
+                                uint16_t* keys, uint32_t* vals, cudaStream_t st);
 
-cudaError_t gs_launch_pack_sorted(const uint64_t* keys, const uint32_t* vals, long long m, int n_tiles, int ntx,
-                                  const float4* gA, const float2* gB, const float4* gC, const ushort4* rect,
-                                  const uint32_t* offsets, float4* pA, float2* pB, float4* pC, int* tile_accum,
+cudaError_t gs_launch_pack_sorted(const uint16_t* keys, const uint32_t* vals, long long m, int n_tiles, int ntx,
+                                  const GsRec* rec, float4* pA, float2* pB, float4* pC, int* tile_accum,
                                   cudaStream_t st);
+
+cudaError_t gs_launch_iota(uint32_t* out, int n, cudaStream_t st);
 
 // ---- blend.cu --------------------------------------------------------------------------
 cudaError_t gs_launch_blend_fwd(const float4* pA, const float2* pB, const float4* pC, const int* tile_accum,

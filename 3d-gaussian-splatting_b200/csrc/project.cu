@@ -47,9 +47,9 @@ __device__ __forceinline__ void load_activated(const float* __restrict__ quat, c
 __global__ void __launch_bounds__(kBlock) fused_project_kernel(
     const float* __restrict__ pos, const float* __restrict__ rgb, const float* __restrict__ opa,
     const float* __restrict__ quat, const float* __restrict__ scale, int n, int scale_act, GsCam cam,
-    GsTileGrid grid, float near_plane, float half_w, float half_h, float4* __restrict__ gA,
-    float2* __restrict__ gB, float4* __restrict__ gC, ushort4* __restrict__ rect, float* __restrict__ depth,
-    uint32_t* __restrict__ count, int64_t* __restrict__ mask, unsigned int* __restrict__ n_visible) {
+    GsTileGrid grid, float near_plane, float half_w, float half_h, GsRec* __restrict__ rec,
+    uint32_t* __restrict__ count, uint32_t* __restrict__ dkey, int64_t* __restrict__ mask,
+    unsigned int* __restrict__ n_visible) {
   int i = blockIdx.x * kBlock + threadIdx.x;
   bool vis = false;
   if (i < n) {
@@ -66,15 +66,16 @@ __global__ void __launch_bounds__(kBlock) fused_project_kernel(
         cnt = (tx1 - tx0) * (ty1 - ty0);
         GsConic k = gs_make_conic(o.a, o.b, o.c, o.d);
         float op = gs_sigmoid(opa[i]);
-        gA[i] = make_float4(o.x, o.y, k.ca, k.cb);
-        gB[i] = make_float2(k.cc, log2f(op));
-        gC[i] = make_float4(gs_sigmoid(rgb[3 * i]), gs_sigmoid(rgb[3 * i + 1]), gs_sigmoid(rgb[3 * i + 2]), 0.f);
-        rect[i] = make_ushort4((unsigned short)tx0, (unsigned short)ty0, (unsigned short)(tx1 - tx0),
-                               (unsigned short)(ty1 - ty0));
-        depth[i] = o.depth;
+        GsRec* r = rec + i;
+        r->a = make_float4(o.x, o.y, k.ca, k.cb);
+        r->b = make_float4(k.cc, log2f(op), gs_sigmoid(rgb[3 * i]), gs_sigmoid(rgb[3 * i + 1]));
+        r->c = make_float4(gs_sigmoid(rgb[3 * i + 2]), o.depth, __uint_as_float(tx0 | (ty0 << 16)),
+                           __uint_as_float((tx1 - tx0) | ((ty1 - ty0) << 16)));
       }
     }
     count[i] = cnt;
+    // depth sort key: positive float bits order like the floats; Gaussians without instances last
+    dkey[i] = cnt ? __float_as_uint(o.depth) : 0xffffffffu;
   }
   int nv = __syncthreads_count(vis);
   if (threadIdx.x == 0 && nv) atomicAdd(n_visible, (unsigned int)nv);
@@ -86,15 +87,16 @@ __global__ void __launch_bounds__(kBlock) fused_project_kernel(
 __global__ void __launch_bounds__(kBlock) fused_project_bwd_kernel(
     const float* __restrict__ pos, const float* __restrict__ rgb, const float* __restrict__ opa,
     const float* __restrict__ quat, const float* __restrict__ scale, int n, int scale_act, GsCam cam,
-    float near_plane, float half_w, float half_h, const uint32_t* __restrict__ offsets,
-    const float* __restrict__ grad_inst, float* __restrict__ g_pos, float* __restrict__ g_rgb,
+    float near_plane, float half_w, float half_h, const GsRec* __restrict__ rec,
+    const uint32_t* __restrict__ count, const float* __restrict__ grad_inst, float* __restrict__ g_pos, float* __restrict__ g_rgb,
     float* __restrict__ g_opa, float* __restrict__ g_quat, float* __restrict__ g_scale) {
   int i = blockIdx.x * kBlock + threadIdx.x;
   if (i >= n) return;
   float gp[3] = {0.f, 0.f, 0.f}, gq_raw[4] = {0.f, 0.f, 0.f, 0.f}, gs_raw[3] = {0.f, 0.f, 0.f};
   float go = 0.f, gcol[3] = {0.f, 0.f, 0.f};
-  uint32_t o0 = offsets[i], o1 = offsets[i + 1];
-  if (o1 > o0) {
+  const uint32_t cnt = count[i];
+  if (cnt > 0) {
+    const uint32_t o0 = rec[i].d.x, o1 = o0 + cnt;   // this Gaussian's contiguous gradient rows
     float acc[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) acc[k] = 0.f;
@@ -295,23 +297,22 @@ extern "C" int gs_jacobian(const float* pos_cam, int n, float* jac, gs_stream_t 
 cudaError_t gs_launch_fused_project(const float* pos, const float* rgb, const float* opa, const float* quat,
                                     const float* scale, int n, int scale_act, const GsCam& cam,
                                     const GsTileGrid& grid, float near_plane, float half_w, float half_h,
-                                    float4* gA, float2* gB, float4* gC, ushort4* rect, float* depth,
-                                    uint32_t* count, int64_t* mask, unsigned int* n_visible, cudaStream_t st) {
+                                    GsRec* rec, uint32_t* count, uint32_t* dkey, int64_t* mask,
+                                    unsigned int* n_visible, cudaStream_t st) {
   if (n == 0) return cudaSuccess;
   fused_project_kernel<<<grid_for(n), kBlock, 0, st>>>(pos, rgb, opa, quat, scale, n, scale_act, cam, grid,
-                                                       near_plane, half_w, half_h, gA, gB, gC, rect, depth, count,
-                                                       mask, n_visible);
+                                                       near_plane, half_w, half_h, rec, count, dkey, mask, n_visible);
   return cudaGetLastError();
 }
 
 cudaError_t gs_launch_fused_project_bwd(const float* pos, const float* rgb, const float* opa, const float* quat,
                                         const float* scale, int n, int scale_act, const GsCam& cam,
-                                        float near_plane, float half_w, float half_h, const uint32_t* offsets,
-                                        const float* grad_inst, float* g_pos, float* g_rgb, float* g_opa,
+                                        float near_plane, float half_w, float half_h, const GsRec* rec,
+                                        const uint32_t* count, const float* grad_inst, float* g_pos, float* g_rgb, float* g_opa,
                                         float* g_quat, float* g_scale, cudaStream_t st) {
   if (n == 0) return cudaSuccess;
   fused_project_bwd_kernel<<<grid_for(n), kBlock, 0, st>>>(pos, rgb, opa, quat, scale, n, scale_act, cam, near_plane,
-                                                           half_w, half_h, offsets, grad_inst, g_pos, g_rgb, g_opa,
+                                                           half_w, half_h, rec, count, grad_inst, g_pos, g_rgb, g_opa,
                                                            g_quat, g_scale);
   return cudaGetLastError();
 }

@@ -1,11 +1,14 @@
 // Frame orchestration for the fused path: owns device workspaces and strings the stages
-//   project -> exclusive scan -> key emit -> CUB radix sort (onesweep) -> range+pack -> blend
+//   project -> depth sort of the N Gaussians + scan -> emit in depth order -> stable tile-id
+//   radix sort of the M instances (CUB onesweep, 2 passes at 1080p) -> range+pack -> blend
 // and the backward  blend_bwd -> project_bwd (segment-sum + chain rule).
 // Replaces the PyTorch glue of reference splatter.py:513-655 (4 boolean-mask compactions, the
 // dense [T, N/20] tile list, cumsum, two 4-tensor gathers, fp32-key torch.sort, >= 7 host
 // syncs) with 7 launches and ONE 8-byte readback (the instance count M sizes the sort).
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
 
 #include <cmath>
 #include <cstdio>
@@ -13,6 +16,14 @@
 #include <new>
 
 #include "internal.h"
+
+// count of the Gaussian at depth-sorted position i (0 for the sentinel item i == n)
+struct GsCountInSortedOrder {
+  const uint32_t* count;
+  const uint32_t* perm;
+  uint32_t n;
+  __host__ __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return i < n ? count[perm[i]] : 0u; }
+};
 
 // ---- error plumbing ---------------------------------------------------------------------
 static thread_local char g_err[512] = {0};
@@ -59,7 +70,8 @@ struct DevBuf {
 struct gs_ctx {
   int device = 0;
   // per Gaussian
-  DevBuf gA, gB, gC, rect, depth, count, offsets;
+  DevBuf rec, count, offsets, dkey_in, dkey_out, perm, iota;
+  size_t iota_n = 0;
   // per instance
   DevBuf keys_in, keys_out, vals_in, vals_out, pA, pB, pC, grad_inst;
   // per tile / misc
@@ -105,7 +117,7 @@ extern "C" int gs_ctx_create(gs_ctx** out) {
 extern "C" void gs_ctx_destroy(gs_ctx* c) {
   if (!c) return;
   cudaDeviceSynchronize();
-  DevBuf* bufs[] = {&c->gA, &c->gB, &c->gC, &c->rect, &c->depth, &c->count, &c->offsets, &c->keys_in, &c->keys_out,
+  DevBuf* bufs[] = {&c->rec, &c->count, &c->offsets, &c->dkey_in, &c->dkey_out, &c->perm, &c->iota, &c->keys_in, &c->keys_out,
                     &c->vals_in, &c->vals_out, &c->pA, &c->pB, &c->pC, &c->grad_inst, &c->tile_accum, &c->tile_neff,
                     &c->cub_tmp, &c->counters, &c->img_dev, &c->gimg_dev};
   for (DevBuf* b : bufs) b->release();
@@ -141,7 +153,7 @@ extern "C" int gs_render_forward(gs_ctx* c, const float* pos, const float* rgb, 
   g.n_tiles = g.ntx * g.nty;
   g.fx = cam->focal_x;
   g.fy = cam->focal_y;
-  if (g.ntx > 65535 || g.nty > 65535) return gs_set_error_msg(GS_ERR_INVALID_ARG, "gs_render_forward: image too large");
+  if (g.n_tiles > 65536) return gs_set_error_msg(GS_ERR_UNSUPPORTED, "gs_render_forward: more than 65536 tiles");
 
   // Host scalars are formed in double then narrowed, like the Python floats that the reference
   // passes through pybind (splatter.py:279-282, :532-533).
@@ -160,34 +172,47 @@ extern "C" int gs_render_forward(gs_ctx* c, const float* pos, const float* rgb, 
   float half_h = (float)((double)cam->height * 1.2 / 2.0 / (double)cam->focal_y);
 
   size_t N = (size_t)n;
-  GS_CUDA_TRY(c->gA.reserve(N * 16, st));
-  GS_CUDA_TRY(c->gB.reserve(N * 8, st));
-  GS_CUDA_TRY(c->gC.reserve(N * 16, st));
-  GS_CUDA_TRY(c->rect.reserve(N * 8, st));
-  GS_CUDA_TRY(c->depth.reserve(N * 4, st));
+  GS_CUDA_TRY(c->rec.reserve(N * sizeof(GsRec), st));
   GS_CUDA_TRY(c->count.reserve((N + 1) * 4, st));
   GS_CUDA_TRY(c->offsets.reserve((N + 1) * 4, st));
+  GS_CUDA_TRY(c->dkey_in.reserve(N * 4 + 4, st));
+  GS_CUDA_TRY(c->dkey_out.reserve(N * 4 + 4, st));
+  GS_CUDA_TRY(c->perm.reserve(N * 4 + 4, st));
   GS_CUDA_TRY(c->tile_accum.reserve((size_t)(g.n_tiles + 1) * 4, st));
   GS_CUDA_TRY(c->tile_neff.reserve((size_t)g.n_tiles * 4, st));
   GS_CUDA_TRY(c->counters.reserve(64, st));
+  if (c->iota_n < N) {   // 0..N-1 values for the depth sort (kept across frames)
+    GS_CUDA_TRY(c->iota.reserve(N * 4 + 4, st));
+    GS_CUDA_TRY(gs_launch_iota(c->iota.as<uint32_t>(), n, st));
+    c->iota_n = N;
+  }
 
   // 1. projection + activations + tile rectangle
   c->ev_fwd_valid = false;
   gs_mark(c, 0, st);
   GS_CUDA_TRY(cudaMemsetAsync(c->counters.p, 0, 64, st));
-  GS_CUDA_TRY(cudaMemsetAsync(c->count.as<uint32_t>() + N, 0, 4, st));
   GS_CUDA_TRY(gs_launch_fused_project(pos, rgb, opa, quat, scale, n, scale_activation, dc, grid, cam->near_plane,
-                                      half_w, half_h, c->gA.as<float4>(), c->gB.as<float2>(), c->gC.as<float4>(),
-                                      c->rect.as<ushort4>(), c->depth.as<float>(), c->count.as<uint32_t>(),
-                                      culling_mask, c->counters.as<unsigned int>(), st));
-  // 2. exclusive scan of the per-Gaussian tile counts (N+1 items: offsets[N] = M)
+                                      half_w, half_h, c->rec.as<GsRec>(), c->count.as<uint32_t>(),
+                                      c->dkey_in.as<uint32_t>(), culling_mask, c->counters.as<unsigned int>(), st));
+  // 2. stable depth sort of the N Gaussians, then exclusive scan of their tile counts in that
+  //    order (N+1 items: offsets[N] = M); the count gather is fused into the scan's input iterator
   gs_mark(c, 1, st);
-  size_t scan_tmp = 0;
-  GS_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp, c->count.as<uint32_t>(), c->offsets.as<uint32_t>(),
-                                            n + 1, st));
-  GS_CUDA_TRY(c->cub_tmp.reserve(scan_tmp, st));
-  GS_CUDA_TRY(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, scan_tmp, c->count.as<uint32_t>(),
-                                            c->offsets.as<uint32_t>(), n + 1, st));
+  size_t tmp_bytes = 0, tmp2 = 0;
+  if (n > 0)
+    GS_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, c->dkey_in.as<uint32_t>(),
+                                                c->dkey_out.as<uint32_t>(), c->iota.as<uint32_t>(),
+                                                c->perm.as<uint32_t>(), n, 0, 32, st));
+  GsCountInSortedOrder cnt_it_fn{c->count.as<uint32_t>(), c->perm.as<uint32_t>(), (uint32_t)n};
+  cub::CountingInputIterator<uint32_t> idx_it(0);
+  cub::TransformInputIterator<uint32_t, GsCountInSortedOrder, cub::CountingInputIterator<uint32_t>> cnt_it(idx_it,
+                                                                                                            cnt_it_fn);
+  GS_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp2, cnt_it, c->offsets.as<uint32_t>(), n + 1, st));
+  GS_CUDA_TRY(c->cub_tmp.reserve(tmp_bytes > tmp2 ? tmp_bytes : tmp2, st));
+  if (n > 0)
+    GS_CUDA_TRY(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp_bytes, c->dkey_in.as<uint32_t>(),
+                                                c->dkey_out.as<uint32_t>(), c->iota.as<uint32_t>(),
+                                                c->perm.as<uint32_t>(), n, 0, 32, st));
+  GS_CUDA_TRY(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp2, cnt_it, c->offsets.as<uint32_t>(), n + 1, st));
   // the one host round trip of the frame
   *c->host_m = 0;
   GS_CUDA_TRY(cudaMemcpyAsync(c->host_m, c->offsets.as<uint32_t>() + N, 4, cudaMemcpyDeviceToHost, st));
@@ -201,33 +226,32 @@ extern "C" int gs_render_forward(gs_ctx* c, const float* pos, const float* rgb, 
   GS_CUDA_TRY(c->pC.reserve(M * 16 + 16, st));
   GS_CUDA_TRY(c->pB.reserve((M + 2) * 8, st));
   if (m > 0) {
-    GS_CUDA_TRY(c->keys_in.reserve(M * 8, st));
-    GS_CUDA_TRY(c->keys_out.reserve(M * 8, st));
+    GS_CUDA_TRY(c->keys_in.reserve(M * 2 + 16, st));
+    GS_CUDA_TRY(c->keys_out.reserve(M * 2 + 16, st));
     GS_CUDA_TRY(c->vals_in.reserve(M * 4, st));
     GS_CUDA_TRY(c->vals_out.reserve(M * 4, st));
-    // 3. keys
-    GS_CUDA_TRY(gs_launch_emit_keys(c->rect.as<ushort4>(), c->depth.as<float>(), c->offsets.as<uint32_t>(), n, g.ntx,
-                                    c->keys_in.as<uint64_t>(), c->vals_in.as<uint32_t>(), st));
-    // 4. (tile | depth) radix sort — only the significant key bits
+    // 3. instances in (depth, id) order: tile-id keys + Gaussian-id values
+    GS_CUDA_TRY(gs_launch_emit_keys(c->rec.as<GsRec>(), c->perm.as<uint32_t>(), c->offsets.as<uint32_t>(), n, g.ntx,
+                                    c->keys_in.as<uint16_t>(), c->vals_in.as<uint32_t>(), st));
+    // 4. stable radix sort on the tile id only -> (tile, depth, id)
     gs_mark(c, 3, st);
-    int end_bit = 32 + ceil_log2((unsigned)g.n_tiles);
-    if (end_bit < 33) end_bit = 33;
+    int end_bit = ceil_log2((unsigned)g.n_tiles);
+    if (end_bit < 1) end_bit = 1;
     size_t sort_tmp = 0;
-    GS_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, c->keys_in.as<uint64_t>(),
-                                                c->keys_out.as<uint64_t>(), c->vals_in.as<uint32_t>(),
+    GS_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, c->keys_in.as<uint16_t>(),
+                                                c->keys_out.as<uint16_t>(), c->vals_in.as<uint32_t>(),
                                                 c->vals_out.as<uint32_t>(), (int)m, 0, end_bit, st));
     GS_CUDA_TRY(c->cub_tmp.reserve(sort_tmp, st));
-    GS_CUDA_TRY(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, sort_tmp, c->keys_in.as<uint64_t>(),
-                                                c->keys_out.as<uint64_t>(), c->vals_in.as<uint32_t>(),
+    GS_CUDA_TRY(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, sort_tmp, c->keys_in.as<uint16_t>(),
+                                                c->keys_out.as<uint16_t>(), c->vals_in.as<uint32_t>(),
                                                 c->vals_out.as<uint32_t>(), (int)m, 0, end_bit, st));
   }
   // 5. tile ranges + packed sorted record streams
   if (m == 0) gs_mark(c, 3, st);
   gs_mark(c, 4, st);
-  GS_CUDA_TRY(gs_launch_pack_sorted(c->keys_out.as<uint64_t>(), c->vals_out.as<uint32_t>(), m, g.n_tiles, g.ntx,
-                                    c->gA.as<float4>(), c->gB.as<float2>(), c->gC.as<float4>(),
-                                    c->rect.as<ushort4>(), c->offsets.as<uint32_t>(), c->pA.as<float4>(),
-                                    c->pB.as<float2>(), c->pC.as<float4>(), c->tile_accum.as<int>(), st));
+  GS_CUDA_TRY(gs_launch_pack_sorted(c->keys_out.as<uint16_t>(), c->vals_out.as<uint32_t>(), m, g.n_tiles, g.ntx,
+                                    c->rec.as<GsRec>(), c->pA.as<float4>(), c->pB.as<float2>(),
+                                    c->pC.as<float4>(), c->tile_accum.as<int>(), st));
   // 6. blend
   gs_mark(c, 5, st);
   GS_CUDA_TRY(gs_launch_blend_fwd(c->pA.as<float4>(), c->pB.as<float2>(), c->pC.as<float4>(), c->tile_accum.as<int>(),
@@ -266,7 +290,8 @@ extern "C" int gs_render_backward(gs_ctx* c, const float* pos, const float* rgb,
                                     st));
   gs_mark(c, 8, st);
   GS_CUDA_TRY(gs_launch_fused_project_bwd(pos, rgb, opa, quat, scale, c->n, c->scale_act, c->cam, c->near_plane,
-                                          c->half_w, c->half_h, c->offsets.as<uint32_t>(), c->grad_inst.as<float>(),
+                                          c->half_w, c->half_h, c->rec.as<GsRec>(), c->count.as<uint32_t>(),
+                                          c->grad_inst.as<float>(),
                                           grad_pos, grad_rgb, grad_opa, grad_quat, grad_scale, st));
   gs_mark(c, 9, st);
   c->ev_bwd_valid = c->timing && c->ev_ok;

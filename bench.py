@@ -293,7 +293,7 @@ def run_ours(args, world, rank, local):
         "gpu_launches_note": "our kernels per step: fused_project, emit_keys, pack_sorted, blend_fwd"
                              + ("" if fwd_only else ", blend_bwd, fused_project_bwd") +
                              "; plus CUB scan (2) and onesweep radix sort (8) library kernels",
-        "stage_ms": dict(zip(["project", "scan+readback", "emit_keys", "radix_sort", "pack", "blend_fwd",
+        "stage_ms": dict(zip(["project", "depth_sort+scan+readback", "emit_keys", "tile_sort", "pack", "blend_fwd",
                               "blend_bwd", "project_bwd"], [round(x, 4) for x in stage])),
         "roofline": {"bound": "hbm", "kernel": roof_kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,

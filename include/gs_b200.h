@@ -155,7 +155,8 @@ int gs_render_backward(gs_ctx* ctx, const float* pos, const float* rgb, const fl
 
 /* Per-stage device timing with CUDA events recorded on the frame's stream (off by default).
  * gs_frame_stage_ms fills out[GS_N_STAGES] with the milliseconds of the last frame's stages:
- * 0 project, 1 scan + M readback, 2 key emit, 3 radix sort, 4 range + pack, 5 blend forward,
+ * 0 project, 1 depth sort of Gaussians + scan + M readback, 2 key emit, 3 tile-id radix sort,
+ * 4 range + pack, 5 blend forward,
  * 6 blend backward, 7 project backward (-1 where not available).  Synchronises `stream`. */
 #define GS_N_STAGES 8
 int gs_ctx_set_timing(gs_ctx* ctx, int enable);
