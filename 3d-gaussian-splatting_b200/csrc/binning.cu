@@ -92,13 +92,15 @@ __global__ void gather_kernel(const int* __restrict__ accum, const int* __restri
 // items - cheap); (2) instances are emitted in that order (instance `rank` of the Gaussian at
 // sorted position i goes to row offsets_sorted[i] + rank, rank = row-major index inside its
 // tile rectangle), so the instance array is already ordered by (depth, id, rank);
-// (3) a STABLE radix sort of the M instances on the tile id alone (16-bit key, ceil(log2 T) bits
-// = 2 passes at 1080p, 6 B / item) yields exactly (tile, depth, id).
-// The pre-sort row index doubles as the "slot" the backward writes this instance's gradient
-// record to, so the records of one Gaussian are contiguous (rec[g].d.x .. + count[g]).
-__global__ void __launch_bounds__(kBlock) emit_keys_kernel(GsRec* __restrict__ rec, const uint32_t* __restrict__ perm,
+// (3) a STABLE radix sort of the M instances on the tile id alone (32-bit key of which only ceil(log2 T)
+// bits are sorted = 2 passes at 1080p, 8 B / item) yields exactly (tile, depth, id).
+// The backward writes an instance's gradient record to row ("slot") offsets_g[g] + rank, where
+// offsets_g is the exclusive scan of the tile counts in Gaussian-id order: the records of one
+// Gaussian are contiguous, and nothing in the pipeline needs a scattered store (scattered
+// 4-byte stores cost 0.5 ms at C3 when tried: partial-sector read-modify-write in L2).
+__global__ void __launch_bounds__(kBlock) emit_keys_kernel(const GsRec* __restrict__ rec, const uint32_t* __restrict__ perm,
                                                             const uint32_t* __restrict__ offsets_sorted, int n,
-                                                            int ntx, uint16_t* __restrict__ keys,
+                                                            int ntx, uint32_t* __restrict__ keys,
                                                             uint32_t* __restrict__ vals) {
   int i = blockIdx.x * kBlock + threadIdx.x;
   if (i >= n) return;
@@ -106,20 +108,20 @@ __global__ void __launch_bounds__(kBlock) emit_keys_kernel(GsRec* __restrict__ r
   if (o1 == o0) return;
   uint32_t g = perm[i];
   float4 c = rec[g].c;
-  rec[g].d.x = o0;
   uint32_t rxy = __float_as_uint(c.z), rwh = __float_as_uint(c.w);
   uint32_t tx0 = rxy & 0xffffu, ty0 = rxy >> 16, w = rwh & 0xffffu, h = rwh >> 16;
   uint32_t r = o0;
   for (uint32_t ty = ty0; ty < ty0 + h; ++ty)
     for (uint32_t tx = tx0; tx < tx0 + w; ++tx, ++r) {
-      keys[r] = (uint16_t)(ty * ntx + tx);
+      keys[r] = ty * ntx + tx;
       vals[r] = g;
     }
 }
 
-__global__ void __launch_bounds__(kBlock) pack_sorted_kernel(const uint16_t* __restrict__ keys,
+__global__ void __launch_bounds__(kBlock) pack_sorted_kernel(const uint32_t* __restrict__ keys,
                                                               const uint32_t* __restrict__ vals, long long m,
                                                               int n_tiles, int ntx, const GsRec* __restrict__ rec,
+                                                              const uint32_t* __restrict__ offsets_g,
                                                               float4* __restrict__ pA, float2* __restrict__ pB,
                                                               float4* __restrict__ pC,
                                                               int* __restrict__ tile_accum) {
@@ -136,9 +138,10 @@ __global__ void __launch_bounds__(kBlock) pack_sorted_kernel(const uint16_t* __r
   if (i == m - 1)
     for (uint32_t t = tile + 1; t <= (uint32_t)n_tiles; ++t) tile_accum[t] = (int)m;
 
-  const GsRec* r = rec + vals[i];
+  const uint32_t g = vals[i];
+  const GsRec* r = rec + g;
   float4 a = r->a, b = r->b, c = r->c;
-  uint32_t off = r->d.x;
+  uint32_t off = offsets_g[g];
   uint32_t rxy = __float_as_uint(c.z), rwh = __float_as_uint(c.w);
   uint32_t tx = tile % ntx, ty = tile / ntx;
   uint32_t slot = off + (ty - (rxy >> 16)) * (rwh & 0xffffu) + (tx - (rxy & 0xffffu));
@@ -207,18 +210,18 @@ extern "C" int gs_gather(const int* tile_n_point_accum, const int* tile_gaussian
   return 0;
 }
 
-cudaError_t gs_launch_emit_keys(GsRec* rec, const uint32_t* perm, const uint32_t* offsets_sorted, int n, int ntx,
-                                uint16_t* keys, uint32_t* vals, cudaStream_t st) {
+cudaError_t gs_launch_emit_keys(const GsRec* rec, const uint32_t* perm, const uint32_t* offsets_sorted, int n, int ntx,
+                                uint32_t* keys, uint32_t* vals, cudaStream_t st) {
   if (n == 0) return cudaSuccess;
   emit_keys_kernel<<<(n + kBlock - 1) / kBlock, kBlock, 0, st>>>(rec, perm, offsets_sorted, n, ntx, keys, vals);
   return cudaGetLastError();
 }
 
-cudaError_t gs_launch_pack_sorted(const uint16_t* keys, const uint32_t* vals, long long m, int n_tiles, int ntx,
-                                  const GsRec* rec, float4* pA, float2* pB, float4* pC, int* tile_accum,
-                                  cudaStream_t st) {
+cudaError_t gs_launch_pack_sorted(const uint32_t* keys, const uint32_t* vals, long long m, int n_tiles, int ntx,
+                                  const GsRec* rec, const uint32_t* offsets_g, float4* pA, float2* pB, float4* pC,
+                                  int* tile_accum, cudaStream_t st) {
   if (m == 0) return cudaMemsetAsync(tile_accum, 0, sizeof(int) * (size_t)(n_tiles + 1), st);
   pack_sorted_kernel<<<(unsigned)((m + kBlock - 1) / kBlock), kBlock, 0, st>>>(
-      keys, vals, m, n_tiles, ntx, rec, pA, pB, pC, tile_accum);
+      keys, vals, m, n_tiles, ntx, rec, offsets_g, pA, pB, pC, tile_accum);
   return cudaGetLastError();
 }

@@ -21,8 +21,9 @@ namespace {
 // =======================================================================================
 // forward
 // =======================================================================================
-constexpr int FWD_THREADS = 256;
-constexpr int FWD_CH = 256;
+constexpr int FWD_THREADS = 64;    // 2 warps per tile; each thread owns a row of 4 adjacent pixels
+constexpr int FWD_PX = 4;
+constexpr int FWD_CH = 128;
 constexpr int FWD_STAGES = 2;
 
 struct FwdSmem {
@@ -45,6 +46,9 @@ __device__ __forceinline__ void issue_chunk(SM& sm, int stage, const float4* __r
   gs_bulk_g2s(sm.B[stage], pB + (base - shift), bytes_b, &sm.full[stage]);
 }
 
+// Per (thread, instance): 3 broadcast LDS + 4 row-shared FP32 ops (dy, cb*dy, cc*dy, l2o-cc*dy^2)
+// + 4 pixels x (dx, u, exponent, MUFU.EX2, setp, mul, sel, 3 FFMA colour, T update) = 12.75
+// issue slots per (pixel, instance) instead of 17-18 with one pixel per thread.
 __global__ void __launch_bounds__(FWD_THREADS) blend_fwd_kernel(const float4* __restrict__ pA,
                                                                  const float2* __restrict__ pB,
                                                                  const float4* __restrict__ pC,
@@ -54,12 +58,14 @@ __global__ void __launch_bounds__(FWD_THREADS) blend_fwd_kernel(const float4* __
                                                                  int* __restrict__ tile_neff) {
   __shared__ __align__(16) FwdSmem sm;
   const int tile = blockIdx.x;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x;
   const int tx = tile % ntx, ty = tile / ntx;
-  // warp = 8x4 pixel block of the 16x16 tile
-  const int ix = tx * GS_TILE + (warp & 1) * 8 + (lane & 7);
-  const int iy = ty * GS_TILE + (warp >> 1) * 4 + (lane >> 3);
-  const float px = gs_pixel_coord(ix, wp, fx);
+  // thread -> pixels (ix0 .. ix0+3, iy); warp 0 = tile rows 0-7, warp 1 = rows 8-15
+  const int ix0 = tx * GS_TILE + (tid & 3) * FWD_PX;
+  const int iy = ty * GS_TILE + (tid >> 2);
+  float px[FWD_PX];
+#pragma unroll
+  for (int p = 0; p < FWD_PX; ++p) px[p] = gs_pixel_coord(ix0 + p, wp, fx);
   const float py = gs_pixel_coord(iy, hp, fy);
 
   const int start = tile_accum[tile];
@@ -77,7 +83,12 @@ __global__ void __launch_bounds__(FWD_THREADS) blend_fwd_kernel(const float4* __
       issue_chunk<FwdSmem, FWD_CH>(sm, k, pA, pB, pC, start + k * FWD_CH, min(FWD_CH, cnt - k * FWD_CH), shift);
   }
 
-  float T = 1.f, cr = 0.f, cg = 0.f, cb = 0.f;
+  float T[FWD_PX], cr[FWD_PX], cg[FWD_PX], cb[FWD_PX];
+#pragma unroll
+  for (int p = 0; p < FWD_PX; ++p) {
+    T[p] = 1.f;
+    cr[p] = cg[p] = cb[p] = 0.f;
+  }
   int consumed = cnt;
   int k = 0;
   for (; k < nchunks; ++k) {
@@ -88,27 +99,32 @@ __global__ void __launch_bounds__(FWD_THREADS) blend_fwd_kernel(const float4* __
     const float4* __restrict__ sC = sm.C[stage];
     const float2* __restrict__ sB = sm.B[stage] + shift;
 
-#define GS_FWD_BODY(J)                                                        \
-  {                                                                           \
-    const float4 a = sA[J];                                                   \
-    const float2 b = sB[J];                                                   \
-    const float4 c = sC[J];                                                   \
-    const float dx = px - a.x, dy = py - a.y;                                 \
-    const float eu = fmaf(a.z, dx, -a.w * dy);                                \
-    const float ev = fmaf(-b.x * dy, dy, b.y);                                \
-    const float alpha = gs_ex2(fmaf(-dx, eu, ev)); /* l2o - (ca dx^2 - cb dx dy + cc dy^2) */ \
-    const float w = (T > GS_T_STOP) ? alpha * T : 0.f;                        \
-    cr = fmaf(c.x, w, cr);                                                    \
-    cg = fmaf(c.y, w, cg);                                                    \
-    cb = fmaf(c.z, w, cb);                                                    \
-    T -= w;                                                                   \
+#define GS_FWD_BODY(J)                                                                      \
+  {                                                                                         \
+    const float4 a = sA[J];                                                                 \
+    const float2 b = sB[J];                                                                 \
+    const float4 c = sC[J];                                                                 \
+    const float dy = py - a.y;                                                              \
+    const float m1 = a.w * dy;                                                              \
+    const float ev = fmaf(-b.x * dy, dy, b.y);                                              \
+    _Pragma("unroll") for (int p = 0; p < FWD_PX; ++p) {                                    \
+      const float dx = px[p] - a.x;                                                         \
+      const float eu = fmaf(a.z, dx, -m1);                                                  \
+      const float alpha = gs_ex2(fmaf(-dx, eu, ev)); /* l2o - (ca dx^2 - cb dx dy + cc dy^2) */ \
+      const float w = (T[p] > GS_T_STOP) ? alpha * T[p] : 0.f;                              \
+      cr[p] = fmaf(c.x, w, cr[p]);                                                          \
+      cg[p] = fmaf(c.y, w, cg[p]);                                                          \
+      cb[p] = fmaf(c.z, w, cb[p]);                                                          \
+      T[p] -= w;                                                                            \
+    }                                                                                       \
   }
     int j = 0;
     bool warp_dead = false;
-    for (; j + 8 <= n; j += 8) {
+    for (; j + 4 <= n; j += 4) {
 #pragma unroll
-      for (int u = 0; u < 8; ++u) GS_FWD_BODY(j + u)
-      if (__all_sync(0xffffffffu, !(T > GS_T_STOP))) {
+      for (int u = 0; u < 4; ++u) GS_FWD_BODY(j + u)
+      const bool dead = !(T[0] > GS_T_STOP) && !(T[1] > GS_T_STOP) && !(T[2] > GS_T_STOP) && !(T[3] > GS_T_STOP);
+      if (__all_sync(0xffffffffu, dead)) {
         warp_dead = true;
         break;
       }
@@ -117,7 +133,8 @@ __global__ void __launch_bounds__(FWD_THREADS) blend_fwd_kernel(const float4* __
       for (; j < n; ++j) GS_FWD_BODY(j)
 #undef GS_FWD_BODY
 
-    const int all_dead = __syncthreads_and(!(T > GS_T_STOP));
+    const bool dead = !(T[0] > GS_T_STOP) && !(T[1] > GS_T_STOP) && !(T[2] > GS_T_STOP) && !(T[3] > GS_T_STOP);
+    const int all_dead = __syncthreads_and(dead);
     if (all_dead) {
       consumed = min(cnt, (k + 1) * FWD_CH);
       break;
@@ -132,10 +149,11 @@ __global__ void __launch_bounds__(FWD_THREADS) blend_fwd_kernel(const float4* __
     for (int kk = k + 1; kk < nchunks && kk < k + FWD_STAGES; ++kk)
       gs_mbar_wait(&sm.full[kk % FWD_STAGES], (uint32_t)((kk / FWD_STAGES) & 1));
   }
-  float* o = image + ((size_t)iy * wp + ix) * 3;
-  o[0] = cr;
-  o[1] = cg;
-  o[2] = cb;
+  // 4 pixels x 3 channels = 48 contiguous, 16-byte aligned bytes
+  float4* o = reinterpret_cast<float4*>(image + ((size_t)iy * wp + ix0) * 3);
+  o[0] = make_float4(cr[0], cg[0], cb[0], cr[1]);
+  o[1] = make_float4(cg[1], cb[1], cr[2], cg[2]);
+  o[2] = make_float4(cb[2], cr[3], cg[3], cb[3]);
   if (tile_neff && tid == 0) tile_neff[tile] = consumed;
 }
 
@@ -173,24 +191,30 @@ __global__ void __launch_bounds__(BWD_THREADS) blend_bwd_kernel(const float4* __
   const int shift = start & 1;
   const int nchunks = (cnt + BWD_CH - 1) / BWD_CH;
 
-  // thread -> 2x2 pixel block
-  const int ix0 = tx * GS_TILE + (tid & 7) * 2;
-  const int iy0 = ty * GS_TILE + (tid >> 3) * 2;
-  float px[2], py[2];
-  px[0] = gs_pixel_coord(ix0, wp, fx);
-  px[1] = gs_pixel_coord(ix0 + 1, wp, fx);
-  py[0] = gs_pixel_coord(iy0, hp, fy);
-  py[1] = gs_pixel_coord(iy0 + 1, hp, fy);
+  // thread -> a row of 4 adjacent pixels (ix0..ix0+3, iy): dy and the dy-only terms of the
+  // exponent are shared by the 4 pixels
+  const int ix0 = tx * GS_TILE + (tid & 3) * 4;
+  const int iy = ty * GS_TILE + (tid >> 2);
+  float px[4];
+#pragma unroll
+  for (int p = 0; p < 4; ++p) px[p] = gs_pixel_coord(ix0 + p, wp, fx);
+  const float py = gs_pixel_coord(iy, hp, fy);
 
   float T[4], R[4], gr[4], gg[4], gb[4];
+  {
+    const size_t off = ((size_t)iy * wp + ix0) * 3;     // 48 contiguous, 16-byte aligned bytes
+    const float4* gi = reinterpret_cast<const float4*>(grad_image + off);
+    const float4* im = reinterpret_cast<const float4*>(image + off);
+    const float4 g0 = gi[0], g1 = gi[1], g2 = gi[2], i0 = im[0], i1 = im[1], i2 = im[2];
+    gr[0] = g0.x; gg[0] = g0.y; gb[0] = g0.z; gr[1] = g0.w;
+    gg[1] = g1.x; gb[1] = g1.y; gr[2] = g1.z; gg[2] = g1.w;
+    gb[2] = g2.x; gr[3] = g2.y; gg[3] = g2.z; gb[3] = g2.w;
+    R[0] = gr[0] * i0.x + gg[0] * i0.y + gb[0] * i0.z;
+    R[1] = gr[1] * i0.w + gg[1] * i1.x + gb[1] * i1.y;
+    R[2] = gr[2] * i1.z + gg[2] * i1.w + gb[2] * i2.x;
+    R[3] = gr[3] * i2.y + gg[3] * i2.z + gb[3] * i2.w;
 #pragma unroll
-  for (int p = 0; p < 4; ++p) {
-    const size_t off = ((size_t)(iy0 + (p >> 1)) * wp + (ix0 + (p & 1))) * 3;
-    gr[p] = grad_image[off];
-    gg[p] = grad_image[off + 1];
-    gb[p] = grad_image[off + 2];
-    R[p] = gr[p] * image[off] + gg[p] * image[off + 1] + gb[p] * image[off + 2];
-    T[p] = 1.f;
+    for (int p = 0; p < 4; ++p) T[p] = 1.f;
   }
 
   if (tid == 0) {
@@ -227,11 +251,13 @@ __global__ void __launch_bounds__(BWD_THREADS) blend_bwd_kernel(const float4* __
 #pragma unroll
       for (int u = 0; u < 8; ++u) v[u] = 0.f;
       float v8 = 0.f;
+      const float dy = py - a.y;
+      const float m1 = a.w * dy;
+      const float ev = fmaf(-b.x * dy, dy, b.y);
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
-        const float dx = px[p & 1] - a.x, dy = py[p >> 1] - a.y;
-        const float eu = fmaf(a.z, dx, -a.w * dy);
-        const float ev = fmaf(-b.x * dy, dy, b.y);
+        const float dx = px[p] - a.x;
+        const float eu = fmaf(a.z, dx, -m1);
         const float alpha = gs_ex2(fmaf(-dx, eu, ev));   // l2o - (ca dx^2 - cb dx dy + cc dy^2)
         const bool live = T[p] > GS_T_STOP;
         const float w = live ? alpha * T[p] : 0.f;

@@ -24,17 +24,17 @@ cudaError_t gs_launch_fused_project(const float* pos, const float* rgb, const fl
 
 cudaError_t gs_launch_fused_project_bwd(const float* pos, const float* rgb, const float* opa, const float* quat,
                                         const float* scale, int n, int scale_act, const GsCam& cam,
-                                        float near_plane, float half_w, float half_h, const GsRec* rec,
+                                        float near_plane, float half_w, float half_h, const uint32_t* offsets_g,
                                         const uint32_t* count, const float* grad_inst, float* g_pos, float* g_rgb, float* g_opa,
                                         float* g_quat, float* g_scale, cudaStream_t st);
 
 // ---- binning.cu ------------------------------------------------------------------------
-cudaError_t gs_launch_emit_keys(GsRec* rec, const uint32_t* perm, const uint32_t* offsets_sorted, int n, int ntx,
-                                uint16_t* keys, uint32_t* vals, cudaStream_t st);
+cudaError_t gs_launch_emit_keys(const GsRec* rec, const uint32_t* perm, const uint32_t* offsets_sorted, int n, int ntx,
+                                uint32_t* keys, uint32_t* vals, cudaStream_t st);
 
-cudaError_t gs_launch_pack_sorted(const uint16_t* keys, const uint32_t* vals, long long m, int n_tiles, int ntx,
-                                  const GsRec* rec, float4* pA, float2* pB, float4* pC, int* tile_accum,
-                                  cudaStream_t st);
+cudaError_t gs_launch_pack_sorted(const uint32_t* keys, const uint32_t* vals, long long m, int n_tiles, int ntx,
+                                  const GsRec* rec, const uint32_t* offsets_g, float4* pA, float2* pB, float4* pC,
+                                  int* tile_accum, cudaStream_t st);
 
 cudaError_t gs_launch_iota(uint32_t* out, int n, cudaStream_t st);
 

@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(kBlock) fused_project_kernel(
 __global__ void __launch_bounds__(kBlock) fused_project_bwd_kernel(
     const float* __restrict__ pos, const float* __restrict__ rgb, const float* __restrict__ opa,
     const float* __restrict__ quat, const float* __restrict__ scale, int n, int scale_act, GsCam cam,
-    float near_plane, float half_w, float half_h, const GsRec* __restrict__ rec,
+    float near_plane, float half_w, float half_h, const uint32_t* __restrict__ offsets_g,
     const uint32_t* __restrict__ count, const float* __restrict__ grad_inst, float* __restrict__ g_pos, float* __restrict__ g_rgb,
     float* __restrict__ g_opa, float* __restrict__ g_quat, float* __restrict__ g_scale) {
   int i = blockIdx.x * kBlock + threadIdx.x;
@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(kBlock) fused_project_bwd_kernel(
   float go = 0.f, gcol[3] = {0.f, 0.f, 0.f};
   const uint32_t cnt = count[i];
   if (cnt > 0) {
-    const uint32_t o0 = rec[i].d.x, o1 = o0 + cnt;   // this Gaussian's contiguous gradient rows
+    const uint32_t o0 = offsets_g[i], o1 = o0 + cnt;   // this Gaussian's contiguous gradient rows
     float acc[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) acc[k] = 0.f;
@@ -307,12 +307,12 @@ cudaError_t gs_launch_fused_project(const float* pos, const float* rgb, const fl
 
 cudaError_t gs_launch_fused_project_bwd(const float* pos, const float* rgb, const float* opa, const float* quat,
                                         const float* scale, int n, int scale_act, const GsCam& cam,
-                                        float near_plane, float half_w, float half_h, const GsRec* rec,
+                                        float near_plane, float half_w, float half_h, const uint32_t* offsets_g,
                                         const uint32_t* count, const float* grad_inst, float* g_pos, float* g_rgb, float* g_opa,
                                         float* g_quat, float* g_scale, cudaStream_t st) {
   if (n == 0) return cudaSuccess;
   fused_project_bwd_kernel<<<grid_for(n), kBlock, 0, st>>>(pos, rgb, opa, quat, scale, n, scale_act, cam, near_plane,
-                                                           half_w, half_h, rec, count, grad_inst, g_pos, g_rgb, g_opa,
+                                                           half_w, half_h, offsets_g, count, grad_inst, g_pos, g_rgb, g_opa,
                                                            g_quat, g_scale);
   return cudaGetLastError();
 }

@@ -70,7 +70,7 @@ struct DevBuf {
 struct gs_ctx {
   int device = 0;
   // per Gaussian
-  DevBuf rec, count, offsets, dkey_in, dkey_out, perm, iota;
+  DevBuf rec, count, offsets, dkey_in, dkey_out, perm, iota, offsets_g;
   size_t iota_n = 0;
   // per instance
   DevBuf keys_in, keys_out, vals_in, vals_out, pA, pB, pC, grad_inst;
@@ -117,7 +117,7 @@ extern "C" int gs_ctx_create(gs_ctx** out) {
 extern "C" void gs_ctx_destroy(gs_ctx* c) {
   if (!c) return;
   cudaDeviceSynchronize();
-  DevBuf* bufs[] = {&c->rec, &c->count, &c->offsets, &c->dkey_in, &c->dkey_out, &c->perm, &c->iota, &c->keys_in, &c->keys_out,
+  DevBuf* bufs[] = {&c->rec, &c->count, &c->offsets, &c->dkey_in, &c->dkey_out, &c->perm, &c->iota, &c->offsets_g, &c->keys_in, &c->keys_out,
                     &c->vals_in, &c->vals_out, &c->pA, &c->pB, &c->pC, &c->grad_inst, &c->tile_accum, &c->tile_neff,
                     &c->cub_tmp, &c->counters, &c->img_dev, &c->gimg_dev};
   for (DevBuf* b : bufs) b->release();
@@ -153,7 +153,7 @@ extern "C" int gs_render_forward(gs_ctx* c, const float* pos, const float* rgb, 
   g.n_tiles = g.ntx * g.nty;
   g.fx = cam->focal_x;
   g.fy = cam->focal_y;
-  if (g.n_tiles > 65536) return gs_set_error_msg(GS_ERR_UNSUPPORTED, "gs_render_forward: more than 65536 tiles");
+  if (g.ntx > 65535 || g.nty > 65535) return gs_set_error_msg(GS_ERR_INVALID_ARG, "gs_render_forward: image too large");
 
   // Host scalars are formed in double then narrowed, like the Python floats that the reference
   // passes through pybind (splatter.py:279-282, :532-533).
@@ -178,6 +178,7 @@ extern "C" int gs_render_forward(gs_ctx* c, const float* pos, const float* rgb, 
   GS_CUDA_TRY(c->dkey_in.reserve(N * 4 + 4, st));
   GS_CUDA_TRY(c->dkey_out.reserve(N * 4 + 4, st));
   GS_CUDA_TRY(c->perm.reserve(N * 4 + 4, st));
+  GS_CUDA_TRY(c->offsets_g.reserve((N + 1) * 4, st));
   GS_CUDA_TRY(c->tile_accum.reserve((size_t)(g.n_tiles + 1) * 4, st));
   GS_CUDA_TRY(c->tile_neff.reserve((size_t)g.n_tiles * 4, st));
   GS_CUDA_TRY(c->counters.reserve(64, st));
@@ -191,13 +192,15 @@ extern "C" int gs_render_forward(gs_ctx* c, const float* pos, const float* rgb, 
   c->ev_fwd_valid = false;
   gs_mark(c, 0, st);
   GS_CUDA_TRY(cudaMemsetAsync(c->counters.p, 0, 64, st));
+  GS_CUDA_TRY(cudaMemsetAsync(c->count.as<uint32_t>() + N, 0, 4, st));
   GS_CUDA_TRY(gs_launch_fused_project(pos, rgb, opa, quat, scale, n, scale_activation, dc, grid, cam->near_plane,
                                       half_w, half_h, c->rec.as<GsRec>(), c->count.as<uint32_t>(),
                                       c->dkey_in.as<uint32_t>(), culling_mask, c->counters.as<unsigned int>(), st));
-  // 2. stable depth sort of the N Gaussians, then exclusive scan of their tile counts in that
-  //    order (N+1 items: offsets[N] = M); the count gather is fused into the scan's input iterator
+  // 2. (a) exclusive scan of the tile counts in Gaussian-id order -> gradient-row bases and M;
+  //    (b) stable depth sort of the N Gaussians; (c) scan of the counts in depth order (the
+  //    count gather is fused into the scan's input iterator) -> instance emission offsets
   gs_mark(c, 1, st);
-  size_t tmp_bytes = 0, tmp2 = 0;
+  size_t tmp_bytes = 0, tmp2 = 0, tmp3 = 0;
   if (n > 0)
     GS_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, c->dkey_in.as<uint32_t>(),
                                                 c->dkey_out.as<uint32_t>(), c->iota.as<uint32_t>(),
@@ -207,7 +210,13 @@ extern "C" int gs_render_forward(gs_ctx* c, const float* pos, const float* rgb, 
   cub::TransformInputIterator<uint32_t, GsCountInSortedOrder, cub::CountingInputIterator<uint32_t>> cnt_it(idx_it,
                                                                                                             cnt_it_fn);
   GS_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp2, cnt_it, c->offsets.as<uint32_t>(), n + 1, st));
-  GS_CUDA_TRY(c->cub_tmp.reserve(tmp_bytes > tmp2 ? tmp_bytes : tmp2, st));
+  GS_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp3, c->count.as<uint32_t>(), c->offsets_g.as<uint32_t>(),
+                                            n + 1, st));
+  if (tmp2 > tmp_bytes) tmp_bytes = tmp2;
+  if (tmp3 > tmp_bytes) tmp_bytes = tmp3;
+  GS_CUDA_TRY(c->cub_tmp.reserve(tmp_bytes, st));
+  GS_CUDA_TRY(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp3, c->count.as<uint32_t>(), c->offsets_g.as<uint32_t>(),
+                                            n + 1, st));
   if (n > 0)
     GS_CUDA_TRY(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp_bytes, c->dkey_in.as<uint32_t>(),
                                                 c->dkey_out.as<uint32_t>(), c->iota.as<uint32_t>(),
@@ -226,32 +235,32 @@ extern "C" int gs_render_forward(gs_ctx* c, const float* pos, const float* rgb, 
   GS_CUDA_TRY(c->pC.reserve(M * 16 + 16, st));
   GS_CUDA_TRY(c->pB.reserve((M + 2) * 8, st));
   if (m > 0) {
-    GS_CUDA_TRY(c->keys_in.reserve(M * 2 + 16, st));
-    GS_CUDA_TRY(c->keys_out.reserve(M * 2 + 16, st));
+    GS_CUDA_TRY(c->keys_in.reserve(M * 4 + 16, st));
+    GS_CUDA_TRY(c->keys_out.reserve(M * 4 + 16, st));
     GS_CUDA_TRY(c->vals_in.reserve(M * 4, st));
     GS_CUDA_TRY(c->vals_out.reserve(M * 4, st));
     // 3. instances in (depth, id) order: tile-id keys + Gaussian-id values
     GS_CUDA_TRY(gs_launch_emit_keys(c->rec.as<GsRec>(), c->perm.as<uint32_t>(), c->offsets.as<uint32_t>(), n, g.ntx,
-                                    c->keys_in.as<uint16_t>(), c->vals_in.as<uint32_t>(), st));
+                                    c->keys_in.as<uint32_t>(), c->vals_in.as<uint32_t>(), st));
     // 4. stable radix sort on the tile id only -> (tile, depth, id)
     gs_mark(c, 3, st);
     int end_bit = ceil_log2((unsigned)g.n_tiles);
     if (end_bit < 1) end_bit = 1;
     size_t sort_tmp = 0;
-    GS_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, c->keys_in.as<uint16_t>(),
-                                                c->keys_out.as<uint16_t>(), c->vals_in.as<uint32_t>(),
+    GS_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, c->keys_in.as<uint32_t>(),
+                                                c->keys_out.as<uint32_t>(), c->vals_in.as<uint32_t>(),
                                                 c->vals_out.as<uint32_t>(), (int)m, 0, end_bit, st));
     GS_CUDA_TRY(c->cub_tmp.reserve(sort_tmp, st));
-    GS_CUDA_TRY(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, sort_tmp, c->keys_in.as<uint16_t>(),
-                                                c->keys_out.as<uint16_t>(), c->vals_in.as<uint32_t>(),
+    GS_CUDA_TRY(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, sort_tmp, c->keys_in.as<uint32_t>(),
+                                                c->keys_out.as<uint32_t>(), c->vals_in.as<uint32_t>(),
                                                 c->vals_out.as<uint32_t>(), (int)m, 0, end_bit, st));
   }
   // 5. tile ranges + packed sorted record streams
   if (m == 0) gs_mark(c, 3, st);
   gs_mark(c, 4, st);
-  GS_CUDA_TRY(gs_launch_pack_sorted(c->keys_out.as<uint16_t>(), c->vals_out.as<uint32_t>(), m, g.n_tiles, g.ntx,
-                                    c->rec.as<GsRec>(), c->pA.as<float4>(), c->pB.as<float2>(),
-                                    c->pC.as<float4>(), c->tile_accum.as<int>(), st));
+  GS_CUDA_TRY(gs_launch_pack_sorted(c->keys_out.as<uint32_t>(), c->vals_out.as<uint32_t>(), m, g.n_tiles, g.ntx,
+                                    c->rec.as<GsRec>(), c->offsets_g.as<uint32_t>(), c->pA.as<float4>(),
+                                    c->pB.as<float2>(), c->pC.as<float4>(), c->tile_accum.as<int>(), st));
   // 6. blend
   gs_mark(c, 5, st);
   GS_CUDA_TRY(gs_launch_blend_fwd(c->pA.as<float4>(), c->pB.as<float2>(), c->pC.as<float4>(), c->tile_accum.as<int>(),
@@ -290,7 +299,7 @@ extern "C" int gs_render_backward(gs_ctx* c, const float* pos, const float* rgb,
                                     st));
   gs_mark(c, 8, st);
   GS_CUDA_TRY(gs_launch_fused_project_bwd(pos, rgb, opa, quat, scale, c->n, c->scale_act, c->cam, c->near_plane,
-                                          c->half_w, c->half_h, c->rec.as<GsRec>(), c->count.as<uint32_t>(),
+                                          c->half_w, c->half_h, c->offsets_g.as<uint32_t>(), c->count.as<uint32_t>(),
                                           c->grad_inst.as<float>(),
                                           grad_pos, grad_rgb, grad_opa, grad_quat, grad_scale, st));
   gs_mark(c, 9, st);
