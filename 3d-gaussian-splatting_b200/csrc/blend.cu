@@ -14,6 +14,8 @@
 //   * backward: 64 threads x 4 pixels per tile; 9 moment sums per instance are reduced with a
 //     recursive-halving shuffle network (14 SHFL instead of 45), combined across the two warps
 //     through shared memory and written as ONE record per instance (no atomics, deterministic).
+#include <cstdlib>
+
 #include "internal.h"
 
 namespace {
@@ -160,28 +162,37 @@ __global__ void __launch_bounds__(FWD_THREADS) blend_fwd_kernel(const float4* __
 // =======================================================================================
 // backward
 // =======================================================================================
-constexpr int BWD_THREADS = 64;
 constexpr int BWD_CH = 64;
 constexpr int BWD_STAGES = 2;
 constexpr int BWD_NV = 9;   // Sx Sy Sxx Sxy Syy S0 Cr Cg | Cb
 
+template <int WARPS>
 struct BwdSmem {
   float4 A[BWD_STAGES][BWD_CH];
   float4 C[BWD_STAGES][BWD_CH];
   float2 B[BWD_STAGES][BWD_CH + 2];
   uint64_t full[BWD_STAGES];
-  float partial[2][BWD_CH * BWD_NV];
+  float partial[WARPS][BWD_CH * BWD_NV];
 };
 
-__global__ void __launch_bounds__(BWD_THREADS) blend_bwd_kernel(const float4* __restrict__ pA,
-                                                                 const float2* __restrict__ pB,
-                                                                 const float4* __restrict__ pC,
-                                                                 const int* __restrict__ tile_accum, int wp, int hp,
-                                                                 int ntx, float fx, float fy,
-                                                                 const float* __restrict__ image,
-                                                                 const float* __restrict__ grad_image,
-                                                                 float* __restrict__ grad_inst) {
-  __shared__ __align__(16) BwdSmem sm;
+// WARPS warps per tile; every thread owns a row of PX = 8 / WARPS ... i.e. 256 / (32*WARPS)
+// horizontally adjacent pixels, so dy and every dy-only factor is shared by its pixels:
+// per pixel only S0 += e, Sx += e dx, Sxx += e dx^2 are accumulated and
+// Sy = dy S0, Sxy = dy Sx, Syy = dy^2 S0 are formed once per (thread, instance).
+template <int WARPS>
+__global__ void __launch_bounds__(32 * WARPS) blend_bwd_kernel(const float4* __restrict__ pA,
+                                                                const float2* __restrict__ pB,
+                                                                const float4* __restrict__ pC,
+                                                                const int* __restrict__ tile_accum, int wp, int hp,
+                                                                int ntx, float fx, float fy,
+                                                                const float* __restrict__ image,
+                                                                const float* __restrict__ grad_image,
+                                                                float* __restrict__ grad_inst) {
+  constexpr int THREADS = 32 * WARPS;
+  constexpr int PX = 256 / THREADS;          // 8 (1 warp) or 4 (2 warps)
+  constexpr int TPR = GS_TILE / PX;          // threads per pixel row
+  using Smem = BwdSmem<WARPS>;
+  __shared__ __align__(16) Smem sm;
   const int tile = blockIdx.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tx = tile % ntx, ty = tile / ntx;
@@ -191,30 +202,33 @@ __global__ void __launch_bounds__(BWD_THREADS) blend_bwd_kernel(const float4* __
   const int shift = start & 1;
   const int nchunks = (cnt + BWD_CH - 1) / BWD_CH;
 
-  // thread -> a row of 4 adjacent pixels (ix0..ix0+3, iy): dy and the dy-only terms of the
-  // exponent are shared by the 4 pixels
-  const int ix0 = tx * GS_TILE + (tid & 3) * 4;
-  const int iy = ty * GS_TILE + (tid >> 2);
-  float px[4];
+  const int ix0 = tx * GS_TILE + (tid % TPR) * PX;
+  const int iy = ty * GS_TILE + (tid / TPR);
+  float px[PX];
 #pragma unroll
-  for (int p = 0; p < 4; ++p) px[p] = gs_pixel_coord(ix0 + p, wp, fx);
+  for (int p = 0; p < PX; ++p) px[p] = gs_pixel_coord(ix0 + p, wp, fx);
   const float py = gs_pixel_coord(iy, hp, fy);
 
-  float T[4], R[4], gr[4], gg[4], gb[4];
+  float T[PX], R[PX], gr[PX], gg[PX], gb[PX];
   {
-    const size_t off = ((size_t)iy * wp + ix0) * 3;     // 48 contiguous, 16-byte aligned bytes
+    const size_t off = ((size_t)iy * wp + ix0) * 3;     // PX*12 contiguous, 16-byte aligned bytes
     const float4* gi = reinterpret_cast<const float4*>(grad_image + off);
     const float4* im = reinterpret_cast<const float4*>(image + off);
-    const float4 g0 = gi[0], g1 = gi[1], g2 = gi[2], i0 = im[0], i1 = im[1], i2 = im[2];
-    gr[0] = g0.x; gg[0] = g0.y; gb[0] = g0.z; gr[1] = g0.w;
-    gg[1] = g1.x; gb[1] = g1.y; gr[2] = g1.z; gg[2] = g1.w;
-    gb[2] = g2.x; gr[3] = g2.y; gg[3] = g2.z; gb[3] = g2.w;
-    R[0] = gr[0] * i0.x + gg[0] * i0.y + gb[0] * i0.z;
-    R[1] = gr[1] * i0.w + gg[1] * i1.x + gb[1] * i1.y;
-    R[2] = gr[2] * i1.z + gg[2] * i1.w + gb[2] * i2.x;
-    R[3] = gr[3] * i2.y + gg[3] * i2.z + gb[3] * i2.w;
+    float gbuf[PX * 3], ibuf[PX * 3];
 #pragma unroll
-    for (int p = 0; p < 4; ++p) T[p] = 1.f;
+    for (int q = 0; q < PX * 3 / 4; ++q) {
+      const float4 g4 = gi[q], i4 = im[q];
+      gbuf[4 * q] = g4.x; gbuf[4 * q + 1] = g4.y; gbuf[4 * q + 2] = g4.z; gbuf[4 * q + 3] = g4.w;
+      ibuf[4 * q] = i4.x; ibuf[4 * q + 1] = i4.y; ibuf[4 * q + 2] = i4.z; ibuf[4 * q + 3] = i4.w;
+    }
+#pragma unroll
+    for (int p = 0; p < PX; ++p) {
+      gr[p] = gbuf[3 * p];
+      gg[p] = gbuf[3 * p + 1];
+      gb[p] = gbuf[3 * p + 2];
+      R[p] = gr[p] * ibuf[3 * p] + gg[p] * ibuf[3 * p + 1] + gb[p] * ibuf[3 * p + 2];
+      T[p] = 1.f;
+    }
   }
 
   if (tid == 0) {
@@ -224,7 +238,7 @@ __global__ void __launch_bounds__(BWD_THREADS) blend_bwd_kernel(const float4* __
   __syncthreads();
   if (tid == 0) {
     for (int k = 0; k < BWD_STAGES && k < nchunks; ++k)
-      issue_chunk<BwdSmem, BWD_CH>(sm, k, pA, pB, pC, start + k * BWD_CH, min(BWD_CH, cnt - k * BWD_CH), shift);
+      issue_chunk<Smem, BWD_CH>(sm, k, pA, pB, pC, start + k * BWD_CH, min(BWD_CH, cnt - k * BWD_CH), shift);
   }
 
   int consumed = cnt;
@@ -241,21 +255,20 @@ __global__ void __launch_bounds__(BWD_THREADS) blend_bwd_kernel(const float4* __
     int j = 0;
     for (; j < n; ++j) {
       if ((j & 3) == 0) {
-        const bool dead = !(T[0] > GS_T_STOP) && !(T[1] > GS_T_STOP) && !(T[2] > GS_T_STOP) && !(T[3] > GS_T_STOP);
+        bool dead = true;
+#pragma unroll
+        for (int p = 0; p < PX; ++p) dead = dead && !(T[p] > GS_T_STOP);
         if (__all_sync(0xffffffffu, dead)) break;
       }
       const float4 a = sA[j];
       const float2 b = sB[j];
       const float4 c = sC[j];
-      float v[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) v[u] = 0.f;
-      float v8 = 0.f;
+      float s0 = 0.f, sx = 0.f, sxx = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
       const float dy = py - a.y;
       const float m1 = a.w * dy;
       const float ev = fmaf(-b.x * dy, dy, b.y);
 #pragma unroll
-      for (int p = 0; p < 4; ++p) {
+      for (int p = 0; p < PX; ++p) {
         const float dx = px[p] - a.x;
         const float eu = fmaf(a.z, dx, -m1);
         const float alpha = gs_ex2(fmaf(-dx, eu, ev));   // l2o - (ca dx^2 - cb dx dy + cc dy^2)
@@ -267,17 +280,24 @@ __global__ void __launch_bounds__(BWD_THREADS) blend_bwd_kernel(const float4* __
         const float dal = fmaf(T[p], gc, -R[p] * rc);                // d L / d alpha            (:710-722)
         const float e = live ? dal * alpha : 0.f;
         T[p] -= w;
-        const float ex = e * dx, ey = e * dy;
-        v[0] += ex;
-        v[1] += ey;
-        v[2] = fmaf(ex, dx, v[2]);
-        v[3] = fmaf(ex, dy, v[3]);
-        v[4] = fmaf(ey, dy, v[4]);
-        v[5] += e;
-        v[6] = fmaf(gr[p], w, v[6]);
-        v[7] = fmaf(gg[p], w, v[7]);
-        v8 = fmaf(gb[p], w, v8);
+        const float ex = e * dx;
+        s0 += e;
+        sx += ex;
+        sxx = fmaf(ex, dx, sxx);
+        c0 = fmaf(gr[p], w, c0);
+        c1 = fmaf(gg[p], w, c1);
+        c2 = fmaf(gb[p], w, c2);
       }
+      float v[8];
+      v[0] = sx;
+      v[1] = dy * s0;
+      v[2] = sxx;
+      v[3] = dy * sx;
+      v[4] = dy * v[1];
+      v[5] = s0;
+      v[6] = c0;
+      v[7] = c1;
+      float v8 = c2;
       // recursive-halving reduction of v[0..7] over the warp, plain butterfly for v8
       {
         const bool up = (lane & 16) != 0;
@@ -315,10 +335,14 @@ __global__ void __launch_bounds__(BWD_THREADS) blend_bwd_kernel(const float4* __
     for (int z = j * BWD_NV + lane; z < n * BWD_NV; z += 32) part[z] = 0.f;
     __syncthreads();
 
-    for (int t = tid; t < n; t += BWD_THREADS) {
+    for (int t = tid; t < n; t += THREADS) {
       float s[BWD_NV];
 #pragma unroll
-      for (int u = 0; u < BWD_NV; ++u) s[u] = sm.partial[0][t * BWD_NV + u] + sm.partial[1][t * BWD_NV + u];
+      for (int u = 0; u < BWD_NV; ++u) {
+        s[u] = sm.partial[0][t * BWD_NV + u];
+#pragma unroll
+        for (int w2 = 1; w2 < WARPS; ++w2) s[u] += sm.partial[w2][t * BWD_NV + u];
+      }
       const float4 a = sA[t];
       const float2 b = sB[t];
       const uint32_t slot = __float_as_uint(sC[t].w);
@@ -329,7 +353,9 @@ __global__ void __launch_bounds__(BWD_THREADS) blend_bwd_kernel(const float4* __
       out[1] = make_float4(-GS_LN2 * s[4], GS_LN2 * s[5], s[6], s[7]);
       out[2] = make_float4(s[8], 0.f, 0.f, 0.f);
     }
-    const bool dead = !(T[0] > GS_T_STOP) && !(T[1] > GS_T_STOP) && !(T[2] > GS_T_STOP) && !(T[3] > GS_T_STOP);
+    bool dead = true;
+#pragma unroll
+    for (int p = 0; p < PX; ++p) dead = dead && !(T[p] > GS_T_STOP);
     const int all_dead = __syncthreads_and(dead);
     if (all_dead) {
       consumed = min(cnt, (k + 1) * BWD_CH);
@@ -337,7 +363,7 @@ __global__ void __launch_bounds__(BWD_THREADS) blend_bwd_kernel(const float4* __
     }
     if (tid == 0 && k + BWD_STAGES < nchunks) {
       const int kn = k + BWD_STAGES;
-      issue_chunk<BwdSmem, BWD_CH>(sm, stage, pA, pB, pC, start + kn * BWD_CH, min(BWD_CH, cnt - kn * BWD_CH), shift);
+      issue_chunk<Smem, BWD_CH>(sm, stage, pA, pB, pC, start + kn * BWD_CH, min(BWD_CH, cnt - kn * BWD_CH), shift);
     }
   }
   if (tid == 0 && k < nchunks) {
@@ -345,7 +371,7 @@ __global__ void __launch_bounds__(BWD_THREADS) blend_bwd_kernel(const float4* __
       gs_mbar_wait(&sm.full[kk % BWD_STAGES], (uint32_t)((kk / BWD_STAGES) & 1));
   }
   // the unread tail of a saturated tile has zero gradient
-  for (int t = consumed + tid; t < cnt; t += BWD_THREADS) {
+  for (int t = consumed + tid; t < cnt; t += THREADS) {
     const uint32_t slot = __float_as_uint(pC[start + t].w);
     float4* out = reinterpret_cast<float4*>(grad_inst + (size_t)slot * GS_GREC);
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -434,8 +460,13 @@ cudaError_t gs_launch_blend_fwd(const float4* pA, const float2* pB, const float4
 cudaError_t gs_launch_blend_bwd(const float4* pA, const float2* pB, const float4* pC, const int* tile_accum,
                                 const GsFrameGeom& g, const float* image, const float* grad_image, float* grad_inst,
                                 cudaStream_t st) {
-  blend_bwd_kernel<<<g.n_tiles, BWD_THREADS, 0, st>>>(pA, pB, pC, tile_accum, g.wp, g.hp, g.ntx, g.fx, g.fy, image,
-                                                      grad_image, grad_inst);
+  static const int warps = getenv("GS_BWD_WARPS") ? atoi(getenv("GS_BWD_WARPS")) : 2;   // A/B knob: 1 = one warp x 8 px
+  if (warps == 2)
+    blend_bwd_kernel<2><<<g.n_tiles, 64, 0, st>>>(pA, pB, pC, tile_accum, g.wp, g.hp, g.ntx, g.fx, g.fy, image,
+                                                  grad_image, grad_inst);
+  else
+    blend_bwd_kernel<1><<<g.n_tiles, 32, 0, st>>>(pA, pB, pC, tile_accum, g.wp, g.hp, g.ntx, g.fx, g.fy, image,
+                                                  grad_image, grad_inst);
   return cudaGetLastError();
 }
 
