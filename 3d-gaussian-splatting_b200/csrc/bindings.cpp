@@ -291,6 +291,25 @@ struct RenderContext {
     return v;
   }
 
+  void backward_into(torch::Tensor pos, torch::Tensor rgb, torch::Tensor opa, torch::Tensor quat, torch::Tensor scale,
+                     torch::Tensor image, torch::Tensor grad_image, torch::Tensor g_pos, torch::Tensor g_rgb,
+                     torch::Tensor g_opa, torch::Tensor g_quat, torch::Tensor g_scale) {
+    GS_CHECK_F32(pos); GS_CHECK_F32(rgb); GS_CHECK_F32(opa); GS_CHECK_F32(quat); GS_CHECK_F32(scale);
+    GS_CHECK_F32(image); GS_CHECK_F32(g_pos); GS_CHECK_F32(g_rgb); GS_CHECK_F32(g_opa); GS_CHECK_F32(g_quat);
+    GS_CHECK_F32(g_scale);
+    TORCH_CHECK(grad_image.is_cuda() && grad_image.scalar_type() == at::kFloat && grad_image.sizes() == image.sizes(),
+                "RenderContext.backward_into: grad_image must match image");
+    TORCH_CHECK(g_pos.numel() == pos.numel() && g_rgb.numel() == rgb.numel() && g_opa.numel() == opa.numel() &&
+                    g_quat.numel() == quat.numel() && g_scale.numel() == scale.numel(),
+                "RenderContext.backward_into: gradient buffers must match their parameters");
+    TORCH_CHECK(reinterpret_cast<uintptr_t>(g_quat.data_ptr()) % 16 == 0, "grad_quat must be 16-byte aligned");
+    c10::cuda::CUDAGuard guard(pos.device());
+    auto gi = grad_image.contiguous();
+    check_rc(gs_render_backward(ctx, fp(pos), fp(rgb), fp(opa), fp(quat), fp(scale), fp(image), fp(gi), fpm(g_pos),
+                                fpm(g_rgb), fpm(g_opa), fpm(g_quat), fpm(g_scale), cur_stream()),
+             "gs_render_backward");
+  }
+
   py::dict stats() {
     gs_frame_info fi{};
     check_rc(gs_frame_stats(ctx, &fi, cur_stream()), "gs_frame_stats");
@@ -356,6 +375,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def(py::init<>())
       .def("forward", &RenderContext::forward)
       .def("backward", &RenderContext::backward)
+      .def("backward_into", &RenderContext::backward_into)
       .def("stats", &RenderContext::stats)
       .def("set_timing", &RenderContext::set_timing)
       .def("stage_ms", &RenderContext::stage_ms)

@@ -42,12 +42,17 @@ class GradBucket:
         if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(self.group) == 1:
             return None
         grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in self.params]
-        flat = _flatten_dense_tensors(grads)
+        flat = _as_one_buffer(grads)          # zero-copy when the grads are views of one flat buffer
+        in_place = flat is not None
+        if not in_place:
+            flat = _flatten_dense_tensors(grads)
         work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=async_op)
 
         def finish():
             if self.average:
                 flat.div_(dist.get_world_size(self.group))
+            if in_place:
+                return
             for p, g, f in zip(self.params, grads, _unflatten_dense_tensors(flat, grads)):
                 if p.grad is None:
                     p.grad = f.clone()
@@ -57,6 +62,27 @@ class GradBucket:
         if async_op:
             return work, finish
         finish()
+        return None
+
+
+def _as_one_buffer(grads):
+    """If the gradient tensors are contiguous views laid out in order in ONE storage with at most
+    3 pad elements between them (the fused backward allocates them that way,
+    renderer._RenderFrame.backward), return the flat 1-D view spanning them so the collective
+    runs in place; else None."""
+    try:
+        g0 = grads[0]
+        base = g0.untyped_storage().data_ptr()
+        off = g0.storage_offset()
+        end = off
+        for g in grads:
+            gap = g.storage_offset() - end
+            if (g.dtype != g0.dtype or not g.is_contiguous() or g.untyped_storage().data_ptr() != base
+                    or gap < 0 or gap > 3):
+                return None
+            end = g.storage_offset() + g.numel()
+        return torch.empty(0, dtype=g0.dtype, device=g0.device).set_(g0.untyped_storage(), off, (end - off,))
+    except Exception:
         return None
 
 

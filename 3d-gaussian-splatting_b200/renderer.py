@@ -161,8 +161,21 @@ class _RenderFrame(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_image, _grad_mask):
         pos, rgb, opa, quat, scale, image = ctx.saved_tensors
-        g = ctx.rctx.backward(pos, rgb, opa, quat, scale, image, _f32(grad_image))
-        return (None, g[0], g[1], g[2], g[3], g[4]) + (None,) * 9
+        # all five gradients are views of ONE flat buffer (order pos, rgb, opa, quat, scale) so
+        # that the data-parallel all-reduce runs in place on a single bucket (dp.GradBucket)
+        sizes = [t.numel() for t in (pos, rgb, opa, quat, scale)]
+        starts, o = [], 0
+        for n in sizes:                       # 16-byte aligned segments (float4 stores in the kernel)
+            starts.append(o)
+            o += (n + 3) // 4 * 4
+        flat = torch.empty(o, device=pos.device, dtype=torch.float32)
+        outs = []
+        for t, n, b in zip((pos, rgb, opa, quat, scale), sizes, starts):
+            outs.append(flat[b:b + n].view(t.shape))
+            if n % 4:
+                flat[b + n:b + (n + 3) // 4 * 4].zero_()     # keep the (<= 3 float) pads finite
+        ctx.rctx.backward_into(pos, rgb, opa, quat, scale, image, _f32(grad_image), *outs)
+        return (None, outs[0], outs[1], outs[2], outs[3], outs[4]) + (None,) * 9
 
 
 render_frame = _RenderFrame.apply

@@ -369,6 +369,10 @@ def run_reference(args, world, rank, local):
 
 
 def main():
+    # NCCL / torchrun helpers write banners to fd 1; keep the contract "ONE JSON line on stdout":
+    # everything else goes to stderr, the JSON line is written to the saved original stdout.
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
@@ -385,7 +389,8 @@ def main():
     else:
         out = run_ours(args, world, rank, local)
     if rank == 0 and out is not None:
-        print(json.dumps(out))
+        real_stdout.write(json.dumps(out) + "\n")
+        real_stdout.flush()
     if world > 1:
         import torch.distributed as dist
         if args.impl != "reference":

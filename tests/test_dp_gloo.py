@@ -44,6 +44,16 @@ def _worker(rank, world, port, out):
     work.wait()
     finish()
     ok = ok and bool((params[0].grad == 0.5).all())
+    # zero-copy path: gradients that are views of one flat buffer (as the fused backward makes them)
+    flat = torch.zeros(150 + 2 + 52 + 200)          # pads of 2 after the first segment
+    gviews = [flat[0:150].view(50, 3), flat[152:202].view(50), flat[204:404].view(50, 4)]
+    for p, v in zip(params, gviews):
+        v.fill_(float(rank + 1))
+        p.grad = v
+    assert dp._as_one_buffer([p.grad for p in params]) is not None
+    dp.GradBucket(params).allreduce()
+    ok = ok and bool((flat[0:150] == 3.0).all()) and bool((params[2].grad == 3.0).all()) \
+        and params[0].grad.untyped_storage().data_ptr() == flat.untyped_storage().data_ptr()
     out[rank] = (ok, views, bucket.nbytes())
     dist.destroy_process_group()
 
