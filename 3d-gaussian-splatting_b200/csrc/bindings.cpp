@@ -124,9 +124,13 @@ static void check_draw_inputs(const torch::Tensor& pos, const torch::Tensor& rgb
                               bool use_sh_coeff) {
   GS_CHECK_F32(pos); GS_CHECK_F32(rgb); GS_CHECK_F32(opa); GS_CHECK_F32(cov); GS_CHECK_I32(accum); GS_CHECK_F32(img);
   int64_t m = pos.size(0);
-  int64_t d = use_sh_coeff ? 27 : 3;
   TORCH_CHECK(pos.dim() == 2 && pos.size(1) == 3, "draw: pos must be [m,3]");
-  TORCH_CHECK(rgb.numel() == m * d, "draw: rgb must be [m,", d, "]");
+  if (use_sh_coeff) {   // 27 = degree 2 (the reference's layout [c*9+k]); 48 = degree 3 extension [c*16+k]
+    TORCH_CHECK(rgb.dim() == 2 && rgb.size(0) == m && (rgb.size(1) == 27 || rgb.size(1) == 48),
+                "draw: SH rgb must be [m,27] or [m,48]");
+  } else {
+    TORCH_CHECK(rgb.numel() == m * 3, "draw: rgb must be [m,3]");
+  }
   TORCH_CHECK(opa.numel() == m && cov.numel() == m * 4, "draw: opa must be [m], cov [m,2,2]");
   TORCH_CHECK(img.dim() == 3 && img.size(2) == 3 && img.size(0) % 16 == 0 && img.size(1) % 16 == 0,
               "draw: image must be [Hp,Wp,3] with Hp,Wp multiples of 16");
@@ -140,7 +144,7 @@ void draw(torch::Tensor pos, torch::Tensor rgb, torch::Tensor opa, torch::Tensor
   (void)fast;   // both exp flavours of the reference are within 2 ulp of ex2.approx; one code path
   check_draw_inputs(pos, rgb, opa, cov, tile_n_point_accum, res, use_sh_coeff);
   c10::cuda::CUDAGuard guard(pos.device());
-  int m = (int)pos.size(0), d = use_sh_coeff ? 27 : 3;
+  int m = (int)pos.size(0), d = use_sh_coeff ? (int)rgb.size(1) : 3;
   auto ws = torch::empty({(int64_t)gs_draw_workspace_bytes(m, d)}, pos.options().dtype(at::kByte));
   const float *ro = nullptr, *lt = nullptr, *dx = nullptr, *dy = nullptr;
   if (use_sh_coeff) {
@@ -167,7 +171,7 @@ void draw_backward(torch::Tensor pos, torch::Tensor rgb, torch::Tensor opa, torc
                   grad_cov.numel() == cov.numel(), "draw_backward: gradient buffers must match their inputs");
   c10::cuda::CUDAGuard guard(pos.device());
   auto go = grad_output.contiguous();   // autograd may hand us a strided view (crop backward)
-  int m = (int)pos.size(0), d = use_sh_coeff ? 27 : 3;
+  int m = (int)pos.size(0), d = use_sh_coeff ? (int)rgb.size(1) : 3;
   auto ws = torch::empty({(int64_t)gs_draw_workspace_bytes(m, d)}, pos.options().dtype(at::kByte));
   const float *ro = nullptr, *lt = nullptr, *dx = nullptr, *dy = nullptr;
   if (use_sh_coeff) {

@@ -150,12 +150,54 @@ __global__ void __launch_bounds__(kBlock) pack_sorted_kernel(const uint32_t* __r
   pC[i] = make_float4(b.z, b.w, c.x, __uint_as_float(slot));
 }
 
+// SH variant: the third stream row is {raw coefficients rgb[g][0..d), slot, pad}
+__global__ void __launch_bounds__(kBlock) pack_sorted_sh_kernel(const uint32_t* __restrict__ keys,
+                                                                 const uint32_t* __restrict__ vals, long long m,
+                                                                 int n_tiles, int ntx, const GsRec* __restrict__ rec,
+                                                                 const uint32_t* __restrict__ offsets_g,
+                                                                 const float* __restrict__ rgb, int d, int sw,
+                                                                 float4* __restrict__ pA, float2* __restrict__ pB,
+                                                                 float* __restrict__ pS, int* __restrict__ tile_accum) {
+  long long i = (long long)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= m) return;
+  uint32_t tile = keys[i];
+  if (i == 0) {
+    for (uint32_t t = 0; t <= tile; ++t) tile_accum[t] = 0;
+  } else {
+    uint32_t prev = keys[i - 1];
+    for (uint32_t t = prev + 1; t <= tile; ++t) tile_accum[t] = (int)i;
+  }
+  if (i == m - 1)
+    for (uint32_t t = tile + 1; t <= (uint32_t)n_tiles; ++t) tile_accum[t] = (int)m;
+  const uint32_t g = vals[i];
+  const GsRec* r = rec + g;
+  float4 a = r->a, b = r->b, c = r->c;
+  uint32_t rxy = __float_as_uint(c.z), rwh = __float_as_uint(c.w);
+  uint32_t tx = tile % ntx, ty = tile / ntx;
+  uint32_t slot = offsets_g[g] + (ty - (rxy >> 16)) * (rwh & 0xffffu) + (tx - (rxy & 0xffffu));
+  pA[i] = a;
+  pB[i] = make_float2(b.x, b.y);
+  float* row = pS + (size_t)i * sw;
+  const float* src = rgb + (size_t)g * d;
+  for (int q = 0; q < d; ++q) row[q] = src[q];
+  row[d] = __uint_as_float(slot);
+}
+
 __global__ void __launch_bounds__(kBlock) iota_kernel(uint32_t* out, int n) {
   int i = blockIdx.x * kBlock + threadIdx.x;
   if (i < n) out[i] = (uint32_t)i;
 }
 
 }  // namespace
+
+cudaError_t gs_launch_pack_sorted_sh(const uint32_t* keys, const uint32_t* vals, long long m, int n_tiles, int ntx,
+                                     const GsRec* rec, const uint32_t* offsets_g, const float* rgb, int d, int sw,
+                                     float4* pA, float2* pB, float* pS, int* tile_accum, cudaStream_t st) {
+  if (m == 0) return cudaMemsetAsync(tile_accum, 0, sizeof(int) * (size_t)(n_tiles + 1), st);
+  pack_sorted_sh_kernel<<<(unsigned)((m + kBlock - 1) / kBlock), kBlock, 0, st>>>(
+      keys, vals, m, n_tiles, ntx, rec, offsets_g, rgb, d, sw, pA, pB, pS, tile_accum);
+  return cudaGetLastError();
+}
 
 cudaError_t gs_launch_iota(uint32_t* out, int n, cudaStream_t st) {
   if (n == 0) return cudaSuccess;

@@ -425,6 +425,50 @@ __global__ void __launch_bounds__(256) legacy_unpack_grads_kernel(const float* _
   g_rgb[3 * i + 2] = v2.x;
 }
 
+// SH variants: third stream row = {coef[0..d), slot, pad}; gradient row = {6 geometry, d coefficient}
+__global__ void __launch_bounds__(256) legacy_pack_sh_kernel(const float* __restrict__ pos,
+                                                              const float* __restrict__ rgb,
+                                                              const float* __restrict__ opa,
+                                                              const float* __restrict__ cov, int m, int d, int sw,
+                                                              float4* __restrict__ pA, float2* __restrict__ pB,
+                                                              float* __restrict__ pS) {
+  int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= m) return;
+  float4 cv = reinterpret_cast<const float4*>(cov)[i];
+  GsConic k = gs_make_conic(cv.x, cv.y, cv.z, cv.w);
+  pA[i] = make_float4(pos[3 * i], pos[3 * i + 1], k.ca, k.cb);
+  pB[i] = make_float2(k.cc, log2f(opa[i]));
+  float* row = pS + (size_t)i * sw;
+  const float* src = rgb + (size_t)i * d;
+  for (int q = 0; q < d; ++q) row[q] = src[q];
+  row[d] = __uint_as_float((uint32_t)i);
+}
+
+__global__ void __launch_bounds__(256) legacy_unpack_grads_sh_kernel(const float* __restrict__ grad_inst, int gw,
+                                                                      const float* __restrict__ opa,
+                                                                      const float* __restrict__ cov, int m, int d,
+                                                                      float* __restrict__ g_pos,
+                                                                      float* __restrict__ g_rgb,
+                                                                      float* __restrict__ g_opa,
+                                                                      float* __restrict__ g_cov) {
+  int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= m) return;
+  const float* row = grad_inst + (size_t)i * gw;
+  float4 cv = reinterpret_cast<const float4*>(cov)[i];
+  float det = cv.x * cv.w - cv.y * cv.z;
+  double pn = 2.0 * (double)det + 1e-14;
+  float sc = (float)((double)GS_LOG2E / pn);
+  float kk = 2.f * sc * sc / GS_LOG2E;
+  float d_ca = row[2], d_cb = row[3], d_cc = row[4];
+  float gsc = d_ca * cv.w + d_cb * (cv.y + cv.z) + d_cc * cv.x;
+  g_pos[3 * i] = row[0];
+  g_pos[3 * i + 1] = row[1];
+  reinterpret_cast<float4*>(g_cov)[i] = make_float4(d_cc * sc - gsc * kk * cv.w, d_cb * sc + gsc * kk * cv.z,
+                                                    d_cb * sc + gsc * kk * cv.y, d_ca * sc - gsc * kk * cv.x);
+  g_opa[i] = row[5] / (opa[i] * GS_LN2);
+  for (int q = 0; q < d; ++q) g_rgb[(size_t)i * d + q] = row[6 + q];
+}
+
 struct LegacyWs {
   float4* pA;
   float2* pB;
@@ -434,17 +478,20 @@ struct LegacyWs {
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-inline size_t legacy_ws_layout(int m, LegacyWs* ws, char* base) {
+// d == 3: pC is the float4 colour stream; d == 27 / 48: pC aliases the SH stream (sw floats / row)
+inline size_t legacy_ws_layout(int m, int d, LegacyWs* ws, char* base) {
   size_t off = 0;
   size_t mm = (size_t)(m > 0 ? m : 0);
+  size_t crow = d == 3 ? 16 : (size_t)gs_sh_stream_width(d) * 4;
+  size_t grow = d == 3 ? (size_t)GS_GREC * 4 : (size_t)gs_sh_grad_width(d) * 4;
   if (ws) ws->pA = reinterpret_cast<float4*>(base + off);
   off += align_up(mm * 16, 256);
   if (ws) ws->pC = reinterpret_cast<float4*>(base + off);
-  off += align_up(mm * 16, 256);
+  off += align_up(mm * crow + 16, 256);
   if (ws) ws->pB = reinterpret_cast<float2*>(base + off);
   off += align_up((mm + 2) * 8, 256);
   if (ws) ws->grad_inst = reinterpret_cast<float*>(base + off);
-  off += align_up(mm * GS_GREC * 4, 256);
+  off += align_up(mm * grow, 256);
   return off;
 }
 
@@ -471,15 +518,15 @@ cudaError_t gs_launch_blend_bwd(const float4* pA, const float2* pB, const float4
 }
 
 extern "C" size_t gs_draw_workspace_bytes(int m, int d) {
-  (void)d;
-  return legacy_ws_layout(m, nullptr, nullptr);
+  if (d != 3 && gs_sh_basis_count(d) == 0) return 0;
+  return legacy_ws_layout(m, d, nullptr, nullptr);
 }
 
 static int check_draw_args(const char* fn, int m, int d, int wp, int hp, int weight_normalize, int sigmoid,
                            size_t ws_bytes, void* ws) {
   if (m < 0 || wp <= 0 || hp <= 0 || (wp % GS_TILE) || (hp % GS_TILE))
     return gs_set_error_msg(GS_ERR_INVALID_ARG, fn);
-  if (weight_normalize || sigmoid || d != 3) return gs_set_error_msg(GS_ERR_UNSUPPORTED, fn);
+  if (weight_normalize || sigmoid || (d != 3 && gs_sh_basis_count(d) == 0)) return gs_set_error_msg(GS_ERR_UNSUPPORTED, fn);
   if (m > 0 && (ws == nullptr || ws_bytes < gs_draw_workspace_bytes(m, d)))
     return gs_set_error_msg(GS_ERR_INVALID_ARG, fn);
   return 0;
@@ -490,15 +537,20 @@ extern "C" int gs_draw_fwd(const float* pos, const float* rgb, const float* opa,
                            float focal_x, float focal_y, int weight_normalize, int sigmoid, const float* rays_o,
                            const float* lefttop, const float* vec_dx, const float* vec_dy, float* image,
                            void* workspace, size_t workspace_bytes, gs_stream_t stream) {
-  (void)rays_o; (void)lefttop; (void)vec_dx; (void)vec_dy;
   int rc = check_draw_args("gs_draw_fwd: bad/unsupported arguments", m, d, width_padded, height_padded,
                            weight_normalize, sigmoid, workspace_bytes, workspace);
   if (rc) return rc;
+  if (d != 3 && (!rays_o || !lefttop || !vec_dx || !vec_dy))
+    return gs_set_error_msg(GS_ERR_INVALID_ARG, "gs_draw_fwd: SH colour needs rays_o / lefttop / vec_dx / vec_dy");
   cudaStream_t st = (cudaStream_t)stream;
   LegacyWs ws{};
-  legacy_ws_layout(m, &ws, static_cast<char*>(workspace));
+  legacy_ws_layout(m, d, &ws, static_cast<char*>(workspace));
   if (m > 0) {
-    legacy_pack_kernel<<<(m + 255) / 256, 256, 0, st>>>(pos, rgb, opa, cov, m, ws.pA, ws.pB, ws.pC);
+    if (d == 3)
+      legacy_pack_kernel<<<(m + 255) / 256, 256, 0, st>>>(pos, rgb, opa, cov, m, ws.pA, ws.pB, ws.pC);
+    else
+      legacy_pack_sh_kernel<<<(m + 255) / 256, 256, 0, st>>>(pos, rgb, opa, cov, m, d, gs_sh_stream_width(d), ws.pA,
+                                                             ws.pB, reinterpret_cast<float*>(ws.pC));
     GS_CUDA_TRY(cudaGetLastError());
   }
   GsFrameGeom g{};
@@ -509,7 +561,13 @@ extern "C" int gs_draw_fwd(const float* pos, const float* rgb, const float* opa,
   g.n_tiles = g.ntx * g.nty;
   g.fx = focal_x;
   g.fy = focal_y;
-  GS_CUDA_TRY(gs_launch_blend_fwd(ws.pA, ws.pB, ws.pC, tile_n_point_accum, g, image, nullptr, st));
+  if (d == 3) {
+    GS_CUDA_TRY(gs_launch_blend_fwd(ws.pA, ws.pB, ws.pC, tile_n_point_accum, g, image, nullptr, st));
+  } else {
+    GsRayPtrs r{rays_o, lefttop, vec_dx, vec_dy};
+    GS_CUDA_TRY(gs_launch_blend_sh_fwd(ws.pA, ws.pB, reinterpret_cast<float*>(ws.pC), d, tile_n_point_accum, g, r,
+                                       image, nullptr, st));
+  }
   return 0;
 }
 
@@ -519,15 +577,20 @@ extern "C" int gs_draw_bwd(const float* pos, const float* rgb, const float* opa,
                            const float* lefttop, const float* vec_dx, const float* vec_dy, const float* image,
                            const float* grad_image, float* grad_pos, float* grad_rgb, float* grad_opa,
                            float* grad_cov, void* workspace, size_t workspace_bytes, gs_stream_t stream) {
-  (void)rays_o; (void)lefttop; (void)vec_dx; (void)vec_dy;
   int rc = check_draw_args("gs_draw_bwd: bad/unsupported arguments", m, d, width_padded, height_padded,
                            weight_normalize, sigmoid, workspace_bytes, workspace);
   if (rc) return rc;
   if (m == 0) return 0;
+  if (d != 3 && (!rays_o || !lefttop || !vec_dx || !vec_dy))
+    return gs_set_error_msg(GS_ERR_INVALID_ARG, "gs_draw_bwd: SH colour needs rays_o / lefttop / vec_dx / vec_dy");
   cudaStream_t st = (cudaStream_t)stream;
   LegacyWs ws{};
-  legacy_ws_layout(m, &ws, static_cast<char*>(workspace));
-  legacy_pack_kernel<<<(m + 255) / 256, 256, 0, st>>>(pos, rgb, opa, cov, m, ws.pA, ws.pB, ws.pC);
+  legacy_ws_layout(m, d, &ws, static_cast<char*>(workspace));
+  if (d == 3)
+    legacy_pack_kernel<<<(m + 255) / 256, 256, 0, st>>>(pos, rgb, opa, cov, m, ws.pA, ws.pB, ws.pC);
+  else
+    legacy_pack_sh_kernel<<<(m + 255) / 256, 256, 0, st>>>(pos, rgb, opa, cov, m, d, gs_sh_stream_width(d), ws.pA,
+                                                           ws.pB, reinterpret_cast<float*>(ws.pC));
   GS_CUDA_TRY(cudaGetLastError());
   GsFrameGeom g{};
   g.wp = width_padded;
@@ -537,9 +600,17 @@ extern "C" int gs_draw_bwd(const float* pos, const float* rgb, const float* opa,
   g.n_tiles = g.ntx * g.nty;
   g.fx = focal_x;
   g.fy = focal_y;
-  GS_CUDA_TRY(gs_launch_blend_bwd(ws.pA, ws.pB, ws.pC, tile_n_point_accum, g, image, grad_image, ws.grad_inst, st));
-  legacy_unpack_grads_kernel<<<(m + 255) / 256, 256, 0, st>>>(ws.grad_inst, opa, cov, m, grad_pos, grad_rgb, grad_opa,
-                                                            grad_cov);
+  if (d == 3) {
+    GS_CUDA_TRY(gs_launch_blend_bwd(ws.pA, ws.pB, ws.pC, tile_n_point_accum, g, image, grad_image, ws.grad_inst, st));
+    legacy_unpack_grads_kernel<<<(m + 255) / 256, 256, 0, st>>>(ws.grad_inst, opa, cov, m, grad_pos, grad_rgb,
+                                                              grad_opa, grad_cov);
+  } else {
+    GsRayPtrs r{rays_o, lefttop, vec_dx, vec_dy};
+    GS_CUDA_TRY(gs_launch_blend_sh_bwd(ws.pA, ws.pB, reinterpret_cast<float*>(ws.pC), d, tile_n_point_accum, g, r,
+                                       image, grad_image, ws.grad_inst, st));
+    legacy_unpack_grads_sh_kernel<<<(m + 255) / 256, 256, 0, st>>>(ws.grad_inst, gs_sh_grad_width(d), opa, cov, m, d,
+                                                                 grad_pos, grad_rgb, grad_opa, grad_cov);
+  }
   GS_CUDA_TRY(cudaGetLastError());
   return 0;
 }

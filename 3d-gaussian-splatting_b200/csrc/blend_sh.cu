@@ -1,0 +1,452 @@
+// Tile blend with per-pixel spherical-harmonics colour (reference `use_sh_coeff`,
+// gaussian.cu:849-861 ray setup, :405-426 basis, :936-948 forward colour, :665-689 backward).
+//
+// The reference evaluates SH PER PIXEL RAY inside the blend: colour_c(pixel, instance) =
+// sigmoid(sum_k SH_k(dir_pixel) * coef[c*K + k]) with K = 9 (degree 2, D = 27).  K = 16
+// (degree 3, D = 48; svox2's C3 constants, defined but unused in the reference :395-403) is the
+// extension BASELINE.json's configs[2] asks for.  Same staging / early-exit / reduction design
+// as blend.cu; the third stream carries the 3K coefficients + the gradient slot per instance.
+#include "internal.h"
+
+namespace {
+
+__host__ __device__ constexpr int sh_sw(int K) { return (3 * K + 1 + 3) / 4 * 4; }       // floats per pS row
+__host__ __device__ constexpr int sh_nv(int K) { return 6 + 3 * K; }                     // reduced values
+__host__ __device__ constexpr int sh_nvp(int K) { return (sh_nv(K) + 7) / 8 * 8; }       // padded to blocks of 8
+
+constexpr float SH_C0 = 0.28209479177387814f;
+constexpr float SH_C1 = 0.4886025119029199f;
+constexpr float SH_C2_0 = 1.0925484305920792f, SH_C2_1 = -1.0925484305920792f, SH_C2_2 = 0.31539156525252005f,
+                SH_C2_3 = -1.0925484305920792f, SH_C2_4 = 0.5462742152960396f;
+constexpr float SH_C3_0 = -0.5900435899266435f, SH_C3_1 = 2.890611442640554f, SH_C3_2 = -0.4570457994644658f,
+                SH_C3_3 = 0.3731763325901154f, SH_C3_4 = -0.4570457994644658f, SH_C3_5 = 1.445305721320277f,
+                SH_C3_6 = -0.5900435899266435f;
+
+template <int K>
+__device__ __forceinline__ void sh_basis(float x, float y, float z, float* out) {
+  out[0] = SH_C0;
+  out[1] = -SH_C1 * y;
+  out[2] = SH_C1 * z;
+  out[3] = -SH_C1 * x;
+  const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+  out[4] = SH_C2_0 * xy;
+  out[5] = SH_C2_1 * yz;
+  out[6] = SH_C2_2 * (2.0f * zz - xx - yy);
+  out[7] = SH_C2_3 * xz;
+  out[8] = SH_C2_4 * (xx - yy);
+  if (K > 9) {
+    out[9] = SH_C3_0 * y * (3.f * xx - yy);
+    out[10] = SH_C3_1 * xy * z;
+    out[11] = SH_C3_2 * y * (4.f * zz - xx - yy);
+    out[12] = SH_C3_3 * z * (2.f * zz - 3.f * xx - 3.f * yy);
+    out[13] = SH_C3_4 * x * (4.f * zz - xx - yy);
+    out[14] = SH_C3_5 * z * (xx - yy);
+    out[15] = SH_C3_6 * x * (xx - 3.f * yy);
+  }
+}
+
+// ray direction of padded pixel (ix, iy): gaussian.cu:849-860
+template <int K>
+__device__ __forceinline__ void pixel_sh(int ix, int iy, const float* __restrict__ rays_o,
+                                         const float* __restrict__ lefttop, const float* __restrict__ vdx,
+                                         const float* __restrict__ vdy, float* out) {
+  float d[3], nn = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    d[i] = __ldg(lefttop + i) + (float)ix * __ldg(vdx + i) + (float)iy * __ldg(vdy + i) - __ldg(rays_o + i);
+    nn += d[i] * d[i];
+  }
+  const float inv = 1.f / (sqrtf(nn) + 1e-7f);
+  sh_basis<K>(d[0] * inv, d[1] * inv, d[2] * inv, out);
+}
+
+template <int K, int CH, int STAGES>
+struct ShStage {
+  float4 A[STAGES][CH];
+  float2 B[STAGES][CH + 2];
+  float S[STAGES][CH * sh_sw(K)];
+  uint64_t full[STAGES];
+};
+
+template <int K, typename SM>
+__device__ __forceinline__ void issue_sh(SM& sm, int stage, const float4* __restrict__ pA,
+                                         const float2* __restrict__ pB, const float* __restrict__ pS, int base,
+                                         int n, int shift) {
+  const uint32_t bytes_a = (uint32_t)n * 16u;
+  const uint32_t bytes_s = (uint32_t)n * (uint32_t)(sh_sw(K) * 4);
+  const uint32_t nb = (uint32_t)(n + shift + 1) & ~1u;
+  const uint32_t bytes_b = nb * 8u;
+  gs_mbar_expect_tx(&sm.full[stage], bytes_a + bytes_s + bytes_b);
+  gs_bulk_g2s(sm.A[stage], pA + base, bytes_a, &sm.full[stage]);
+  gs_bulk_g2s(sm.S[stage], pS + (size_t)base * sh_sw(K), bytes_s, &sm.full[stage]);
+  gs_bulk_g2s(sm.B[stage], pB + (base - shift), bytes_b, &sm.full[stage]);
+}
+
+__device__ __forceinline__ float sh_sigmoid(float x) { return gs_rcp(1.f + gs_ex2(-x * GS_LOG2E)); }
+
+// ---------------------------------------------------------------------------------------
+// forward: 64 threads per tile, a row of 4 pixels per thread
+// ---------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(64) blend_sh_fwd_kernel(const float4* __restrict__ pA, const float2* __restrict__ pB,
+                                                           const float* __restrict__ pS,
+                                                           const int* __restrict__ tile_accum, int wp, int hp, int ntx,
+                                                           float fx, float fy, const float* __restrict__ rays_o,
+                                                           const float* __restrict__ lefttop,
+                                                           const float* __restrict__ vdx,
+                                                           const float* __restrict__ vdy, float* __restrict__ image,
+                                                           int* __restrict__ tile_neff) {
+  constexpr int CH = 64, STAGES = 2, PX = 4, SW = sh_sw(K);
+  using SM = ShStage<K, CH, STAGES>;
+  __shared__ __align__(16) SM sm;
+  const int tile = blockIdx.x, tid = threadIdx.x;
+  const int tx = tile % ntx, ty = tile / ntx;
+  const int ix0 = tx * GS_TILE + (tid & 3) * PX;
+  const int iy = ty * GS_TILE + (tid >> 2);
+  float px[PX], sh[PX][K];
+#pragma unroll
+  for (int p = 0; p < PX; ++p) {
+    px[p] = gs_pixel_coord(ix0 + p, wp, fx);
+    pixel_sh<K>(ix0 + p, iy, rays_o, lefttop, vdx, vdy, sh[p]);
+  }
+  const float py = gs_pixel_coord(iy, hp, fy);
+  const int start = tile_accum[tile];
+  const int cnt = tile_accum[tile + 1] - start;
+  const int shift = start & 1;
+  const int nchunks = (cnt + CH - 1) / CH;
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) gs_mbar_init(&sm.full[s], 1);
+    gs_fence_barrier_init();
+  }
+  __syncthreads();
+  if (tid == 0)
+    for (int k = 0; k < STAGES && k < nchunks; ++k)
+      issue_sh<K>(sm, k, pA, pB, pS, start + k * CH, min(CH, cnt - k * CH), shift);
+
+  float T[PX], cr[PX], cg[PX], cb[PX];
+#pragma unroll
+  for (int p = 0; p < PX; ++p) {
+    T[p] = 1.f;
+    cr[p] = cg[p] = cb[p] = 0.f;
+  }
+  int consumed = cnt, k = 0;
+  for (; k < nchunks; ++k) {
+    const int stage = k % STAGES;
+    gs_mbar_wait(&sm.full[stage], (uint32_t)((k / STAGES) & 1));
+    const int n = min(CH, cnt - k * CH);
+    const float4* __restrict__ sA = sm.A[stage];
+    const float2* __restrict__ sB = sm.B[stage] + shift;
+    const float* __restrict__ sS = sm.S[stage];
+    for (int j = 0; j < n; ++j) {
+      if ((j & 3) == 0) {
+        const bool dead = !(T[0] > GS_T_STOP) && !(T[1] > GS_T_STOP) && !(T[2] > GS_T_STOP) && !(T[3] > GS_T_STOP);
+        if (__all_sync(0xffffffffu, dead)) break;
+      }
+      const float4 a = sA[j];
+      const float2 b = sB[j];
+      float cf[3 * K];
+      {
+        const float4* c4 = reinterpret_cast<const float4*>(sS + j * SW);
+#pragma unroll
+        for (int q = 0; q < (3 * K + 3) / 4; ++q) {
+          const float4 t4 = c4[q];
+          if (4 * q < 3 * K) cf[4 * q] = t4.x;
+          if (4 * q + 1 < 3 * K) cf[4 * q + 1] = t4.y;
+          if (4 * q + 2 < 3 * K) cf[4 * q + 2] = t4.z;
+          if (4 * q + 3 < 3 * K) cf[4 * q + 3] = t4.w;
+        }
+      }
+      const float dy = py - a.y;
+      const float m1 = a.w * dy;
+      const float ev = fmaf(-b.x * dy, dy, b.y);
+#pragma unroll
+      for (int p = 0; p < PX; ++p) {
+        const float dx = px[p] - a.x;
+        const float eu = fmaf(a.z, dx, -m1);
+        const float alpha = gs_ex2(fmaf(-dx, eu, ev));
+        const float w = (T[p] > GS_T_STOP) ? alpha * T[p] : 0.f;
+        float col[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          float acc = 0.f;
+#pragma unroll
+          for (int q = 0; q < K; ++q) acc = fmaf(sh[p][q], cf[c * K + q], acc);
+          col[c] = sh_sigmoid(acc);
+        }
+        cr[p] = fmaf(col[0], w, cr[p]);
+        cg[p] = fmaf(col[1], w, cg[p]);
+        cb[p] = fmaf(col[2], w, cb[p]);
+        T[p] -= w;
+      }
+    }
+    const bool dead = !(T[0] > GS_T_STOP) && !(T[1] > GS_T_STOP) && !(T[2] > GS_T_STOP) && !(T[3] > GS_T_STOP);
+    if (__syncthreads_and(dead)) {
+      consumed = min(cnt, (k + 1) * CH);
+      break;
+    }
+    if (tid == 0 && k + STAGES < nchunks) {
+      const int kn = k + STAGES;
+      issue_sh<K>(sm, stage, pA, pB, pS, start + kn * CH, min(CH, cnt - kn * CH), shift);
+    }
+  }
+  if (tid == 0 && k < nchunks)
+    for (int kk = k + 1; kk < nchunks && kk < k + STAGES; ++kk)
+      gs_mbar_wait(&sm.full[kk % STAGES], (uint32_t)((kk / STAGES) & 1));
+  float4* o = reinterpret_cast<float4*>(image + ((size_t)iy * wp + ix0) * 3);
+  o[0] = make_float4(cr[0], cg[0], cb[0], cr[1]);
+  o[1] = make_float4(cg[1], cb[1], cr[2], cg[2]);
+  o[2] = make_float4(cb[2], cr[3], cg[3], cb[3]);
+  if (tile_neff && tid == 0) tile_neff[tile] = consumed;
+}
+
+// reduce 8 values over the warp: afterwards lane L holds the total of value ((L >> 2) & 7)
+// (bit 4 -> +4, bit 3 -> +2, bit 2 -> +1) in v[0]; 9 SHFL instead of 40
+__device__ __forceinline__ float reduce8(float* v, int lane) {
+  {
+    const bool up = (lane & 16) != 0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float keep = up ? v[u + 4] : v[u];
+      const float send = up ? v[u] : v[u + 4];
+      v[u] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  }
+  {
+    const bool up = (lane & 8) != 0;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const float keep = up ? v[u + 2] : v[u];
+      const float send = up ? v[u] : v[u + 2];
+      v[u] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+  }
+  {
+    const bool up = (lane & 4) != 0;
+    const float keep = up ? v[1] : v[0];
+    const float send = up ? v[0] : v[1];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+  return v[0];
+}
+
+// ---------------------------------------------------------------------------------------
+// backward: 64 threads per tile, a row of 4 pixels per thread
+// grad row (GS_SH_GREC(K) floats): d/d{x, y, ca, cb, cc, l2o}, d/d coef[0..3K)
+// ---------------------------------------------------------------------------------------
+template <int K>
+struct ShBwdSmem {
+  ShStage<K, 32, 2> st;
+  float partial[2][32 * sh_nvp(K)];
+};
+
+template <int K>
+__global__ void __launch_bounds__(64) blend_sh_bwd_kernel(const float4* __restrict__ pA, const float2* __restrict__ pB,
+                                                           const float* __restrict__ pS,
+                                                           const int* __restrict__ tile_accum, int wp, int hp, int ntx,
+                                                           float fx, float fy, const float* __restrict__ rays_o,
+                                                           const float* __restrict__ lefttop,
+                                                           const float* __restrict__ vdx,
+                                                           const float* __restrict__ vdy,
+                                                           const float* __restrict__ image,
+                                                           const float* __restrict__ grad_image,
+                                                           float* __restrict__ grad_inst) {
+  constexpr int CH = 32, STAGES = 2, PX = 4, SW = sh_sw(K), NV = sh_nv(K), NVP = sh_nvp(K), THREADS = 64;
+  constexpr int GREC = (NV + 3) / 4 * 4;
+  __shared__ __align__(16) ShBwdSmem<K> smem;
+  auto& sm = smem.st;
+  const int tile = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tx = tile % ntx, ty = tile / ntx;
+  const int start = tile_accum[tile];
+  const int cnt = tile_accum[tile + 1] - start;
+  if (cnt == 0) return;
+  const int shift = start & 1;
+  const int nchunks = (cnt + CH - 1) / CH;
+  const int ix0 = tx * GS_TILE + (tid & 3) * PX;
+  const int iy = ty * GS_TILE + (tid >> 2);
+  float px[PX], sh[PX][K];
+#pragma unroll
+  for (int p = 0; p < PX; ++p) {
+    px[p] = gs_pixel_coord(ix0 + p, wp, fx);
+    pixel_sh<K>(ix0 + p, iy, rays_o, lefttop, vdx, vdy, sh[p]);
+  }
+  const float py = gs_pixel_coord(iy, hp, fy);
+  float T[PX], R[PX], gr[PX], gg[PX], gb[PX];
+  {
+    const size_t off = ((size_t)iy * wp + ix0) * 3;
+    const float4* gi = reinterpret_cast<const float4*>(grad_image + off);
+    const float4* im = reinterpret_cast<const float4*>(image + off);
+    const float4 g0 = gi[0], g1 = gi[1], g2 = gi[2], i0 = im[0], i1 = im[1], i2 = im[2];
+    gr[0] = g0.x; gg[0] = g0.y; gb[0] = g0.z; gr[1] = g0.w;
+    gg[1] = g1.x; gb[1] = g1.y; gr[2] = g1.z; gg[2] = g1.w;
+    gb[2] = g2.x; gr[3] = g2.y; gg[3] = g2.z; gb[3] = g2.w;
+    R[0] = gr[0] * i0.x + gg[0] * i0.y + gb[0] * i0.z;
+    R[1] = gr[1] * i0.w + gg[1] * i1.x + gb[1] * i1.y;
+    R[2] = gr[2] * i1.z + gg[2] * i1.w + gb[2] * i2.x;
+    R[3] = gr[3] * i2.y + gg[3] * i2.z + gb[3] * i2.w;
+#pragma unroll
+    for (int p = 0; p < PX; ++p) T[p] = 1.f;
+  }
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) gs_mbar_init(&sm.full[s], 1);
+    gs_fence_barrier_init();
+  }
+  __syncthreads();
+  if (tid == 0)
+    for (int k = 0; k < STAGES && k < nchunks; ++k)
+      issue_sh<K>(sm, k, pA, pB, pS, start + k * CH, min(CH, cnt - k * CH), shift);
+
+  int consumed = cnt, k = 0;
+  for (; k < nchunks; ++k) {
+    const int stage = k % STAGES;
+    gs_mbar_wait(&sm.full[stage], (uint32_t)((k / STAGES) & 1));
+    const int n = min(CH, cnt - k * CH);
+    const float4* __restrict__ sA = sm.A[stage];
+    const float2* __restrict__ sB = sm.B[stage] + shift;
+    const float* __restrict__ sS = sm.S[stage];
+    float* __restrict__ part = smem.partial[warp];
+    int j = 0;
+    for (; j < n; ++j) {
+      {
+        const bool dead = !(T[0] > GS_T_STOP) && !(T[1] > GS_T_STOP) && !(T[2] > GS_T_STOP) && !(T[3] > GS_T_STOP);
+        if (__all_sync(0xffffffffu, dead)) break;
+      }
+      const float4 a = sA[j];
+      const float2 b = sB[j];
+      float cf[3 * K];
+      {
+        const float4* c4 = reinterpret_cast<const float4*>(sS + j * SW);
+#pragma unroll
+        for (int q = 0; q < (3 * K + 3) / 4; ++q) {
+          const float4 t4 = c4[q];
+          if (4 * q < 3 * K) cf[4 * q] = t4.x;
+          if (4 * q + 1 < 3 * K) cf[4 * q + 1] = t4.y;
+          if (4 * q + 2 < 3 * K) cf[4 * q + 2] = t4.z;
+          if (4 * q + 3 < 3 * K) cf[4 * q + 3] = t4.w;
+        }
+      }
+      float acc[NVP];
+#pragma unroll
+      for (int u = 0; u < NVP; ++u) acc[u] = 0.f;
+      float s0 = 0.f, sx = 0.f, sxx = 0.f;
+      const float dy = py - a.y;
+      const float m1 = a.w * dy;
+      const float ev = fmaf(-b.x * dy, dy, b.y);
+#pragma unroll
+      for (int p = 0; p < PX; ++p) {
+        const float dx = px[p] - a.x;
+        const float eu = fmaf(a.z, dx, -m1);
+        const float alpha = gs_ex2(fmaf(-dx, eu, ev));
+        const bool live = T[p] > GS_T_STOP;
+        const float w = live ? alpha * T[p] : 0.f;
+        float col[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          float t = 0.f;
+#pragma unroll
+          for (int q = 0; q < K; ++q) t = fmaf(sh[p][q], cf[c * K + q], t);
+          col[c] = sh_sigmoid(t);
+        }
+        const float gc = fmaf(gr[p], col[0], fmaf(gg[p], col[1], gb[p] * col[2]));
+        R[p] = fmaf(-gc, w, R[p]);
+        const float rc = gs_rcp(1.0000001f - alpha);
+        const float dal = fmaf(T[p], gc, -R[p] * rc);
+        const float e = live ? dal * alpha : 0.f;
+        T[p] -= w;
+        const float ex = e * dx;
+        s0 += e;
+        sx += ex;
+        sxx = fmaf(ex, dx, sxx);
+        // d colour_c / d coef[c*K+q] = sigma'(.) * SH_q      (gaussian.cu:666-674)
+        const float d0 = gr[p] * w * col[0] * (1.f - col[0]);
+        const float d1 = gg[p] * w * col[1] * (1.f - col[1]);
+        const float d2 = gb[p] * w * col[2] * (1.f - col[2]);
+#pragma unroll
+        for (int q = 0; q < K; ++q) {
+          acc[6 + q] = fmaf(d0, sh[p][q], acc[6 + q]);
+          acc[6 + K + q] = fmaf(d1, sh[p][q], acc[6 + K + q]);
+          acc[6 + 2 * K + q] = fmaf(d2, sh[p][q], acc[6 + 2 * K + q]);
+        }
+      }
+      acc[0] = sx;
+      acc[1] = dy * s0;
+      acc[2] = sxx;
+      acc[3] = dy * sx;
+      acc[4] = dy * acc[1];
+      acc[5] = s0;
+#pragma unroll
+      for (int blk = 0; blk < NVP / 8; ++blk) {
+        const float r = reduce8(acc + blk * 8, lane);
+        if ((lane & 3) == 0) part[j * NVP + blk * 8 + ((lane >> 2) & 7)] = r;
+      }
+    }
+    for (int z = j * NVP + lane; z < n * NVP; z += 32) part[z] = 0.f;
+    __syncthreads();
+    for (int t = tid; t < n; t += THREADS) {
+      const float* p0 = smem.partial[0] + t * NVP;
+      const float* p1 = smem.partial[1] + t * NVP;
+      const float4 a = sA[t];
+      const float2 b = sB[t];
+      const uint32_t slot = __float_as_uint(sS[t * SW + 3 * K]);
+      float* out = grad_inst + (size_t)slot * GREC;
+      float s[6];
+#pragma unroll
+      for (int u = 0; u < 6; ++u) s[u] = p0[u] + p1[u];
+      out[0] = GS_LN2 * (2.f * a.z * s[0] - a.w * s[1]);
+      out[1] = GS_LN2 * (2.f * b.x * s[1] - a.w * s[0]);
+      out[2] = -GS_LN2 * s[2];
+      out[3] = GS_LN2 * s[3];
+      out[4] = -GS_LN2 * s[4];
+      out[5] = GS_LN2 * s[5];
+      for (int u = 6; u < NV; ++u) out[u] = p0[u] + p1[u];
+    }
+    const bool dead = !(T[0] > GS_T_STOP) && !(T[1] > GS_T_STOP) && !(T[2] > GS_T_STOP) && !(T[3] > GS_T_STOP);
+    if (__syncthreads_and(dead)) {
+      consumed = min(cnt, (k + 1) * CH);
+      break;
+    }
+    if (tid == 0 && k + STAGES < nchunks) {
+      const int kn = k + STAGES;
+      issue_sh<K>(sm, stage, pA, pB, pS, start + kn * CH, min(CH, cnt - kn * CH), shift);
+    }
+  }
+  if (tid == 0 && k < nchunks)
+    for (int kk = k + 1; kk < nchunks && kk < k + STAGES; ++kk)
+      gs_mbar_wait(&sm.full[kk % STAGES], (uint32_t)((kk / STAGES) & 1));
+  for (int t = consumed + tid; t < cnt; t += THREADS) {
+    const uint32_t slot = __float_as_uint(pS[(size_t)(start + t) * SW + 3 * K]);
+    float* out = grad_inst + (size_t)slot * GREC;
+    for (int u = 0; u < NV; ++u) out[u] = 0.f;
+  }
+}
+
+}  // namespace
+
+int gs_sh_basis_count(int d) { return d == 27 ? 9 : (d == 48 ? 16 : 0); }
+int gs_sh_stream_width(int d) { return d == 27 ? sh_sw(9) : sh_sw(16); }
+int gs_sh_grad_width(int d) { return d == 27 ? (sh_nv(9) + 3) / 4 * 4 : (sh_nv(16) + 3) / 4 * 4; }
+
+cudaError_t gs_launch_blend_sh_fwd(const float4* pA, const float2* pB, const float* pS, int d, const int* tile_accum,
+                                   const GsFrameGeom& g, const GsRayPtrs& r, float* image, int* tile_neff,
+                                   cudaStream_t st) {
+  if (d == 27)
+    blend_sh_fwd_kernel<9><<<g.n_tiles, 64, 0, st>>>(pA, pB, pS, tile_accum, g.wp, g.hp, g.ntx, g.fx, g.fy, r.rays_o,
+                                                     r.lefttop, r.dx, r.dy, image, tile_neff);
+  else
+    blend_sh_fwd_kernel<16><<<g.n_tiles, 64, 0, st>>>(pA, pB, pS, tile_accum, g.wp, g.hp, g.ntx, g.fx, g.fy, r.rays_o,
+                                                      r.lefttop, r.dx, r.dy, image, tile_neff);
+  return cudaGetLastError();
+}
+
+cudaError_t gs_launch_blend_sh_bwd(const float4* pA, const float2* pB, const float* pS, int d, const int* tile_accum,
+                                   const GsFrameGeom& g, const GsRayPtrs& r, const float* image,
+                                   const float* grad_image, float* grad_inst, cudaStream_t st) {
+  if (d == 27)
+    blend_sh_bwd_kernel<9><<<g.n_tiles, 64, 0, st>>>(pA, pB, pS, tile_accum, g.wp, g.hp, g.ntx, g.fx, g.fy, r.rays_o,
+                                                     r.lefttop, r.dx, r.dy, image, grad_image, grad_inst);
+  else
+    blend_sh_bwd_kernel<16><<<g.n_tiles, 64, 0, st>>>(pA, pB, pS, tile_accum, g.wp, g.hp, g.ntx, g.fx, g.fy, r.rays_o,
+                                                      r.lefttop, r.dx, r.dy, image, grad_image, grad_inst);
+  return cudaGetLastError();
+}

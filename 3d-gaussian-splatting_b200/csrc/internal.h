@@ -15,15 +15,31 @@ struct GsFrameGeom {
   float fx, fy;
 };
 
+// world-space ray setup for per-pixel SH (reference splatter.py:305-321), DEVICE pointers to 3 floats each
+struct GsRayPtrs {
+  const float *rays_o, *lefttop, *dx, *dy;
+};
+
+// ---- blend_sh.cu -----------------------------------------------------------------------
+int gs_sh_basis_count(int d);      // 27 -> 9, 48 -> 16, else 0
+int gs_sh_stream_width(int d);     // floats per instance row of the SH stream (coefficients + slot, padded)
+int gs_sh_grad_width(int d);       // floats per instance gradient row (6 geometry + d coefficients, padded)
+cudaError_t gs_launch_blend_sh_fwd(const float4* pA, const float2* pB, const float* pS, int d, const int* tile_accum,
+                                   const GsFrameGeom& g, const GsRayPtrs& r, float* image, int* tile_neff,
+                                   cudaStream_t st);
+cudaError_t gs_launch_blend_sh_bwd(const float4* pA, const float2* pB, const float* pS, int d, const int* tile_accum,
+                                   const GsFrameGeom& g, const GsRayPtrs& r, const float* image,
+                                   const float* grad_image, float* grad_inst, cudaStream_t st);
+
 // ---- project.cu ------------------------------------------------------------------------
 cudaError_t gs_launch_fused_project(const float* pos, const float* rgb, const float* opa, const float* quat,
-                                    const float* scale, int n, int scale_act, const GsCam& cam,
+                                    const float* scale, int n, int d, int scale_act, const GsCam& cam,
                                     const GsTileGrid& grid, float near_plane, float half_w, float half_h,
                                     GsRec* rec, uint32_t* count, uint32_t* dkey, int64_t* mask,
                                     unsigned int* n_visible, cudaStream_t st);
 
 cudaError_t gs_launch_fused_project_bwd(const float* pos, const float* rgb, const float* opa, const float* quat,
-                                        const float* scale, int n, int scale_act, const GsCam& cam,
+                                        const float* scale, int n, int d, int scale_act, const GsCam& cam,
                                         float near_plane, float half_w, float half_h, const uint32_t* offsets_g,
                                         const uint32_t* count, const float* grad_inst, float* g_pos, float* g_rgb, float* g_opa,
                                         float* g_quat, float* g_scale, cudaStream_t st);
@@ -36,6 +52,9 @@ cudaError_t gs_launch_pack_sorted(const uint32_t* keys, const uint32_t* vals, lo
                                   const GsRec* rec, const uint32_t* offsets_g, float4* pA, float2* pB, float4* pC,
                                   int* tile_accum, cudaStream_t st);
 
+cudaError_t gs_launch_pack_sorted_sh(const uint32_t* keys, const uint32_t* vals, long long m, int n_tiles, int ntx,
+                                     const GsRec* rec, const uint32_t* offsets_g, const float* rgb, int d, int sw,
+                                     float4* pA, float2* pB, float* pS, int* tile_accum, cudaStream_t st);
 cudaError_t gs_launch_iota(uint32_t* out, int n, cudaStream_t st);
 
 // ---- blend.cu --------------------------------------------------------------------------

@@ -46,7 +46,7 @@ __device__ __forceinline__ void load_activated(const float* __restrict__ quat, c
 
 __global__ void __launch_bounds__(kBlock) fused_project_kernel(
     const float* __restrict__ pos, const float* __restrict__ rgb, const float* __restrict__ opa,
-    const float* __restrict__ quat, const float* __restrict__ scale, int n, int scale_act, GsCam cam,
+    const float* __restrict__ quat, const float* __restrict__ scale, int n, int d, int scale_act, GsCam cam,
     GsTileGrid grid, float near_plane, float half_w, float half_h, GsRec* __restrict__ rec,
     uint32_t* __restrict__ count, uint32_t* __restrict__ dkey, int64_t* __restrict__ mask,
     unsigned int* __restrict__ n_visible) {
@@ -68,8 +68,16 @@ __global__ void __launch_bounds__(kBlock) fused_project_kernel(
         float op = gs_sigmoid(opa[i]);
         GsRec* r = rec + i;
         r->a = make_float4(o.x, o.y, k.ca, k.cb);
-        r->b = make_float4(k.cc, log2f(op), gs_sigmoid(rgb[3 * i]), gs_sigmoid(rgb[3 * i + 1]));
-        r->c = make_float4(gs_sigmoid(rgb[3 * i + 2]), o.depth, __uint_as_float(tx0 | (ty0 << 16)),
+        // RGB colour = sigmoid(logit) (splatter.py:539); SH coefficients stay raw and are gathered
+        // from the parameter tensor by the pack pass
+        float cr = 0.f, cg = 0.f, cb = 0.f;
+        if (d == 3) {
+          cr = gs_sigmoid(rgb[3 * i]);
+          cg = gs_sigmoid(rgb[3 * i + 1]);
+          cb = gs_sigmoid(rgb[3 * i + 2]);
+        }
+        r->b = make_float4(k.cc, log2f(op), cr, cg);
+        r->c = make_float4(cb, o.depth, __uint_as_float(tx0 | (ty0 << 16)),
                            __uint_as_float((tx1 - tx0) | ((ty1 - ty0) << 16)));
       }
     }
@@ -82,30 +90,36 @@ __global__ void __launch_bounds__(kBlock) fused_project_kernel(
 }
 
 // Segment-sums the per-instance gradient records of each Gaussian (its instances occupy the
-// contiguous rows offsets[i]..offsets[i+1]) and chains them to the RAW parameters.  No
-// atomics anywhere: the result is deterministic.
+// contiguous rows offsets_g[i] .. + count[i]) and chains them to the RAW parameters.  No
+// atomics anywhere: the result is deterministic.  Row layout (GW floats): d/d{x, y, ca, cb, cc,
+// l2o} then D colour gradients (activated RGB for D == 3, raw SH coefficients otherwise).
+template <int D, int GW>
 __global__ void __launch_bounds__(kBlock) fused_project_bwd_kernel(
     const float* __restrict__ pos, const float* __restrict__ rgb, const float* __restrict__ opa,
     const float* __restrict__ quat, const float* __restrict__ scale, int n, int scale_act, GsCam cam,
     float near_plane, float half_w, float half_h, const uint32_t* __restrict__ offsets_g,
-    const uint32_t* __restrict__ count, const float* __restrict__ grad_inst, float* __restrict__ g_pos, float* __restrict__ g_rgb,
-    float* __restrict__ g_opa, float* __restrict__ g_quat, float* __restrict__ g_scale) {
+    const uint32_t* __restrict__ count, const float* __restrict__ grad_inst, float* __restrict__ g_pos,
+    float* __restrict__ g_rgb, float* __restrict__ g_opa, float* __restrict__ g_quat, float* __restrict__ g_scale) {
   int i = blockIdx.x * kBlock + threadIdx.x;
   if (i >= n) return;
   float gp[3] = {0.f, 0.f, 0.f}, gq_raw[4] = {0.f, 0.f, 0.f, 0.f}, gs_raw[3] = {0.f, 0.f, 0.f};
-  float go = 0.f, gcol[3] = {0.f, 0.f, 0.f};
+  float go = 0.f;
+  float acc[GW];
+#pragma unroll
+  for (int k = 0; k < GW; ++k) acc[k] = 0.f;
   const uint32_t cnt = count[i];
   if (cnt > 0) {
     const uint32_t o0 = offsets_g[i], o1 = o0 + cnt;   // this Gaussian's contiguous gradient rows
-    float acc[9];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) acc[k] = 0.f;
     for (uint32_t r = o0; r < o1; ++r) {
-      const float4* row = reinterpret_cast<const float4*>(grad_inst + (size_t)r * GS_GREC);
-      float4 v0 = row[0], v1 = row[1], v2 = row[2];
-      acc[0] += v0.x; acc[1] += v0.y; acc[2] += v0.z; acc[3] += v0.w;
-      acc[4] += v1.x; acc[5] += v1.y; acc[6] += v1.z; acc[7] += v1.w;
-      acc[8] += v2.x;
+      const float4* row = reinterpret_cast<const float4*>(grad_inst + (size_t)r * GW);
+#pragma unroll
+      for (int q = 0; q < GW / 4; ++q) {
+        const float4 v = row[q];
+        acc[4 * q] += v.x;
+        acc[4 * q + 1] += v.y;
+        acc[4 * q + 2] += v.z;
+        acc[4 * q + 3] += v.w;
+      }
     }
     float p[3] = {pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]};
     float q[4], s[3], raw_s[3], qn;
@@ -115,7 +129,7 @@ __global__ void __launch_bounds__(kBlock) fused_project_bwd_kernel(
     float det = o.a * o.d - o.b * o.c;
     double pn = 2.0 * (double)det + 1e-14;
     float sc = (float)((double)GS_LOG2E / pn);
-    float kk = 2.f * sc * sc / GS_LOG2E;                      // -d sc / d det * (1/1) ... d sc/d det = -kk
+    float kk = 2.f * sc * sc / GS_LOG2E;                      // d sc / d det = -kk
     float gsc = acc[2] * o.d + acc[3] * (o.b + o.c) + acc[4] * o.a;
     float gcov[4];
     gcov[0] = acc[4] * sc - gsc * kk * o.d;                   // d det/da =  d
@@ -139,18 +153,21 @@ __global__ void __launch_bounds__(kBlock) fused_project_bwd_kernel(
     float op = gs_sigmoid(opa[i]);
     // l2o = log2(op):  d/d logit = d_l2o / (op ln2) * op (1-op) = d_l2o (1-op) / ln2
     go = acc[5] * (1.f - op) / GS_LN2;
+    if (D == 3) {
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      float c = gs_sigmoid(rgb[3 * i + k]);
-      gcol[k] = acc[6 + k] * c * (1.f - c);
+      for (int k = 0; k < 3; ++k) {
+        float c = gs_sigmoid(rgb[3 * i + k]);
+        acc[6 + k] *= c * (1.f - c);
+      }
     }
   }
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     g_pos[3 * i + k] = gp[k];
     g_scale[3 * i + k] = gs_raw[k];
-    g_rgb[3 * i + k] = gcol[k];
   }
+#pragma unroll
+  for (int k = 0; k < D; ++k) g_rgb[(size_t)i * D + k] = acc[6 + k];
   reinterpret_cast<float4*>(g_quat)[i] = make_float4(gq_raw[0], gq_raw[1], gq_raw[2], gq_raw[3]);
   g_opa[i] = go;
 }
@@ -295,24 +312,29 @@ extern "C" int gs_jacobian(const float* pos_cam, int n, float* jac, gs_stream_t 
 }
 
 cudaError_t gs_launch_fused_project(const float* pos, const float* rgb, const float* opa, const float* quat,
-                                    const float* scale, int n, int scale_act, const GsCam& cam,
+                                    const float* scale, int n, int d, int scale_act, const GsCam& cam,
                                     const GsTileGrid& grid, float near_plane, float half_w, float half_h,
                                     GsRec* rec, uint32_t* count, uint32_t* dkey, int64_t* mask,
                                     unsigned int* n_visible, cudaStream_t st) {
   if (n == 0) return cudaSuccess;
-  fused_project_kernel<<<grid_for(n), kBlock, 0, st>>>(pos, rgb, opa, quat, scale, n, scale_act, cam, grid,
+  fused_project_kernel<<<grid_for(n), kBlock, 0, st>>>(pos, rgb, opa, quat, scale, n, d, scale_act, cam, grid,
                                                        near_plane, half_w, half_h, rec, count, dkey, mask, n_visible);
   return cudaGetLastError();
 }
 
 cudaError_t gs_launch_fused_project_bwd(const float* pos, const float* rgb, const float* opa, const float* quat,
-                                        const float* scale, int n, int scale_act, const GsCam& cam,
+                                        const float* scale, int n, int d, int scale_act, const GsCam& cam,
                                         float near_plane, float half_w, float half_h, const uint32_t* offsets_g,
                                         const uint32_t* count, const float* grad_inst, float* g_pos, float* g_rgb, float* g_opa,
                                         float* g_quat, float* g_scale, cudaStream_t st) {
   if (n == 0) return cudaSuccess;
-  fused_project_bwd_kernel<<<grid_for(n), kBlock, 0, st>>>(pos, rgb, opa, quat, scale, n, scale_act, cam, near_plane,
-                                                           half_w, half_h, offsets_g, count, grad_inst, g_pos, g_rgb, g_opa,
-                                                           g_quat, g_scale);
+#define GS_LAUNCH_PBWD(D, GW)                                                                                     \
+  fused_project_bwd_kernel<D, GW><<<grid_for(n), kBlock, 0, st>>>(pos, rgb, opa, quat, scale, n, scale_act, cam,  \
+                                                                  near_plane, half_w, half_h, offsets_g, count,  \
+                                                                  grad_inst, g_pos, g_rgb, g_opa, g_quat, g_scale)
+  if (d == 3) GS_LAUNCH_PBWD(3, GS_GREC);
+  else if (d == 27) GS_LAUNCH_PBWD(27, 36);
+  else GS_LAUNCH_PBWD(48, 56);
+#undef GS_LAUNCH_PBWD
   return cudaGetLastError();
 }

@@ -75,7 +75,8 @@ struct gs_ctx {
   // per instance
   DevBuf keys_in, keys_out, vals_in, vals_out, pA, pB, pC, grad_inst;
   // per tile / misc
-  DevBuf tile_accum, tile_neff, cub_tmp, counters, img_dev, gimg_dev;
+  DevBuf tile_accum, tile_neff, cub_tmp, counters, img_dev, gimg_dev, rays;
+  float* host_rays = nullptr;             // pinned: rays_o, lefttop, dx, dy (SH colour only)
   unsigned long long* host_m = nullptr;   // pinned: {M}
   // state of the last forward
   bool have_forward = false;
@@ -106,6 +107,7 @@ extern "C" int gs_ctx_create(gs_ctx** out) {
   if (!c) return gs_set_error_msg(GS_ERR_INVALID_ARG, "gs_ctx_create: out of host memory");
   GS_CUDA_TRY(cudaGetDevice(&c->device));
   cudaError_t e = cudaMallocHost(reinterpret_cast<void**>(&c->host_m), 64);
+  if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&c->host_rays), 64);
   if (e != cudaSuccess) {
     delete c;
     return gs_set_error(e, "cudaMallocHost");
@@ -119,9 +121,10 @@ extern "C" void gs_ctx_destroy(gs_ctx* c) {
   cudaDeviceSynchronize();
   DevBuf* bufs[] = {&c->rec, &c->count, &c->offsets, &c->dkey_in, &c->dkey_out, &c->perm, &c->iota, &c->offsets_g, &c->keys_in, &c->keys_out,
                     &c->vals_in, &c->vals_out, &c->pA, &c->pB, &c->pC, &c->grad_inst, &c->tile_accum, &c->tile_neff,
-                    &c->cub_tmp, &c->counters, &c->img_dev, &c->gimg_dev};
+                    &c->cub_tmp, &c->counters, &c->img_dev, &c->gimg_dev, &c->rays};
   for (DevBuf* b : bufs) b->release();
   if (c->host_m) cudaFreeHost(c->host_m);
+  if (c->host_rays) cudaFreeHost(c->host_rays);
   if (c->ev_ok)
     for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
   delete c;
@@ -137,7 +140,8 @@ extern "C" int gs_render_forward(gs_ctx* c, const float* pos, const float* rgb, 
                                  const float* scale, int n, int d, int scale_activation, const gs_camera* cam,
                                  float* image, int64_t* culling_mask, gs_stream_t stream) {
   if (!c || !cam || n < 0) return gs_set_error_msg(GS_ERR_INVALID_ARG, "gs_render_forward: bad arguments");
-  if (d != 3) return gs_set_error_msg(GS_ERR_UNSUPPORTED, "gs_render_forward: only d == 3 (RGB) is implemented");
+  if (d != 3 && gs_sh_basis_count(d) == 0)
+    return gs_set_error_msg(GS_ERR_UNSUPPORTED, "gs_render_forward: colour width must be 3 (RGB), 27 (SH deg 2) or 48 (SH deg 3)");
   if (cam->width <= 0 || cam->height <= 0 || !(cam->focal_x > 0.f) || !(cam->focal_y > 0.f))
     return gs_set_error_msg(GS_ERR_INVALID_ARG, "gs_render_forward: bad camera");
   cudaStream_t st = (cudaStream_t)stream;
@@ -188,12 +192,39 @@ extern "C" int gs_render_forward(gs_ctx* c, const float* pos, const float* rgb, 
     c->iota_n = N;
   }
 
+  if (d != 3) {
+    // world-space ray set-up for per-pixel SH, reference splatter.py:305-321 (RayInfo):
+    // c2w = inverse(w2c); rays_o = -c2w t; lefttop = c2w (((-Wp/2+.5)/fx, (-Hp/2+.5)/fy, 1) - t)
+    GS_CUDA_TRY(c->rays.reserve(64, st));
+    double m3[9], inv[9];
+    for (int k = 0; k < 9; ++k) m3[k] = cam->rot[k];
+    double det3 = m3[0] * (m3[4] * m3[8] - m3[5] * m3[7]) - m3[1] * (m3[3] * m3[8] - m3[5] * m3[6]) +
+                  m3[2] * (m3[3] * m3[7] - m3[4] * m3[6]);
+    inv[0] = (m3[4] * m3[8] - m3[5] * m3[7]) / det3;
+    inv[1] = (m3[2] * m3[7] - m3[1] * m3[8]) / det3;
+    inv[2] = (m3[1] * m3[5] - m3[2] * m3[4]) / det3;
+    inv[3] = (m3[5] * m3[6] - m3[3] * m3[8]) / det3;
+    inv[4] = (m3[0] * m3[8] - m3[2] * m3[6]) / det3;
+    inv[5] = (m3[2] * m3[3] - m3[0] * m3[5]) / det3;
+    inv[6] = (m3[3] * m3[7] - m3[4] * m3[6]) / det3;
+    inv[7] = (m3[1] * m3[6] - m3[0] * m3[7]) / det3;
+    inv[8] = (m3[0] * m3[4] - m3[1] * m3[3]) / det3;
+    double lt[3] = {(-(double)g.wp / 2 + 0.5) / cam->focal_x - cam->tran[0],
+                    (-(double)g.hp / 2 + 0.5) / cam->focal_y - cam->tran[1], 1.0 - cam->tran[2]};
+    for (int k = 0; k < 3; ++k) {
+      c->host_rays[k] = (float)(-(inv[3 * k] * cam->tran[0] + inv[3 * k + 1] * cam->tran[1] + inv[3 * k + 2] * cam->tran[2]));
+      c->host_rays[3 + k] = (float)(inv[3 * k] * lt[0] + inv[3 * k + 1] * lt[1] + inv[3 * k + 2] * lt[2]);
+      c->host_rays[6 + k] = (float)(inv[3 * k] / cam->focal_x);
+      c->host_rays[9 + k] = (float)(inv[3 * k + 1] / cam->focal_y);
+    }
+    GS_CUDA_TRY(cudaMemcpyAsync(c->rays.p, c->host_rays, 48, cudaMemcpyHostToDevice, st));
+  }
   // 1. projection + activations + tile rectangle
   c->ev_fwd_valid = false;
   gs_mark(c, 0, st);
   GS_CUDA_TRY(cudaMemsetAsync(c->counters.p, 0, 64, st));
   GS_CUDA_TRY(cudaMemsetAsync(c->count.as<uint32_t>() + N, 0, 4, st));
-  GS_CUDA_TRY(gs_launch_fused_project(pos, rgb, opa, quat, scale, n, scale_activation, dc, grid, cam->near_plane,
+  GS_CUDA_TRY(gs_launch_fused_project(pos, rgb, opa, quat, scale, n, d, scale_activation, dc, grid, cam->near_plane,
                                       half_w, half_h, c->rec.as<GsRec>(), c->count.as<uint32_t>(),
                                       c->dkey_in.as<uint32_t>(), culling_mask, c->counters.as<unsigned int>(), st));
   // 2. (a) exclusive scan of the tile counts in Gaussian-id order -> gradient-row bases and M;
@@ -232,7 +263,8 @@ extern "C" int gs_render_forward(gs_ctx* c, const float* pos, const float* rgb, 
 
   gs_mark(c, 2, st);
   GS_CUDA_TRY(c->pA.reserve(M * 16 + 16, st));
-  GS_CUDA_TRY(c->pC.reserve(M * 16 + 16, st));
+  const size_t crow = d == 3 ? 16 : (size_t)gs_sh_stream_width(d) * 4;   // colour / SH stream row bytes
+  GS_CUDA_TRY(c->pC.reserve(M * crow + 16, st));
   GS_CUDA_TRY(c->pB.reserve((M + 2) * 8, st));
   if (m > 0) {
     GS_CUDA_TRY(c->keys_in.reserve(M * 4 + 16, st));
@@ -258,13 +290,27 @@ extern "C" int gs_render_forward(gs_ctx* c, const float* pos, const float* rgb, 
   // 5. tile ranges + packed sorted record streams
   if (m == 0) gs_mark(c, 3, st);
   gs_mark(c, 4, st);
-  GS_CUDA_TRY(gs_launch_pack_sorted(c->keys_out.as<uint32_t>(), c->vals_out.as<uint32_t>(), m, g.n_tiles, g.ntx,
-                                    c->rec.as<GsRec>(), c->offsets_g.as<uint32_t>(), c->pA.as<float4>(),
-                                    c->pB.as<float2>(), c->pC.as<float4>(), c->tile_accum.as<int>(), st));
+  if (d == 3) {
+    GS_CUDA_TRY(gs_launch_pack_sorted(c->keys_out.as<uint32_t>(), c->vals_out.as<uint32_t>(), m, g.n_tiles, g.ntx,
+                                      c->rec.as<GsRec>(), c->offsets_g.as<uint32_t>(), c->pA.as<float4>(),
+                                      c->pB.as<float2>(), c->pC.as<float4>(), c->tile_accum.as<int>(), st));
+  } else {
+    GS_CUDA_TRY(gs_launch_pack_sorted_sh(c->keys_out.as<uint32_t>(), c->vals_out.as<uint32_t>(), m, g.n_tiles, g.ntx,
+                                         c->rec.as<GsRec>(), c->offsets_g.as<uint32_t>(), rgb, d,
+                                         gs_sh_stream_width(d), c->pA.as<float4>(), c->pB.as<float2>(),
+                                         c->pC.as<float>(), c->tile_accum.as<int>(), st));
+  }
   // 6. blend
   gs_mark(c, 5, st);
-  GS_CUDA_TRY(gs_launch_blend_fwd(c->pA.as<float4>(), c->pB.as<float2>(), c->pC.as<float4>(), c->tile_accum.as<int>(),
-                                  g, image, c->tile_neff.as<int>(), st));
+  if (d == 3) {
+    GS_CUDA_TRY(gs_launch_blend_fwd(c->pA.as<float4>(), c->pB.as<float2>(), c->pC.as<float4>(),
+                                    c->tile_accum.as<int>(), g, image, c->tile_neff.as<int>(), st));
+  } else {
+    const float* rp = c->rays.as<float>();
+    GsRayPtrs rays{rp, rp + 3, rp + 6, rp + 9};
+    GS_CUDA_TRY(gs_launch_blend_sh_fwd(c->pA.as<float4>(), c->pB.as<float2>(), c->pC.as<float>(), d,
+                                       c->tile_accum.as<int>(), g, rays, image, c->tile_neff.as<int>(), st));
+  }
   gs_mark(c, 6, st);
   c->ev_fwd_valid = c->timing && c->ev_ok;
 
@@ -290,15 +336,26 @@ extern "C" int gs_render_backward(gs_ctx* c, const float* pos, const float* rgb,
   if (!c->have_forward) return gs_set_error_msg(GS_ERR_NO_FORWARD, "gs_render_backward: no forward on this ctx");
   cudaStream_t st = (cudaStream_t)stream;
   size_t M = (size_t)c->m;
-  GS_CUDA_TRY(c->grad_inst.reserve(M * GS_GREC * 4 + 16, st));
+  const int d = c->d;
+  const size_t grow = d == 3 ? (size_t)GS_GREC * 4 : (size_t)gs_sh_grad_width(d) * 4;
+  GS_CUDA_TRY(c->grad_inst.reserve(M * grow + 16, st));
   c->ev_bwd_valid = false;
   gs_mark(c, 7, st);
-  if (c->m > 0)
-    GS_CUDA_TRY(gs_launch_blend_bwd(c->pA.as<float4>(), c->pB.as<float2>(), c->pC.as<float4>(),
-                                    c->tile_accum.as<int>(), c->geom, image, grad_image, c->grad_inst.as<float>(),
-                                    st));
+  if (c->m > 0) {
+    if (d == 3) {
+      GS_CUDA_TRY(gs_launch_blend_bwd(c->pA.as<float4>(), c->pB.as<float2>(), c->pC.as<float4>(),
+                                      c->tile_accum.as<int>(), c->geom, image, grad_image, c->grad_inst.as<float>(),
+                                      st));
+    } else {
+      const float* rp = c->rays.as<float>();
+      GsRayPtrs rays{rp, rp + 3, rp + 6, rp + 9};
+      GS_CUDA_TRY(gs_launch_blend_sh_bwd(c->pA.as<float4>(), c->pB.as<float2>(), c->pC.as<float>(), d,
+                                         c->tile_accum.as<int>(), c->geom, rays, image, grad_image,
+                                         c->grad_inst.as<float>(), st));
+    }
+  }
   gs_mark(c, 8, st);
-  GS_CUDA_TRY(gs_launch_fused_project_bwd(pos, rgb, opa, quat, scale, c->n, c->scale_act, c->cam, c->near_plane,
+  GS_CUDA_TRY(gs_launch_fused_project_bwd(pos, rgb, opa, quat, scale, c->n, d, c->scale_act, c->cam, c->near_plane,
                                           c->half_w, c->half_h, c->offsets_g.as<uint32_t>(), c->count.as<uint32_t>(),
                                           c->grad_inst.as<float>(),
                                           grad_pos, grad_rgb, grad_opa, grad_quat, grad_scale, st));

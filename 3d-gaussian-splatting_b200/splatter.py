@@ -74,9 +74,9 @@ class Splatter(nn.Module):
         images: optional per-view uint8 HxWx3 ground truth (reference keeps them on the GPU)."""
         super().__init__()
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-        if use_sh_coeff:
-            raise NotImplementedError("fused path: SH colour not implemented yet (RGB only)")
-        self.use_sh_coeff = use_sh_coeff
+        self.use_sh_coeff = use_sh_coeff          # rgb is [N,27] (degree 2) / [N,48] (degree 3) raw SH coefficients
+        if bool(use_sh_coeff) != (gaussians["rgb"].shape[1] != 3):
+            raise ValueError("use_sh_coeff must match the colour width (3 = RGB logits, 27 / 48 = SH)")
         self.near = near
         self.tile_culling_prob_thresh = tile_culling_prob_thresh
         self.scale_activation = scale_activation

@@ -195,6 +195,22 @@ def sh_basis9(d):
         C2[0] * xy, C2[1] * yz, C2[2] * (2.0 * zz - xx - yy), C2[3] * xz, C2[4] * (xx - yy)], dim=-1)
 
 
+C3 = (-0.5900435899266435, 2.890611442640554, -0.4570457994644658, 0.3731763325901154, -0.4570457994644658,
+      1.445305721320277, -0.5900435899266435)
+
+
+def sh_basis16(d):
+    """Degree-3 extension (svox2 convention; the reference defines C3 at gaussian.cu:395-403 but
+    never evaluates it)."""
+    x, y, z = d.unbind(-1)
+    xx, yy, zz, xy = x * x, y * y, z * z, x * y
+    hi = torch.stack([
+        C3[0] * y * (3 * xx - yy), C3[1] * xy * z, C3[2] * y * (4 * zz - xx - yy),
+        C3[3] * z * (2 * zz - 3 * xx - 3 * yy), C3[4] * x * (4 * zz - xx - yy), C3[5] * z * (xx - yy),
+        C3[6] * x * (xx - 3 * yy)], dim=-1)
+    return torch.cat([sh_basis9(d), hi], dim=-1)
+
+
 def ray_info(rot, tran, Hp, Wp, fx, fy):
     """splatter.py:305-321 -> rays_o, lefttop, dx, dy (world space)."""
     c2w = torch.inverse(rot)
@@ -255,8 +271,9 @@ def draw(pos, rgb, opa, cov, tile_n_point_accum, Hp, Wp, fx, fy,
             gy = (ty * 16 + ix).to(dt).reshape(16, 1).expand(16, 16).reshape(-1, 1)
             dirs = lefttop.reshape(1, 3) + gx * vec_dx.reshape(1, 3) + gy * vec_dy.reshape(1, 3) - rays_o.reshape(1, 3)
             dirs = dirs / (dirs.norm(dim=-1, keepdim=True) + 1e-7)                # :852-859
-            SH = sh_basis9(dirs)                                                  # [256,9]
-            coef = rgb[s:e].reshape(-1, 3, 9)
+            K = rgb.shape[1] // 3
+            SH = sh_basis9(dirs) if K == 9 else sh_basis16(dirs)                  # [256,K]
+            coef = rgb[s:e].reshape(-1, 3, K)
             col = torch.sigmoid(torch.einsum("pk,nck->pnc", SH, coef))            # :936-948
             tile_rgb = (wgt.unsqueeze(-1) * col).sum(1)
         else:

@@ -70,6 +70,21 @@ def main(out_dir):
                         grad_pos=cpu(t["pos"].grad), grad_rgb=cpu(t["rgb"].grad), grad_opa=cpu(t["opa"].grad),
                         grad_cov=cpu(t["cov"].grad))
 
+    # ---- draw_sh.npz : draw + draw_backward with per-pixel SH-27 colour ---------------------------
+    inst, cam, grad_img, rays = GC.draw_sh_inputs()
+    counts = inst["accum"][1:] - inst["accum"][:-1]
+    assert int(counts.max()) <= 160, "outside the reference SH backward's safe regime"
+    t = {k: inst[k].to(dev).float().contiguous().requires_grad_(True) for k in ("pos", "rgb", "opa", "cov")}
+    r = [x.to(dev).float().contiguous() for x in rays]
+    img = rref.draw(t["pos"], t["rgb"], t["opa"], t["cov"], inst["accum"].to(dev), cam.Hp, cam.Wp, cam.fx, cam.fy,
+                    False, False, True, True, r[0], r[1], r[2], r[3])
+    img.backward(grad_img.to(dev))
+    np.savez_compressed(os.path.join(out_dir, "draw_sh.npz"), image=cpu(img),
+                        in_pos=cpu(inst["pos"]), in_rgb=cpu(inst["rgb"]), in_opa=cpu(inst["opa"]),
+                        in_cov=cpu(inst["cov"]), in_accum=cpu(inst["accum"]),
+                        grad_pos=cpu(t["pos"].grad), grad_rgb=cpu(t["rgb"].grad), grad_opa=cpu(t["opa"].grad),
+                        grad_cov=cpu(t["cov"].grad))
+
     # ---- frame_c1.npz : the reference's whole per-frame pipeline ---------------------------
     g, v, cam, go = GC.frame_inputs()
     c = GC.CASES["frame_c1.npz"]

@@ -12,6 +12,7 @@ CASES = {
     "project.npz": dict(n=2000, w=256, h=256, k=1),
     "tiles.npz": dict(n=3000, w=320, h=200, k=0),
     "draw_rgb.npz": dict(n=1500, w=128, h=96, opa=(0.005, 0.05)),
+    "draw_sh.npz": dict(n=1000, w=128, h=96, opa=(0.005, 0.05), sh_dim=27),      # max tile <= 160
     # whole-pipeline case: must sit inside the reference's own limits (SURVEY.md hazards 1, 4):
     # max tile count 86 <= MAXP = n//20 = 100 (dense-list capacity, splatter.py:569) and NO two
     # instances of a tile collide in the reference's quantised fp32 sort key (splatter.py:610-612)
@@ -45,6 +46,16 @@ def draw_inputs():
     gen = torch.Generator().manual_seed(202)
     grad_img = torch.rand(cam.Hp, cam.Wp, 3, generator=gen) * 2 - 1
     return inst, cam, grad_img
+
+
+def draw_sh_inputs():
+    c = CASES["draw_sh.npz"]
+    g, v, cam = scene(c["n"], c["w"], c["h"], opa_range=c["opa"], sh_dim=c["sh_dim"])
+    inst = sorted_instances_cpu(g, cam, use_sh=True)
+    gen = torch.Generator().manual_seed(303)
+    grad_img = torch.rand(cam.Hp, cam.Wp, 3, generator=gen) * 2 - 1
+    rays = O.ray_info(cam.rot, cam.tran, cam.Hp, cam.Wp, cam.fx, cam.fy)
+    return inst, cam, grad_img, rays
 
 
 def frame_inputs():
@@ -114,6 +125,16 @@ def check_oracle_against(name, gold):
         assert rel_err(t["rgb"].grad, gold["grad_rgb"]) < 1e-3
         assert rel_err(t["opa"].grad, gold["grad_opa"]) < 1e-3
         assert rel_err(t["cov"].grad, gold["grad_cov"]) < 1e-3
+        assert rel_err(t["pos"].grad[:, :2], gold["grad_pos"][:, :2]) < 1e-3
+    elif name == "draw_sh.npz":
+        inst, cam, grad_img, rays = draw_sh_inputs()
+        t = {k: gold["in_" + k].double().requires_grad_(True) for k in ("pos", "rgb", "opa", "cov")}
+        img = O.draw(t["pos"], t["rgb"], t["opa"], t["cov"], gold["in_accum"], cam.Hp, cam.Wp, cam.fx, cam.fy, True,
+                     *[r.double() for r in rays])
+        img.backward(grad_img.double())
+        assert abs_err(img, gold["image"]) < 1e-4
+        for k in ("rgb", "opa", "cov"):
+            assert rel_err(t[k].grad, gold["grad_" + k]) < 1e-3, k
         assert rel_err(t["pos"].grad[:, :2], gold["grad_pos"][:, :2]) < 1e-3
     elif name == "frame_c1.npz":
         g, v, cam, go = frame_inputs()

@@ -67,6 +67,20 @@ def test_fused_frame_vs_oracle(gs, cuda, n, w, h, k, opa):
     assert float((ours != want).float().mean()) < 0.01
 
 
+@pytest.mark.parametrize("sh_dim,opa", [(27, (0.005, 0.05)), (27, (0.3, 0.95)), (48, (0.05, 0.9))])
+def test_fused_frame_sh_vs_oracle(gs, cuda, sh_dim, opa):
+    n, w, h = 2500, 112, 80
+    g, v, cam = scene(n, w, h, k=1, sh_dim=sh_dim, opa_range=opa)
+    go = S.make_grad_output(h, w, 0) * (h * w)
+    oimg, ograds, aux = _oracle_frame(g, cam, go, use_sh_coeff=True)
+    sp = _splatter(g, [v], cuda, use_sh_coeff=True)
+    img = sp(0)
+    assert abs_err(img, oimg) < IMG_ATOL
+    img.backward(go.to(cuda))
+    for name in ("pos", "rgb", "opa", "quat", "scale"):
+        assert rel_err(getattr(sp.gaussian_3ds, name).grad, ograds[name]) < GRAD_RTOL, name
+
+
 def test_fused_frame_vs_reference_pipeline(gs, ref, cuda):
     """P5: whole reference pipeline (its CUDA build + its renderer.py + the splatter.py call
     sequence) vs our fused path on a C1-class scene inside the reference's safe regime."""

@@ -121,7 +121,7 @@ def test_render_gradients_finite_difference():
         assert abs(fd - an) <= 1e-4 * max(abs(fd), abs(an)) + 1e-12, (name, fd, an)
 
 
-@pytest.mark.parametrize("name", ["project.npz", "tiles.npz", "draw_rgb.npz", "frame_c1.npz"])
+@pytest.mark.parametrize("name", ["project.npz", "tiles.npz", "draw_rgb.npz", "draw_sh.npz", "frame_c1.npz"])
 def test_oracle_matches_reference_golden(name):
     gold = load_golden(name)
     if gold is None:

@@ -248,3 +248,55 @@ def test_world2camera_and_jacobian(gs, cuda):
     zero = torch.zeros_like(x)
     want = torch.stack([1 / z, zero, -x / z ** 2, zero, 1 / z, -y / z ** 2, x / r, y / r, z / r], -1).reshape(-1, 3, 3)
     assert rel_err(jac, want) < 1e-5
+
+
+# ---- SH colour (use_sh_coeff): per-pixel ray SH evaluated inside the blend -----------------
+def _sh_case(n, w, h, sh_dim, opa_range, seed=0):
+    g, v, cam = scene(n, w, h, seed=seed, sh_dim=sh_dim, opa_range=opa_range)
+    inst = sorted_instances_cpu(g, cam, use_sh=True)
+    gen = torch.Generator().manual_seed(seed + 21)
+    grad_img = torch.rand(cam.Hp, cam.Wp, 3, generator=gen) * 2 - 1
+    rays = O.ray_info(cam.rot, cam.tran, cam.Hp, cam.Wp, cam.fx, cam.fy)
+    return cam, inst, grad_img, rays
+
+
+def _run_draw_sh(R, inst, cam, grad_img, rays, dev):
+    t = {k: inst[k].to(dev).float().contiguous().requires_grad_(True) for k in ("pos", "rgb", "opa", "cov")}
+    r = [x.to(dev).float().contiguous() for x in rays]
+    img = R.draw(t["pos"], t["rgb"], t["opa"], t["cov"], inst["accum"].to(dev), cam.Hp, cam.Wp, cam.fx, cam.fy, False,
+                 False, True, True, r[0], r[1], r[2], r[3])
+    img.backward(grad_img.to(dev))
+    return img.detach(), {k: t[k].grad for k in t}
+
+
+@pytest.mark.parametrize("sh_dim,case", [(27, "safe"), (27, "opaque"), (48, "safe"), (48, "opaque")])
+def test_draw_sh_forward_backward_vs_oracle(gs, cuda, sh_dim, case):
+    _, renderer = gs
+    if case == "safe":
+        cam, inst, gi, rays = _sh_case(1500, 96, 64, sh_dim, (0.005, 0.05))
+    else:
+        cam, inst, gi, rays = _sh_case(3000, 64, 48, sh_dim, (0.4, 0.95), seed=3)
+    img, grads = _run_draw_sh(renderer, inst, cam, gi, rays, cuda)
+    t = {k: inst[k].double().requires_grad_(True) for k in ("pos", "rgb", "opa", "cov")}
+    r64 = [x.double() for x in rays]
+    oimg = O.draw(t["pos"], t["rgb"], t["opa"], t["cov"], inst["accum"], cam.Hp, cam.Wp, cam.fx, cam.fy, True, *r64)
+    oimg.backward(gi.double())
+    assert abs_err(img, oimg) < IMG_ATOL
+    for k in ("rgb", "opa", "cov"):
+        assert rel_err(grads[k], t[k].grad) < GRAD_RTOL, k
+    assert rel_err(grads["pos"][:, :2], t["pos"].grad[:, :2]) < GRAD_RTOL
+
+
+def test_draw_sh_vs_reference_build(gs, ref, cuda):
+    """P4 for SH-27 inside the reference's safe regime (<= 160 instances per tile in backward)."""
+    _, renderer = gs
+    _, rref = ref
+    cam, inst, gi, rays = _sh_case(2500, 256, 192, 27, (0.005, 0.05))
+    counts = inst["accum"][1:] - inst["accum"][:-1]
+    assert int(counts.max()) <= 160
+    a_img, a_g = _run_draw_sh(renderer, inst, cam, gi, rays, cuda)
+    b_img, b_g = _run_draw_sh(rref, inst, cam, gi, rays, cuda)
+    assert abs_err(a_img, b_img) < IMG_ATOL
+    for k in ("rgb", "opa", "cov"):
+        assert rel_err(a_g[k], b_g[k]) < GRAD_RTOL, k
+    assert rel_err(a_g["pos"][:, :2], b_g["pos"][:, :2]) < GRAD_RTOL
