@@ -295,6 +295,48 @@ struct RenderContext {
     return v;
   }
 
+  // fused clamp + centre crop: returns (final[H,W,3], raw padded[Hp,Wp,3], mask)
+  std::tuple<torch::Tensor, torch::Tensor, torch::Tensor> forward_final(
+      torch::Tensor pos, torch::Tensor rgb, torch::Tensor opa, torch::Tensor quat, torch::Tensor scale, int width,
+      int height, float fx, float fy, torch::Tensor rot, torch::Tensor tran, float near, float thresh,
+      int scale_activation) {
+    GS_CHECK_F32(pos); GS_CHECK_F32(rgb); GS_CHECK_F32(opa); GS_CHECK_F32(quat); GS_CHECK_F32(scale);
+    int64_t n = pos.size(0);
+    TORCH_CHECK(pos.dim() == 2 && pos.size(1) == 3 && opa.numel() == n && quat.numel() == n * 4 &&
+                    scale.numel() == n * 3 && rgb.dim() == 2 && rgb.size(0) == n, "RenderContext.forward: bad shapes");
+    TORCH_CHECK(pos.device().index() == device, "RenderContext was created on another device");
+    c10::cuda::CUDAGuard guard(pos.device());
+    gs_camera cam = make_cam(width, height, fx, fy, rot, tran, near, thresh);
+    int wp = (width + 15) / 16 * 16, hp = (height + 15) / 16 * 16;
+    auto raw = torch::empty({hp, wp, 3}, pos.options());
+    auto fin = torch::empty({height, width, 3}, pos.options());
+    auto mask = torch::empty({n}, pos.options().dtype(at::kLong));
+    check_rc(gs_render_forward_final(ctx, fp(pos), fp(rgb), fp(opa), fp(quat), fp(scale), (int)n, (int)rgb.size(1),
+                                     scale_activation, &cam, fpm(raw), fpm(fin), mask.data_ptr<int64_t>(),
+                                     cur_stream()),
+             "gs_render_forward_final");
+    return {fin, raw, mask};
+  }
+
+  void backward_final_into(torch::Tensor pos, torch::Tensor rgb, torch::Tensor opa, torch::Tensor quat,
+                           torch::Tensor scale, torch::Tensor raw, torch::Tensor grad_final, torch::Tensor g_pos,
+                           torch::Tensor g_rgb, torch::Tensor g_opa, torch::Tensor g_quat, torch::Tensor g_scale) {
+    GS_CHECK_F32(pos); GS_CHECK_F32(rgb); GS_CHECK_F32(opa); GS_CHECK_F32(quat); GS_CHECK_F32(scale);
+    GS_CHECK_F32(raw); GS_CHECK_F32(g_pos); GS_CHECK_F32(g_rgb); GS_CHECK_F32(g_opa); GS_CHECK_F32(g_quat);
+    GS_CHECK_F32(g_scale);
+    TORCH_CHECK(grad_final.is_cuda() && grad_final.scalar_type() == at::kFloat && grad_final.dim() == 3 &&
+                    grad_final.size(2) == 3, "RenderContext.backward_final_into: grad_final must be [H,W,3] float32");
+    TORCH_CHECK(g_pos.numel() == pos.numel() && g_rgb.numel() == rgb.numel() && g_opa.numel() == opa.numel() &&
+                    g_quat.numel() == quat.numel() && g_scale.numel() == scale.numel(),
+                "RenderContext.backward_final_into: gradient buffers must match their parameters");
+    TORCH_CHECK(reinterpret_cast<uintptr_t>(g_quat.data_ptr()) % 16 == 0, "grad_quat must be 16-byte aligned");
+    c10::cuda::CUDAGuard guard(pos.device());
+    auto gf = grad_final.contiguous();
+    check_rc(gs_render_backward_final(ctx, fp(pos), fp(rgb), fp(opa), fp(quat), fp(scale), fp(raw), fp(gf), fpm(g_pos),
+                                      fpm(g_rgb), fpm(g_opa), fpm(g_quat), fpm(g_scale), cur_stream()),
+             "gs_render_backward_final");
+  }
+
   void backward_into(torch::Tensor pos, torch::Tensor rgb, torch::Tensor opa, torch::Tensor quat, torch::Tensor scale,
                      torch::Tensor image, torch::Tensor grad_image, torch::Tensor g_pos, torch::Tensor g_rgb,
                      torch::Tensor g_opa, torch::Tensor g_quat, torch::Tensor g_scale) {
@@ -380,6 +422,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def("forward", &RenderContext::forward)
       .def("backward", &RenderContext::backward)
       .def("backward_into", &RenderContext::backward_into)
+      .def("forward_final", &RenderContext::forward_final)
+      .def("backward_final_into", &RenderContext::backward_final_into)
       .def("stats", &RenderContext::stats)
       .def("set_timing", &RenderContext::set_timing)
       .def("stage_ms", &RenderContext::stage_ms)

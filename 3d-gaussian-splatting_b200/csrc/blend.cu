@@ -57,7 +57,8 @@ __global__ void __launch_bounds__(FWD_THREADS) blend_fwd_kernel(const float4* __
                                                                  const int* __restrict__ tile_accum, int wp, int hp,
                                                                  int ntx, float fx, float fy,
                                                                  float* __restrict__ image,
-                                                                 int* __restrict__ tile_neff) {
+                                                                 int* __restrict__ tile_neff,
+                                                                 float* __restrict__ final_img, GsCrop crop) {
   __shared__ __align__(16) FwdSmem sm;
   const int tile = blockIdx.x;
   const int tid = threadIdx.x;
@@ -156,6 +157,11 @@ __global__ void __launch_bounds__(FWD_THREADS) blend_fwd_kernel(const float4* __
   o[0] = make_float4(cr[0], cg[0], cb[0], cr[1]);
   o[1] = make_float4(cg[1], cb[1], cr[2], cg[2]);
   o[2] = make_float4(cb[2], cr[3], cg[3], cb[3]);
+  if (final_img) {
+#pragma unroll
+    for (int p = 0; p < FWD_PX; ++p)
+      gs_store_final(final_img, ix0 + p, iy, crop.left, crop.top, crop.width, crop.height, cr[p], cg[p], cb[p]);
+  }
   if (tile_neff && tid == 0) tile_neff[tile] = consumed;
 }
 
@@ -187,7 +193,8 @@ __global__ void __launch_bounds__(32 * WARPS) blend_bwd_kernel(const float4* __r
                                                                 int ntx, float fx, float fy,
                                                                 const float* __restrict__ image,
                                                                 const float* __restrict__ grad_image,
-                                                                float* __restrict__ grad_inst) {
+                                                                float* __restrict__ grad_inst, int grad_is_final,
+                                                                GsCrop crop) {
   constexpr int THREADS = 32 * WARPS;
   constexpr int PX = 256 / THREADS;          // 8 (1 warp) or 4 (2 warps)
   constexpr int TPR = GS_TILE / PX;          // threads per pixel row
@@ -212,14 +219,25 @@ __global__ void __launch_bounds__(32 * WARPS) blend_bwd_kernel(const float4* __r
   float T[PX], R[PX], gr[PX], gg[PX], gb[PX];
   {
     const size_t off = ((size_t)iy * wp + ix0) * 3;     // PX*12 contiguous, 16-byte aligned bytes
-    const float4* gi = reinterpret_cast<const float4*>(grad_image + off);
     const float4* im = reinterpret_cast<const float4*>(image + off);
     float gbuf[PX * 3], ibuf[PX * 3];
 #pragma unroll
     for (int q = 0; q < PX * 3 / 4; ++q) {
-      const float4 g4 = gi[q], i4 = im[q];
-      gbuf[4 * q] = g4.x; gbuf[4 * q + 1] = g4.y; gbuf[4 * q + 2] = g4.z; gbuf[4 * q + 3] = g4.w;
+      const float4 i4 = im[q];
       ibuf[4 * q] = i4.x; ibuf[4 * q + 1] = i4.y; ibuf[4 * q + 2] = i4.z; ibuf[4 * q + 3] = i4.w;
+    }
+    if (!grad_is_final) {
+      const float4* gi = reinterpret_cast<const float4*>(grad_image + off);
+#pragma unroll
+      for (int q = 0; q < PX * 3 / 4; ++q) {
+        const float4 g4 = gi[q];
+        gbuf[4 * q] = g4.x; gbuf[4 * q + 1] = g4.y; gbuf[4 * q + 2] = g4.z; gbuf[4 * q + 3] = g4.w;
+      }
+    } else {
+#pragma unroll
+      for (int p = 0; p < PX; ++p)
+        gs_load_final_grad(grad_image, ibuf + 3 * p, ix0 + p, iy, crop.left, crop.top, crop.width, crop.height,
+                           gbuf[3 * p], gbuf[3 * p + 1], gbuf[3 * p + 2]);
     }
 #pragma unroll
     for (int p = 0; p < PX; ++p) {
@@ -498,22 +516,23 @@ inline size_t legacy_ws_layout(int m, int d, LegacyWs* ws, char* base) {
 }  // namespace
 
 cudaError_t gs_launch_blend_fwd(const float4* pA, const float2* pB, const float4* pC, const int* tile_accum,
-                                const GsFrameGeom& g, float* image, int* tile_neff, cudaStream_t st) {
+                                const GsFrameGeom& g, float* image, int* tile_neff, float* final_img,
+                                const GsCrop& crop, cudaStream_t st) {
   blend_fwd_kernel<<<g.n_tiles, FWD_THREADS, 0, st>>>(pA, pB, pC, tile_accum, g.wp, g.hp, g.ntx, g.fx, g.fy, image,
-                                                      tile_neff);
+                                                      tile_neff, final_img, crop);
   return cudaGetLastError();
 }
 
 cudaError_t gs_launch_blend_bwd(const float4* pA, const float2* pB, const float4* pC, const int* tile_accum,
                                 const GsFrameGeom& g, const float* image, const float* grad_image, float* grad_inst,
-                                cudaStream_t st) {
+                                int grad_is_final, const GsCrop& crop, cudaStream_t st) {
   static const int warps = getenv("GS_BWD_WARPS") ? atoi(getenv("GS_BWD_WARPS")) : 2;   // A/B knob: 1 = one warp x 8 px
   if (warps == 2)
     blend_bwd_kernel<2><<<g.n_tiles, 64, 0, st>>>(pA, pB, pC, tile_accum, g.wp, g.hp, g.ntx, g.fx, g.fy, image,
-                                                  grad_image, grad_inst);
+                                                  grad_image, grad_inst, grad_is_final, crop);
   else
     blend_bwd_kernel<1><<<g.n_tiles, 32, 0, st>>>(pA, pB, pC, tile_accum, g.wp, g.hp, g.ntx, g.fx, g.fy, image,
-                                                  grad_image, grad_inst);
+                                                  grad_image, grad_inst, grad_is_final, crop);
   return cudaGetLastError();
 }
 
@@ -562,11 +581,11 @@ extern "C" int gs_draw_fwd(const float* pos, const float* rgb, const float* opa,
   g.fx = focal_x;
   g.fy = focal_y;
   if (d == 3) {
-    GS_CUDA_TRY(gs_launch_blend_fwd(ws.pA, ws.pB, ws.pC, tile_n_point_accum, g, image, nullptr, st));
+    GS_CUDA_TRY(gs_launch_blend_fwd(ws.pA, ws.pB, ws.pC, tile_n_point_accum, g, image, nullptr, nullptr, GsCrop{}, st));
   } else {
     GsRayPtrs r{rays_o, lefttop, vec_dx, vec_dy};
     GS_CUDA_TRY(gs_launch_blend_sh_fwd(ws.pA, ws.pB, reinterpret_cast<float*>(ws.pC), d, tile_n_point_accum, g, r,
-                                       image, nullptr, st));
+                                       image, nullptr, nullptr, GsCrop{}, st));
   }
   return 0;
 }
@@ -601,13 +620,14 @@ extern "C" int gs_draw_bwd(const float* pos, const float* rgb, const float* opa,
   g.fx = focal_x;
   g.fy = focal_y;
   if (d == 3) {
-    GS_CUDA_TRY(gs_launch_blend_bwd(ws.pA, ws.pB, ws.pC, tile_n_point_accum, g, image, grad_image, ws.grad_inst, st));
+    GS_CUDA_TRY(gs_launch_blend_bwd(ws.pA, ws.pB, ws.pC, tile_n_point_accum, g, image, grad_image, ws.grad_inst, 0,
+                                    GsCrop{}, st));
     legacy_unpack_grads_kernel<<<(m + 255) / 256, 256, 0, st>>>(ws.grad_inst, opa, cov, m, grad_pos, grad_rgb,
                                                               grad_opa, grad_cov);
   } else {
     GsRayPtrs r{rays_o, lefttop, vec_dx, vec_dy};
     GS_CUDA_TRY(gs_launch_blend_sh_bwd(ws.pA, ws.pB, reinterpret_cast<float*>(ws.pC), d, tile_n_point_accum, g, r,
-                                       image, grad_image, ws.grad_inst, st));
+                                       image, grad_image, ws.grad_inst, 0, GsCrop{}, st));
     legacy_unpack_grads_sh_kernel<<<(m + 255) / 256, 256, 0, st>>>(ws.grad_inst, gs_sh_grad_width(d), opa, cov, m, d,
                                                                  grad_pos, grad_rgb, grad_opa, grad_cov);
   }

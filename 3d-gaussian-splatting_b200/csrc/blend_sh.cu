@@ -95,7 +95,8 @@ __global__ void __launch_bounds__(64) blend_sh_fwd_kernel(const float4* __restri
                                                            const float* __restrict__ lefttop,
                                                            const float* __restrict__ vdx,
                                                            const float* __restrict__ vdy, float* __restrict__ image,
-                                                           int* __restrict__ tile_neff) {
+                                                           int* __restrict__ tile_neff,
+                                                           float* __restrict__ final_img, GsCrop crop) {
   constexpr int CH = 64, STAGES = 2, PX = 4, SW = sh_sw(K);
   using SM = ShStage<K, CH, STAGES>;
   __shared__ __align__(16) SM sm;
@@ -196,6 +197,11 @@ __global__ void __launch_bounds__(64) blend_sh_fwd_kernel(const float4* __restri
   o[0] = make_float4(cr[0], cg[0], cb[0], cr[1]);
   o[1] = make_float4(cg[1], cb[1], cr[2], cg[2]);
   o[2] = make_float4(cb[2], cr[3], cg[3], cb[3]);
+  if (final_img) {
+#pragma unroll
+    for (int p = 0; p < PX; ++p)
+      gs_store_final(final_img, ix0 + p, iy, crop.left, crop.top, crop.width, crop.height, cr[p], cg[p], cb[p]);
+  }
   if (tile_neff && tid == 0) tile_neff[tile] = consumed;
 }
 
@@ -251,7 +257,8 @@ __global__ void __launch_bounds__(64) blend_sh_bwd_kernel(const float4* __restri
                                                            const float* __restrict__ vdy,
                                                            const float* __restrict__ image,
                                                            const float* __restrict__ grad_image,
-                                                           float* __restrict__ grad_inst) {
+                                                           float* __restrict__ grad_inst, int grad_is_final,
+                                                           GsCrop crop) {
   constexpr int CH = 32, STAGES = 2, PX = 4, SW = sh_sw(K), NV = sh_nv(K), NVP = sh_nvp(K), THREADS = 64;
   constexpr int GREC = (NV + 3) / 4 * 4;
   __shared__ __align__(16) ShBwdSmem<K> smem;
@@ -275,12 +282,21 @@ __global__ void __launch_bounds__(64) blend_sh_bwd_kernel(const float4* __restri
   float T[PX], R[PX], gr[PX], gg[PX], gb[PX];
   {
     const size_t off = ((size_t)iy * wp + ix0) * 3;
-    const float4* gi = reinterpret_cast<const float4*>(grad_image + off);
     const float4* im = reinterpret_cast<const float4*>(image + off);
-    const float4 g0 = gi[0], g1 = gi[1], g2 = gi[2], i0 = im[0], i1 = im[1], i2 = im[2];
-    gr[0] = g0.x; gg[0] = g0.y; gb[0] = g0.z; gr[1] = g0.w;
-    gg[1] = g1.x; gb[1] = g1.y; gr[2] = g1.z; gg[2] = g1.w;
-    gb[2] = g2.x; gr[3] = g2.y; gg[3] = g2.z; gb[3] = g2.w;
+    const float4 i0 = im[0], i1 = im[1], i2 = im[2];
+    if (!grad_is_final) {
+      const float4* gi = reinterpret_cast<const float4*>(grad_image + off);
+      const float4 g0 = gi[0], g1 = gi[1], g2 = gi[2];
+      gr[0] = g0.x; gg[0] = g0.y; gb[0] = g0.z; gr[1] = g0.w;
+      gg[1] = g1.x; gb[1] = g1.y; gr[2] = g1.z; gg[2] = g1.w;
+      gb[2] = g2.x; gr[3] = g2.y; gg[3] = g2.z; gb[3] = g2.w;
+    } else {
+      const float raw[12] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w, i2.x, i2.y, i2.z, i2.w};
+#pragma unroll
+      for (int p = 0; p < PX; ++p)
+        gs_load_final_grad(grad_image, raw + 3 * p, ix0 + p, iy, crop.left, crop.top, crop.width, crop.height, gr[p],
+                           gg[p], gb[p]);
+    }
     R[0] = gr[0] * i0.x + gg[0] * i0.y + gb[0] * i0.z;
     R[1] = gr[1] * i0.w + gg[1] * i1.x + gb[1] * i1.y;
     R[2] = gr[2] * i1.z + gg[2] * i1.w + gb[2] * i2.x;
@@ -429,24 +445,25 @@ int gs_sh_grad_width(int d) { return d == 27 ? (sh_nv(9) + 3) / 4 * 4 : (sh_nv(1
 
 cudaError_t gs_launch_blend_sh_fwd(const float4* pA, const float2* pB, const float* pS, int d, const int* tile_accum,
                                    const GsFrameGeom& g, const GsRayPtrs& r, float* image, int* tile_neff,
-                                   cudaStream_t st) {
+                                   float* final_img, const GsCrop& crop, cudaStream_t st) {
   if (d == 27)
     blend_sh_fwd_kernel<9><<<g.n_tiles, 64, 0, st>>>(pA, pB, pS, tile_accum, g.wp, g.hp, g.ntx, g.fx, g.fy, r.rays_o,
-                                                     r.lefttop, r.dx, r.dy, image, tile_neff);
+                                                     r.lefttop, r.dx, r.dy, image, tile_neff, final_img, crop);
   else
     blend_sh_fwd_kernel<16><<<g.n_tiles, 64, 0, st>>>(pA, pB, pS, tile_accum, g.wp, g.hp, g.ntx, g.fx, g.fy, r.rays_o,
-                                                      r.lefttop, r.dx, r.dy, image, tile_neff);
+                                                      r.lefttop, r.dx, r.dy, image, tile_neff, final_img, crop);
   return cudaGetLastError();
 }
 
 cudaError_t gs_launch_blend_sh_bwd(const float4* pA, const float2* pB, const float* pS, int d, const int* tile_accum,
                                    const GsFrameGeom& g, const GsRayPtrs& r, const float* image,
-                                   const float* grad_image, float* grad_inst, cudaStream_t st) {
+                                   const float* grad_image, float* grad_inst, int grad_is_final, const GsCrop& crop,
+                                   cudaStream_t st) {
   if (d == 27)
     blend_sh_bwd_kernel<9><<<g.n_tiles, 64, 0, st>>>(pA, pB, pS, tile_accum, g.wp, g.hp, g.ntx, g.fx, g.fy, r.rays_o,
-                                                     r.lefttop, r.dx, r.dy, image, grad_image, grad_inst);
+                                                     r.lefttop, r.dx, r.dy, image, grad_image, grad_inst, grad_is_final, crop);
   else
     blend_sh_bwd_kernel<16><<<g.n_tiles, 64, 0, st>>>(pA, pB, pS, tile_accum, g.wp, g.hp, g.ntx, g.fx, g.fy, r.rays_o,
-                                                      r.lefttop, r.dx, r.dy, image, grad_image, grad_inst);
+                                                      r.lefttop, r.dx, r.dy, image, grad_image, grad_inst, grad_is_final, crop);
   return cudaGetLastError();
 }

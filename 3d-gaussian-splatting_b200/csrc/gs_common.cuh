@@ -105,3 +105,29 @@ __device__ __forceinline__ void gs_mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ float gs_pixel_coord(int idx, int extent, float focal) {
   return (float)(((double)idx + 0.5 - (double)(extent / 2)) / (double)focal);
 }
+
+// ---- fused clamp + crop helpers (reference splatter.py:652-653) ---------------------------
+__device__ __forceinline__ void gs_store_final(float* __restrict__ final_img, int ix, int iy, int left, int top,
+                                               int width, int height, float r, float g, float b) {
+  const int x = ix - left, y = iy - top;
+  if (x >= 0 && x < width && y >= 0 && y < height) {
+    float* o = final_img + ((size_t)y * width + x) * 3;
+    o[0] = fminf(fmaxf(r, 0.f), 1.f);
+    o[1] = fminf(fmaxf(g, 0.f), 1.f);
+    o[2] = fminf(fmaxf(b, 0.f), 1.f);
+  }
+}
+// gradient of the final (clamped, cropped) image seen from the raw padded image: torch.clamp
+// passes the gradient where 0 <= v <= 1; pixels outside the crop receive none
+__device__ __forceinline__ void gs_load_final_grad(const float* __restrict__ grad_final, const float* raw3, int ix,
+                                                   int iy, int left, int top, int width, int height, float& gr,
+                                                   float& gg, float& gb) {
+  const int x = ix - left, y = iy - top;
+  gr = gg = gb = 0.f;
+  if (x >= 0 && x < width && y >= 0 && y < height) {
+    const float* g = grad_final + ((size_t)y * width + x) * 3;
+    gr = (raw3[0] >= 0.f && raw3[0] <= 1.f) ? g[0] : 0.f;
+    gg = (raw3[1] >= 0.f && raw3[1] <= 1.f) ? g[1] : 0.f;
+    gb = (raw3[2] >= 0.f && raw3[2] <= 1.f) ? g[2] : 0.f;
+  }
+}

@@ -15,6 +15,13 @@ struct GsFrameGeom {
   float fx, fy;
 };
 
+// Optional fused post-processing of reference splatter.py:652-653 (clamp to [0,1] + centre crop):
+// forward additionally writes final[height,width,3]; backward takes the gradient of that final
+// image (clamp mask from the raw padded image, zero outside the crop) instead of a padded one.
+struct GsCrop {
+  int left, top, width, height;
+};
+
 // world-space ray setup for per-pixel SH (reference splatter.py:305-321), DEVICE pointers to 3 floats each
 struct GsRayPtrs {
   const float *rays_o, *lefttop, *dx, *dy;
@@ -26,10 +33,11 @@ int gs_sh_stream_width(int d);     // floats per instance row of the SH stream (
 int gs_sh_grad_width(int d);       // floats per instance gradient row (6 geometry + d coefficients, padded)
 cudaError_t gs_launch_blend_sh_fwd(const float4* pA, const float2* pB, const float* pS, int d, const int* tile_accum,
                                    const GsFrameGeom& g, const GsRayPtrs& r, float* image, int* tile_neff,
-                                   cudaStream_t st);
+                                   float* final_img, const GsCrop& crop, cudaStream_t st);
 cudaError_t gs_launch_blend_sh_bwd(const float4* pA, const float2* pB, const float* pS, int d, const int* tile_accum,
                                    const GsFrameGeom& g, const GsRayPtrs& r, const float* image,
-                                   const float* grad_image, float* grad_inst, cudaStream_t st);
+                                   const float* grad_image, float* grad_inst, int grad_is_final, const GsCrop& crop,
+                                   cudaStream_t st);
 
 // ---- project.cu ------------------------------------------------------------------------
 cudaError_t gs_launch_fused_project(const float* pos, const float* rgb, const float* opa, const float* quat,
@@ -59,8 +67,10 @@ cudaError_t gs_launch_iota(uint32_t* out, int n, cudaStream_t st);
 
 // ---- blend.cu --------------------------------------------------------------------------
 cudaError_t gs_launch_blend_fwd(const float4* pA, const float2* pB, const float4* pC, const int* tile_accum,
-                                const GsFrameGeom& g, float* image, int* tile_neff, cudaStream_t st);
+                                const GsFrameGeom& g, float* image, int* tile_neff, float* final_img, const GsCrop& crop,
+                                cudaStream_t st);
 
 cudaError_t gs_launch_blend_bwd(const float4* pA, const float2* pB, const float4* pC, const int* tile_accum,
                                 const GsFrameGeom& g, const float* image, const float* grad_image,
-                                float* grad_inst /*[M,GS_GREC] rows addressed by C.w slot*/, cudaStream_t st);
+                                float* grad_inst /*[M,GS_GREC] rows addressed by C.w slot*/, int grad_is_final,
+                                const GsCrop& crop, cudaStream_t st);

@@ -136,9 +136,9 @@ static int ceil_log2(unsigned v) {
   return b;
 }
 
-extern "C" int gs_render_forward(gs_ctx* c, const float* pos, const float* rgb, const float* opa, const float* quat,
-                                 const float* scale, int n, int d, int scale_activation, const gs_camera* cam,
-                                 float* image, int64_t* culling_mask, gs_stream_t stream) {
+static int render_forward_impl(gs_ctx* c, const float* pos, const float* rgb, const float* opa, const float* quat,
+                               const float* scale, int n, int d, int scale_activation, const gs_camera* cam,
+                               float* image, float* final_img, int64_t* culling_mask, gs_stream_t stream) {
   if (!c || !cam || n < 0) return gs_set_error_msg(GS_ERR_INVALID_ARG, "gs_render_forward: bad arguments");
   if (d != 3 && gs_sh_basis_count(d) == 0)
     return gs_set_error_msg(GS_ERR_UNSUPPORTED, "gs_render_forward: colour width must be 3 (RGB), 27 (SH deg 2) or 48 (SH deg 3)");
@@ -300,16 +300,18 @@ extern "C" int gs_render_forward(gs_ctx* c, const float* pos, const float* rgb, 
                                          gs_sh_stream_width(d), c->pA.as<float4>(), c->pB.as<float2>(),
                                          c->pC.as<float>(), c->tile_accum.as<int>(), st));
   }
-  // 6. blend
+  // 6. blend (+ optional fused clamp & centre crop, splatter.py:652-653 / :267-272)
+  GsCrop crop{(g.wp - g.width) / 2, (g.hp - g.height) / 2, g.width, g.height};
   gs_mark(c, 5, st);
   if (d == 3) {
     GS_CUDA_TRY(gs_launch_blend_fwd(c->pA.as<float4>(), c->pB.as<float2>(), c->pC.as<float4>(),
-                                    c->tile_accum.as<int>(), g, image, c->tile_neff.as<int>(), st));
+                                    c->tile_accum.as<int>(), g, image, c->tile_neff.as<int>(), final_img, crop, st));
   } else {
     const float* rp = c->rays.as<float>();
     GsRayPtrs rays{rp, rp + 3, rp + 6, rp + 9};
     GS_CUDA_TRY(gs_launch_blend_sh_fwd(c->pA.as<float4>(), c->pB.as<float2>(), c->pC.as<float>(), d,
-                                       c->tile_accum.as<int>(), g, rays, image, c->tile_neff.as<int>(), st));
+                                       c->tile_accum.as<int>(), g, rays, image, c->tile_neff.as<int>(), final_img,
+                                       crop, st));
   }
   gs_mark(c, 6, st);
   c->ev_fwd_valid = c->timing && c->ev_ok;
@@ -328,10 +330,26 @@ extern "C" int gs_render_forward(gs_ctx* c, const float* pos, const float* rgb, 
   return 0;
 }
 
-extern "C" int gs_render_backward(gs_ctx* c, const float* pos, const float* rgb, const float* opa, const float* quat,
-                                  const float* scale, const float* image, const float* grad_image, float* grad_pos,
-                                  float* grad_rgb, float* grad_opa, float* grad_quat, float* grad_scale,
-                                  gs_stream_t stream) {
+extern "C" int gs_render_forward(gs_ctx* c, const float* pos, const float* rgb, const float* opa, const float* quat,
+                                 const float* scale, int n, int d, int scale_activation, const gs_camera* cam,
+                                 float* image, int64_t* culling_mask, gs_stream_t stream) {
+  return render_forward_impl(c, pos, rgb, opa, quat, scale, n, d, scale_activation, cam, image, nullptr, culling_mask,
+                             stream);
+}
+
+extern "C" int gs_render_forward_final(gs_ctx* c, const float* pos, const float* rgb, const float* opa,
+                                       const float* quat, const float* scale, int n, int d, int scale_activation,
+                                       const gs_camera* cam, float* image_raw_padded, float* image_final,
+                                       int64_t* culling_mask, gs_stream_t stream) {
+  if (!image_final) return gs_set_error_msg(GS_ERR_INVALID_ARG, "gs_render_forward_final: null image_final");
+  return render_forward_impl(c, pos, rgb, opa, quat, scale, n, d, scale_activation, cam, image_raw_padded, image_final,
+                             culling_mask, stream);
+}
+
+static int render_backward_impl(gs_ctx* c, const float* pos, const float* rgb, const float* opa, const float* quat,
+                                const float* scale, const float* image, const float* grad_image, int grad_is_final,
+                                float* grad_pos, float* grad_rgb, float* grad_opa, float* grad_quat,
+                                float* grad_scale, gs_stream_t stream) {
   if (!c) return gs_set_error_msg(GS_ERR_INVALID_ARG, "gs_render_backward: null ctx");
   if (!c->have_forward) return gs_set_error_msg(GS_ERR_NO_FORWARD, "gs_render_backward: no forward on this ctx");
   cudaStream_t st = (cudaStream_t)stream;
@@ -340,18 +358,19 @@ extern "C" int gs_render_backward(gs_ctx* c, const float* pos, const float* rgb,
   const size_t grow = d == 3 ? (size_t)GS_GREC * 4 : (size_t)gs_sh_grad_width(d) * 4;
   GS_CUDA_TRY(c->grad_inst.reserve(M * grow + 16, st));
   c->ev_bwd_valid = false;
+  GsCrop crop{(c->geom.wp - c->geom.width) / 2, (c->geom.hp - c->geom.height) / 2, c->geom.width, c->geom.height};
   gs_mark(c, 7, st);
   if (c->m > 0) {
     if (d == 3) {
       GS_CUDA_TRY(gs_launch_blend_bwd(c->pA.as<float4>(), c->pB.as<float2>(), c->pC.as<float4>(),
                                       c->tile_accum.as<int>(), c->geom, image, grad_image, c->grad_inst.as<float>(),
-                                      st));
+                                      grad_is_final, crop, st));
     } else {
       const float* rp = c->rays.as<float>();
       GsRayPtrs rays{rp, rp + 3, rp + 6, rp + 9};
       GS_CUDA_TRY(gs_launch_blend_sh_bwd(c->pA.as<float4>(), c->pB.as<float2>(), c->pC.as<float>(), d,
                                          c->tile_accum.as<int>(), c->geom, rays, image, grad_image,
-                                         c->grad_inst.as<float>(), st));
+                                         c->grad_inst.as<float>(), grad_is_final, crop, st));
     }
   }
   gs_mark(c, 8, st);
@@ -362,6 +381,22 @@ extern "C" int gs_render_backward(gs_ctx* c, const float* pos, const float* rgb,
   gs_mark(c, 9, st);
   c->ev_bwd_valid = c->timing && c->ev_ok;
   return 0;
+}
+
+extern "C" int gs_render_backward(gs_ctx* c, const float* pos, const float* rgb, const float* opa, const float* quat,
+                                  const float* scale, const float* image, const float* grad_image, float* grad_pos,
+                                  float* grad_rgb, float* grad_opa, float* grad_quat, float* grad_scale,
+                                  gs_stream_t stream) {
+  return render_backward_impl(c, pos, rgb, opa, quat, scale, image, grad_image, 0, grad_pos, grad_rgb, grad_opa,
+                              grad_quat, grad_scale, stream);
+}
+
+extern "C" int gs_render_backward_final(gs_ctx* c, const float* pos, const float* rgb, const float* opa,
+                                        const float* quat, const float* scale, const float* image_raw_padded,
+                                        const float* grad_final, float* grad_pos, float* grad_rgb, float* grad_opa,
+                                        float* grad_quat, float* grad_scale, gs_stream_t stream) {
+  return render_backward_impl(c, pos, rgb, opa, quat, scale, image_raw_padded, grad_final, 1, grad_pos, grad_rgb,
+                              grad_opa, grad_quat, grad_scale, stream);
 }
 
 extern "C" int gs_frame_stats(gs_ctx* c, gs_frame_info* out, gs_stream_t stream) {

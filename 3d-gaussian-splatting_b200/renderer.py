@@ -139,6 +139,24 @@ global_culling = _GlobalCulling.apply
 SCALE_ACTIVATIONS = {"abs": 0, "exp": 1}
 
 
+def _flat_grads(tensors):
+    """Five gradient views carved out of ONE flat buffer (order pos, rgb, opa, quat, scale; each
+    segment 16-byte aligned for the kernel's float4 stores) so that the data-parallel all-reduce
+    runs in place on a single bucket (dp.GradBucket)."""
+    sizes = [t.numel() for t in tensors]
+    starts, o = [], 0
+    for n in sizes:
+        starts.append(o)
+        o += (n + 3) // 4 * 4
+    flat = torch.empty(o, device=tensors[0].device, dtype=torch.float32)
+    outs = []
+    for t, n, b in zip(tensors, sizes, starts):
+        outs.append(flat[b:b + n].view(t.shape))
+        if n % 4:
+            flat[b + n:b + (n + 3) // 4 * 4].zero_()     # keep the (<= 3 float) pads finite
+    return outs
+
+
 class _RenderFrame(torch.autograd.Function):
     """raw parameters -> padded un-clamped image, replacing splatter.py:513-634's glue.
 
@@ -161,21 +179,37 @@ class _RenderFrame(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_image, _grad_mask):
         pos, rgb, opa, quat, scale, image = ctx.saved_tensors
-        # all five gradients are views of ONE flat buffer (order pos, rgb, opa, quat, scale) so
-        # that the data-parallel all-reduce runs in place on a single bucket (dp.GradBucket)
-        sizes = [t.numel() for t in (pos, rgb, opa, quat, scale)]
-        starts, o = [], 0
-        for n in sizes:                       # 16-byte aligned segments (float4 stores in the kernel)
-            starts.append(o)
-            o += (n + 3) // 4 * 4
-        flat = torch.empty(o, device=pos.device, dtype=torch.float32)
-        outs = []
-        for t, n, b in zip((pos, rgb, opa, quat, scale), sizes, starts):
-            outs.append(flat[b:b + n].view(t.shape))
-            if n % 4:
-                flat[b + n:b + (n + 3) // 4 * 4].zero_()     # keep the (<= 3 float) pads finite
+        outs = _flat_grads((pos, rgb, opa, quat, scale))
         ctx.rctx.backward_into(pos, rgb, opa, quat, scale, image, _f32(grad_image), *outs)
         return (None, outs[0], outs[1], outs[2], outs[3], outs[4]) + (None,) * 9
 
 
 render_frame = _RenderFrame.apply
+
+
+class _RenderFrameFinal(torch.autograd.Function):
+    """Like `render_frame`, with reference splatter.py:652-653 (clamp to [0,1] + centre crop)
+    fused into the blend kernels: returns the final HxWx3 image; backward consumes its gradient
+    directly (no clamp / pad kernels, no padded gradient image)."""
+
+    @staticmethod
+    def forward(ctx, rctx, pos, rgb, opa, quat, scale, width, height, focal_x, focal_y, rot, tran,
+                near, tile_thresh, scale_activation):
+        pos, rgb, opa, quat, scale = (_f32(t.detach()) for t in (pos, rgb, opa, quat, scale))
+        final, raw, mask = rctx.forward_final(pos, rgb, opa, quat, scale, int(width), int(height), float(focal_x),
+                                              float(focal_y), rot.detach().cpu(), tran.detach().cpu(), float(near),
+                                              float(tile_thresh), SCALE_ACTIVATIONS[scale_activation])
+        ctx.rctx = rctx
+        ctx.save_for_backward(pos, rgb, opa, quat, scale, raw)
+        ctx.mark_non_differentiable(mask)
+        return final, mask
+
+    @staticmethod
+    def backward(ctx, grad_final, _grad_mask):
+        pos, rgb, opa, quat, scale, raw = ctx.saved_tensors
+        outs = _flat_grads((pos, rgb, opa, quat, scale))
+        ctx.rctx.backward_final_into(pos, rgb, opa, quat, scale, raw, _f32(grad_final), *outs)
+        return (None, outs[0], outs[1], outs[2], outs[3], outs[4]) + (None,) * 9
+
+
+render_frame_final = _RenderFrameFinal.apply

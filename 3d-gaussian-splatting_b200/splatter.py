@@ -24,7 +24,7 @@ import torch
 import torch.nn as nn
 
 import gaussian
-from renderer import render_frame
+from renderer import render_frame, render_frame_final
 
 EPS = 1e-4
 
@@ -132,9 +132,22 @@ class Splatter(nn.Module):
         return image
 
     def forward(self, camera_id=None, extrinsics=None, intrinsics=None):
+        """reference splatter.py:643-655; clamp(0,1) + centre crop (:652-653) run inside the blend
+        kernels (`render_frame_final`)."""
+        self.set_camera(camera_id, extrinsics, intrinsics)
+        g, v = self.gaussian_3ds, self.current_view
+        image, mask = render_frame_final(self._rctx, g.pos, g.rgb, g.opa, g.quat, g.scale, v["width"], v["height"],
+                                         v["focal_x"], v["focal_y"], v["rot"], v["tran"], self.near,
+                                         self.tile_culling_prob_thresh, self.scale_activation)
+        self.culling_mask = mask
+        self.n_gaussians = g.pos.shape[0]
+        return image
+
+    def forward_unfused_post(self, camera_id=None, extrinsics=None, intrinsics=None):
+        """Same image through the padded raw render + torch clamp/crop (kept for cross-checks)."""
         self.set_camera(camera_id, extrinsics, intrinsics)
         padded = self.render_padded()
-        return self.tile_info.crop(torch.clamp(padded, 0, 1))       # splatter.py:652-653
+        return self.tile_info.crop(torch.clamp(padded, 0, 1))
 
     def frame_stats(self):
         s = self._rctx.stats()

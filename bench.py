@@ -43,6 +43,21 @@ METRIC = "render+backward FPS @1080p (2.4M Gaussians)"
 
 
 # ------------------------------------------------------------------------------------------
+def ncu_traffic(workload, kernel):
+    """dram read+write bytes per launch of `kernel` from the committed ncu --set full capture
+    (profiles/<round>_traffic.json; null when that workload was not captured)."""
+    best = None
+    pdir = os.path.join(ROOT, "profiles")
+    for name in sorted(os.listdir(pdir)) if os.path.isdir(pdir) else []:
+        if name.endswith("_traffic.json"):
+            try:
+                d = json.load(open(os.path.join(pdir, name)))
+                best = d.get(workload, {}).get(kernel, best)
+            except Exception:
+                pass
+    return best
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -148,14 +163,16 @@ def timed_loop(step_fn, steps, warmup, world, dev):
     return max_over_ranks(ms, world, dev)
 
 
-def cpu_baseline(workload, n_tiles_sample=48):
-    """The CPU oracle (pure PyTorch) on the box's host cores: full projection + binning +
-    exact sort of the frame, then blend forward + autograd backward on a tile sub-sample,
-    extrapolated to all tiles (labelled as such)."""
+def cpu_baseline(workload, n_tiles_sample=12, max_threads=32):
+    """The CPU oracle (pure PyTorch) on the box's host cores, bounded to roughly half a minute:
+    full projection + binning + exact sort of the frame (once), then blend forward + autograd
+    backward on a tile sub-sample, extrapolated to all tiles (labelled as such).  PyTorch's CPU
+    kernels stop scaling on these small per-tile tensors well before 32 threads, so the thread
+    count is capped there and reported as `cores`."""
     import gs_oracle as O
     import synthetic as S
     n, w, h, fwd_only = WORKLOADS[workload]
-    cores = os.cpu_count() or 1
+    cores = min(os.cpu_count() or 1, max_threads)
     torch.set_num_threads(cores)
     v = S.make_view(w, h, 0)
     g = S.make_gaussians(n, w, h, 0)
@@ -163,25 +180,33 @@ def cpu_baseline(workload, n_tiles_sample=48):
     T = cam.ntx * cam.nty
     tiles = torch.linspace(0, T - 1, n_tiles_sample).long()
     go = S.make_grad_output(h, w, 0)
-    t0 = time.time()
     p = {k: t.clone().requires_grad_(not fwd_only) for k, t in g.items()}
     with torch.set_grad_enabled(not fwd_only):
-        img, aux = O.render(p["pos"], p["rgb"], p["opa"], p["quat"], p["scale"], cam, tiles=tiles, return_aux=True)
-        t_front_blend = time.time() - t0
+        t0 = time.time()
+        # front end: activations, projection, culling, binning, exact (tile, depth) sort
+        nq, ns, opa_a, rgb_a = O.preactivate(p["quat"], p["scale"], p["opa"], p["rgb"])
+        rp, rc, mask = O.global_culling(p["pos"], nq, ns, cam.rot, cam.tran, cam.near, cam.half_w, cam.half_h)
+        idx = torch.nonzero(mask.bool()).squeeze(-1)
+        p_c, c_c = rp[idx], rc[idx]
+        rects = O.tile_rects(p_c[:, :2], c_c, 0.05, cam.tile_lx, cam.tile_ly, cam.ntx, cam.nty, cam.leftmost,
+                             cam.topmost)
+        gi, accum = O.bin_and_sort(p_c, c_c, rects, cam.ntx, cam.nty)
+        s_pos, s_rgb, s_opa, s_cov = p_c[gi], rgb_a[idx][gi], opa_a[idx][gi], c_c[gi]
+        t_front = time.time() - t0
+        t1 = time.time()
+        img = O.draw(s_pos, s_rgb, s_opa, s_cov, accum, cam.Hp, cam.Wp, cam.fx, cam.fy, tiles=tiles)
+        t_blend = time.time() - t1
         if not fwd_only:
-            img.backward(go)
-    t_total = time.time() - t0
-    # split: the blend part scales with the number of tiles, the front end does not
-    t1 = time.time()
-    with torch.no_grad():
-        O.render(g["pos"], g["rgb"], g["opa"], g["quat"], g["scale"], cam, tiles=tiles[:1])
-    t_front = time.time() - t1                       # ~ projection + binning + sort (+1 tile)
-    t_blend = max(t_total - t_front, 1e-6)
-    est = t_front + t_blend * (T / n_tiles_sample)
+            t2 = time.time()
+            img.backward(torch.ones_like(img) / img.numel())
+            t_bwd = time.time() - t2          # blend backward of the sampled tiles + front-end backward
+        else:
+            t_bwd = 0.0
+    est = t_front + (t_blend + t_bwd) * (T / n_tiles_sample)
     return {"value": 1.0 / est, "unit": "frames/s", "cores": cores, "kind": "port",
-            "sample": f"{workload}: full projection+binning+sort of {n} gaussians, blend fwd"
-                      f"{'' if fwd_only else '+bwd'} on {n_tiles_sample}/{T} tiles, extrapolated "
-                      f"({t_front:.1f}s front end + {t_blend:.1f}s sampled blend)"}
+            "sample": f"{workload}: full projection+binning+sort of {n} gaussians ({t_front:.1f}s), blend fwd"
+                      f"{'' if fwd_only else '+bwd'} on {n_tiles_sample}/{T} tiles ({t_blend + t_bwd:.1f}s), "
+                      f"extrapolated to all tiles; {cores} torch threads"}
 
 
 # ------------------------------------------------------------------------------------------
@@ -296,7 +321,9 @@ def run_ours(args, world, rank, local):
         "stage_ms": dict(zip(["project", "depth_sort+scan+readback", "emit_keys", "tile_sort", "pack", "blend_fwd",
                               "blend_bwd", "project_bwd"], [round(x, 4) for x in stage])),
         "roofline": {"bound": "hbm", "kernel": roof_kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                     "frac": (achieved / peak) if achieved else None, "traffic": ncu_traffic(args.workload, roof_kernel),
+                     "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full)",
+                     "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes,
                      "note": "blend is FP32/MUFU-issue bound, not HBM bound (SURVEY.md §8d): "
                              f"{pairs / 1e9:.2f} G pixel-instance pairs upper bound per launch",

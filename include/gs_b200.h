@@ -153,6 +153,19 @@ int gs_render_backward(gs_ctx* ctx, const float* pos, const float* rgb, const fl
                        const float* grad_image, float* grad_pos, float* grad_rgb, float* grad_opa,
                        float* grad_quat, float* grad_scale, gs_stream_t stream);
 
+/* Same as gs_render_forward / gs_render_backward with the post-processing of reference
+ * splatter.py:652-653 fused in: forward additionally writes image_final[height,width,3] =
+ * centre crop of clamp(image_raw_padded, 0, 1); backward takes grad_final[height,width,3], the
+ * gradient of that final image (clamp passes gradients where 0 <= raw <= 1; padding gets none). */
+int gs_render_forward_final(gs_ctx* ctx, const float* pos, const float* rgb, const float* opa,
+                            const float* quat, const float* scale, int n, int d, int scale_activation,
+                            const gs_camera* cam_host, float* image_raw_padded, float* image_final,
+                            int64_t* culling_mask, gs_stream_t stream);
+int gs_render_backward_final(gs_ctx* ctx, const float* pos, const float* rgb, const float* opa,
+                             const float* quat, const float* scale, const float* image_raw_padded,
+                             const float* grad_final, float* grad_pos, float* grad_rgb, float* grad_opa,
+                             float* grad_quat, float* grad_scale, gs_stream_t stream);
+
 /* Per-stage device timing with CUDA events recorded on the frame's stream (off by default).
  * gs_frame_stage_ms fills out[GS_N_STAGES] with the milliseconds of the last frame's stages:
  * 0 project, 1 depth sort of Gaussians + scan + M readback, 2 key emit, 3 tile-id radix sort,

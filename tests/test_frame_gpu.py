@@ -142,6 +142,24 @@ def test_fused_frame_vs_golden(gs, cuda):
         assert rel_err(getattr(sp.gaussian_3ds, name).grad, gold["grad_" + name]) < GRAD_RTOL, name
 
 
+def test_fused_clamp_crop_equals_torch_post(gs, cuda):
+    """Splatter.forward (clamp + crop inside the kernels) == padded render + torch clamp/crop,
+    image and gradients, on a scene that saturates (values > 1 get clamped) and needs padding."""
+    g, v, cam = scene(6000, 200, 120, k=0, opa_range=(0.3, 0.95))
+    g["rgb"] = g["rgb"] + 3.0                      # bright colours: accumulated colour exceeds 1
+    go = (S.make_grad_output(120, 200, 3) * (120 * 200)).to(cuda)
+    res = []
+    for fused in (True, False):
+        sp = _splatter(g, [v], cuda)
+        img = sp(0) if fused else sp.forward_unfused_post(0)
+        img.backward(go)
+        res.append((img.detach(), [p.grad.clone() for p in sp.gaussian_3ds.parameters()]))
+    assert float(res[1][0].max()) == 1.0           # the clamp is active
+    assert torch.equal(res[0][0], res[1][0])
+    for a, b in zip(res[0][1], res[1][1]):
+        assert rel_err(a, b) < 1e-6
+
+
 def test_edge_cases(gs, cuda):
     v = S.make_view(64, 48, 0)
     # empty scene
