@@ -144,7 +144,9 @@ def test_fused_frame_vs_golden(gs, cuda):
 
 def test_fused_clamp_crop_equals_torch_post(gs, cuda):
     """Splatter.forward (clamp + crop inside the kernels) == padded render + torch clamp/crop,
-    image and gradients, on a scene that saturates (values > 1 get clamped) and needs padding."""
+    image and gradients, on a near-saturated scene whose size needs padding on both axes.
+    (With sigmoid colours and a black background sum_i w_i c_i <= 1, so the clamp only ever
+    guards rounding; the crop / zero-padding of the gradient is what this exercises.)"""
     g, v, cam = scene(6000, 200, 120, k=0, opa_range=(0.3, 0.95))
     g["rgb"] = g["rgb"] + 3.0                      # bright colours: accumulated colour exceeds 1
     go = (S.make_grad_output(120, 200, 3) * (120 * 200)).to(cuda)
@@ -154,7 +156,7 @@ def test_fused_clamp_crop_equals_torch_post(gs, cuda):
         img = sp(0) if fused else sp.forward_unfused_post(0)
         img.backward(go)
         res.append((img.detach(), [p.grad.clone() for p in sp.gaussian_3ds.parameters()]))
-    assert float(res[1][0].max()) == 1.0           # the clamp is active
+    assert float(res[1][0].max()) > 0.9
     assert torch.equal(res[0][0], res[1][0])
     for a, b in zip(res[0][1], res[1][1]):
         assert rel_err(a, b) < 1e-6
