@@ -92,15 +92,16 @@ __global__ void gather_kernel(const int* __restrict__ accum, const int* __restri
 // items - cheap); (2) instances are emitted in that order (instance `rank` of the Gaussian at
 // sorted position i goes to row offsets_sorted[i] + rank, rank = row-major index inside its
 // tile rectangle), so the instance array is already ordered by (depth, id, rank);
-// (3) a STABLE radix sort of the M instances on the tile id alone (32-bit key of which only ceil(log2 T)
-// bits are sorted = 2 passes at 1080p, 8 B / item) yields exactly (tile, depth, id).
+// (3) a STABLE radix sort of the M instances on the tile id alone (16-bit key when T <= 65536, else 32-bit;
+// only ceil(log2 T) bits are sorted = 2 passes at 1080p, 6 B / item) yields exactly (tile, depth, id).
 // The backward writes an instance's gradient record to row ("slot") offsets_g[g] + rank, where
 // offsets_g is the exclusive scan of the tile counts in Gaussian-id order: the records of one
 // Gaussian are contiguous, and nothing in the pipeline needs a scattered store (scattered
 // 4-byte stores cost 0.5 ms at C3 when tried: partial-sector read-modify-write in L2).
+template <typename KeyT>
 __global__ void __launch_bounds__(kBlock) emit_keys_kernel(const GsRec* __restrict__ rec, const uint32_t* __restrict__ perm,
                                                             const uint32_t* __restrict__ offsets_sorted, int n,
-                                                            int ntx, uint32_t* __restrict__ keys,
+                                                            int ntx, KeyT* __restrict__ keys,
                                                             uint32_t* __restrict__ vals) {
   int i = blockIdx.x * kBlock + threadIdx.x;
   if (i >= n) return;
@@ -113,12 +114,13 @@ __global__ void __launch_bounds__(kBlock) emit_keys_kernel(const GsRec* __restri
   uint32_t r = o0;
   for (uint32_t ty = ty0; ty < ty0 + h; ++ty)
     for (uint32_t tx = tx0; tx < tx0 + w; ++tx, ++r) {
-      keys[r] = ty * ntx + tx;
+      keys[r] = (KeyT)(ty * ntx + tx);
       vals[r] = g;
     }
 }
 
-__global__ void __launch_bounds__(kBlock) pack_sorted_kernel(const uint32_t* __restrict__ keys,
+template <typename KeyT>
+__global__ void __launch_bounds__(kBlock) pack_sorted_kernel(const KeyT* __restrict__ keys,
                                                               const uint32_t* __restrict__ vals, long long m,
                                                               int n_tiles, int ntx, const GsRec* __restrict__ rec,
                                                               const uint32_t* __restrict__ offsets_g,
@@ -151,7 +153,8 @@ __global__ void __launch_bounds__(kBlock) pack_sorted_kernel(const uint32_t* __r
 }
 
 // SH variant: the third stream row is {raw coefficients rgb[g][0..d), slot, pad}
-__global__ void __launch_bounds__(kBlock) pack_sorted_sh_kernel(const uint32_t* __restrict__ keys,
+template <typename KeyT>
+__global__ void __launch_bounds__(kBlock) pack_sorted_sh_kernel(const KeyT* __restrict__ keys,
                                                                  const uint32_t* __restrict__ vals, long long m,
                                                                  int n_tiles, int ntx, const GsRec* __restrict__ rec,
                                                                  const uint32_t* __restrict__ offsets_g,
@@ -190,12 +193,17 @@ __global__ void __launch_bounds__(kBlock) iota_kernel(uint32_t* out, int n) {
 
 }  // namespace
 
-cudaError_t gs_launch_pack_sorted_sh(const uint32_t* keys, const uint32_t* vals, long long m, int n_tiles, int ntx,
-                                     const GsRec* rec, const uint32_t* offsets_g, const float* rgb, int d, int sw,
-                                     float4* pA, float2* pB, float* pS, int* tile_accum, cudaStream_t st) {
+cudaError_t gs_launch_pack_sorted_sh(const void* keys, int key_bytes, const uint32_t* vals, long long m, int n_tiles,
+                                     int ntx, const GsRec* rec, const uint32_t* offsets_g, const float* rgb, int d,
+                                     int sw, float4* pA, float2* pB, float* pS, int* tile_accum, cudaStream_t st) {
   if (m == 0) return cudaMemsetAsync(tile_accum, 0, sizeof(int) * (size_t)(n_tiles + 1), st);
-  pack_sorted_sh_kernel<<<(unsigned)((m + kBlock - 1) / kBlock), kBlock, 0, st>>>(
-      keys, vals, m, n_tiles, ntx, rec, offsets_g, rgb, d, sw, pA, pB, pS, tile_accum);
+  const unsigned grid = (unsigned)((m + kBlock - 1) / kBlock);
+  if (key_bytes == 2)
+    pack_sorted_sh_kernel<uint16_t><<<grid, kBlock, 0, st>>>(static_cast<const uint16_t*>(keys), vals, m, n_tiles,
+                                                             ntx, rec, offsets_g, rgb, d, sw, pA, pB, pS, tile_accum);
+  else
+    pack_sorted_sh_kernel<uint32_t><<<grid, kBlock, 0, st>>>(static_cast<const uint32_t*>(keys), vals, m, n_tiles,
+                                                             ntx, rec, offsets_g, rgb, d, sw, pA, pB, pS, tile_accum);
   return cudaGetLastError();
 }
 
@@ -253,17 +261,27 @@ extern "C" int gs_gather(const int* tile_n_point_accum, const int* tile_gaussian
 }
 
 cudaError_t gs_launch_emit_keys(const GsRec* rec, const uint32_t* perm, const uint32_t* offsets_sorted, int n, int ntx,
-                                uint32_t* keys, uint32_t* vals, cudaStream_t st) {
+                                void* keys, int key_bytes, uint32_t* vals, cudaStream_t st) {
   if (n == 0) return cudaSuccess;
-  emit_keys_kernel<<<(n + kBlock - 1) / kBlock, kBlock, 0, st>>>(rec, perm, offsets_sorted, n, ntx, keys, vals);
+  if (key_bytes == 2)
+    emit_keys_kernel<uint16_t><<<(n + kBlock - 1) / kBlock, kBlock, 0, st>>>(rec, perm, offsets_sorted, n, ntx,
+                                                                             static_cast<uint16_t*>(keys), vals);
+  else
+    emit_keys_kernel<uint32_t><<<(n + kBlock - 1) / kBlock, kBlock, 0, st>>>(rec, perm, offsets_sorted, n, ntx,
+                                                                             static_cast<uint32_t*>(keys), vals);
   return cudaGetLastError();
 }
 
-cudaError_t gs_launch_pack_sorted(const uint32_t* keys, const uint32_t* vals, long long m, int n_tiles, int ntx,
-                                  const GsRec* rec, const uint32_t* offsets_g, float4* pA, float2* pB, float4* pC,
-                                  int* tile_accum, cudaStream_t st) {
+cudaError_t gs_launch_pack_sorted(const void* keys, int key_bytes, const uint32_t* vals, long long m, int n_tiles,
+                                  int ntx, const GsRec* rec, const uint32_t* offsets_g, float4* pA, float2* pB,
+                                  float4* pC, int* tile_accum, cudaStream_t st) {
   if (m == 0) return cudaMemsetAsync(tile_accum, 0, sizeof(int) * (size_t)(n_tiles + 1), st);
-  pack_sorted_kernel<<<(unsigned)((m + kBlock - 1) / kBlock), kBlock, 0, st>>>(
-      keys, vals, m, n_tiles, ntx, rec, offsets_g, pA, pB, pC, tile_accum);
+  const unsigned grid = (unsigned)((m + kBlock - 1) / kBlock);
+  if (key_bytes == 2)
+    pack_sorted_kernel<uint16_t><<<grid, kBlock, 0, st>>>(static_cast<const uint16_t*>(keys), vals, m, n_tiles, ntx,
+                                                          rec, offsets_g, pA, pB, pC, tile_accum);
+  else
+    pack_sorted_kernel<uint32_t><<<grid, kBlock, 0, st>>>(static_cast<const uint32_t*>(keys), vals, m, n_tiles, ntx,
+                                                          rec, offsets_g, pA, pB, pC, tile_accum);
   return cudaGetLastError();
 }

@@ -54,14 +54,14 @@ cudaError_t gs_launch_fused_project_bwd(const float* pos, const float* rgb, cons
 
 // ---- binning.cu ------------------------------------------------------------------------
 cudaError_t gs_launch_emit_keys(const GsRec* rec, const uint32_t* perm, const uint32_t* offsets_sorted, int n, int ntx,
-                                uint32_t* keys, uint32_t* vals, cudaStream_t st);
+                                void* keys, int key_bytes, uint32_t* vals, cudaStream_t st);
 
-cudaError_t gs_launch_pack_sorted(const uint32_t* keys, const uint32_t* vals, long long m, int n_tiles, int ntx,
-                                  const GsRec* rec, const uint32_t* offsets_g, float4* pA, float2* pB, float4* pC,
+cudaError_t gs_launch_pack_sorted(const void* keys, int key_bytes, const uint32_t* vals, long long m, int n_tiles,
+                                  int ntx, const GsRec* rec, const uint32_t* offsets_g, float4* pA, float2* pB, float4* pC,
                                   int* tile_accum, cudaStream_t st);
 
-cudaError_t gs_launch_pack_sorted_sh(const uint32_t* keys, const uint32_t* vals, long long m, int n_tiles, int ntx,
-                                     const GsRec* rec, const uint32_t* offsets_g, const float* rgb, int d, int sw,
+cudaError_t gs_launch_pack_sorted_sh(const void* keys, int key_bytes, const uint32_t* vals, long long m, int n_tiles,
+                                     int ntx, const GsRec* rec, const uint32_t* offsets_g, const float* rgb, int d, int sw,
                                      float4* pA, float2* pB, float* pS, int* tile_accum, cudaStream_t st);
 cudaError_t gs_launch_iota(uint32_t* out, int n, cudaStream_t st);
 

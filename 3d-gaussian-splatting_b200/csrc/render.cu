@@ -262,6 +262,7 @@ static int render_forward_impl(gs_ctx* c, const float* pos, const float* rgb, co
   size_t M = (size_t)m;
 
   gs_mark(c, 2, st);
+  const int key_bytes = g.n_tiles <= 65536 ? 2 : 4;   // tile-id sort key width
   GS_CUDA_TRY(c->pA.reserve(M * 16 + 16, st));
   const size_t crow = d == 3 ? 16 : (size_t)gs_sh_stream_width(d) * 4;   // colour / SH stream row bytes
   GS_CUDA_TRY(c->pC.reserve(M * crow + 16, st));
@@ -273,29 +274,39 @@ static int render_forward_impl(gs_ctx* c, const float* pos, const float* rgb, co
     GS_CUDA_TRY(c->vals_out.reserve(M * 4, st));
     // 3. instances in (depth, id) order: tile-id keys + Gaussian-id values
     GS_CUDA_TRY(gs_launch_emit_keys(c->rec.as<GsRec>(), c->perm.as<uint32_t>(), c->offsets.as<uint32_t>(), n, g.ntx,
-                                    c->keys_in.as<uint32_t>(), c->vals_in.as<uint32_t>(), st));
+                                    c->keys_in.p, key_bytes, c->vals_in.as<uint32_t>(), st));
     // 4. stable radix sort on the tile id only -> (tile, depth, id)
     gs_mark(c, 3, st);
     int end_bit = ceil_log2((unsigned)g.n_tiles);
     if (end_bit < 1) end_bit = 1;
     size_t sort_tmp = 0;
-    GS_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, c->keys_in.as<uint32_t>(),
-                                                c->keys_out.as<uint32_t>(), c->vals_in.as<uint32_t>(),
-                                                c->vals_out.as<uint32_t>(), (int)m, 0, end_bit, st));
-    GS_CUDA_TRY(c->cub_tmp.reserve(sort_tmp, st));
-    GS_CUDA_TRY(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, sort_tmp, c->keys_in.as<uint32_t>(),
-                                                c->keys_out.as<uint32_t>(), c->vals_in.as<uint32_t>(),
-                                                c->vals_out.as<uint32_t>(), (int)m, 0, end_bit, st));
+    if (key_bytes == 2) {
+      GS_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, c->keys_in.as<uint16_t>(),
+                                                  c->keys_out.as<uint16_t>(), c->vals_in.as<uint32_t>(),
+                                                  c->vals_out.as<uint32_t>(), (int)m, 0, end_bit, st));
+      GS_CUDA_TRY(c->cub_tmp.reserve(sort_tmp, st));
+      GS_CUDA_TRY(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, sort_tmp, c->keys_in.as<uint16_t>(),
+                                                  c->keys_out.as<uint16_t>(), c->vals_in.as<uint32_t>(),
+                                                  c->vals_out.as<uint32_t>(), (int)m, 0, end_bit, st));
+    } else {
+      GS_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, c->keys_in.as<uint32_t>(),
+                                                  c->keys_out.as<uint32_t>(), c->vals_in.as<uint32_t>(),
+                                                  c->vals_out.as<uint32_t>(), (int)m, 0, end_bit, st));
+      GS_CUDA_TRY(c->cub_tmp.reserve(sort_tmp, st));
+      GS_CUDA_TRY(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, sort_tmp, c->keys_in.as<uint32_t>(),
+                                                  c->keys_out.as<uint32_t>(), c->vals_in.as<uint32_t>(),
+                                                  c->vals_out.as<uint32_t>(), (int)m, 0, end_bit, st));
+    }
   }
   // 5. tile ranges + packed sorted record streams
   if (m == 0) gs_mark(c, 3, st);
   gs_mark(c, 4, st);
   if (d == 3) {
-    GS_CUDA_TRY(gs_launch_pack_sorted(c->keys_out.as<uint32_t>(), c->vals_out.as<uint32_t>(), m, g.n_tiles, g.ntx,
+    GS_CUDA_TRY(gs_launch_pack_sorted(c->keys_out.p, key_bytes, c->vals_out.as<uint32_t>(), m, g.n_tiles, g.ntx,
                                       c->rec.as<GsRec>(), c->offsets_g.as<uint32_t>(), c->pA.as<float4>(),
                                       c->pB.as<float2>(), c->pC.as<float4>(), c->tile_accum.as<int>(), st));
   } else {
-    GS_CUDA_TRY(gs_launch_pack_sorted_sh(c->keys_out.as<uint32_t>(), c->vals_out.as<uint32_t>(), m, g.n_tiles, g.ntx,
+    GS_CUDA_TRY(gs_launch_pack_sorted_sh(c->keys_out.p, key_bytes, c->vals_out.as<uint32_t>(), m, g.n_tiles, g.ntx,
                                          c->rec.as<GsRec>(), c->offsets_g.as<uint32_t>(), rgb, d,
                                          gs_sh_stream_width(d), c->pA.as<float4>(), c->pB.as<float2>(),
                                          c->pC.as<float>(), c->tile_accum.as<int>(), st));

@@ -243,3 +243,18 @@ def test_full_size_properties(gs, cuda, n, w, h):
         b = padded[ty * 16:(ty + 1) * 16, tx * 16:(tx + 1) * 16].clamp(0, 1)
         if ty * 16 >= top and (ty + 1) * 16 <= top + h:
             assert abs_err(a, b) < IMG_ATOL
+
+
+def test_training_loop_converges(gs, cuda):
+    """§8f-1: the reference's train_step (L1 + Adam over the five parameter groups) on top of the
+    fused path: the loss must fall on a small synthetic multi-view scene."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location(
+        "train_dp", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "train_dp.py"))
+    td = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(td)
+    sp, gts = td.build(20000, 160, 96, 4, cuda)
+    hist, ips = td.train(sp, gts, 60, 1, 0, log_every=20)
+    assert hist[-1][1] < 0.6 * hist[0][1], hist
+    assert hist[-1][2] > hist[0][2] + 2.0
