@@ -12,6 +12,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -262,7 +263,9 @@ static int render_forward_impl(gs_ctx* c, const float* pos, const float* rgb, co
   size_t M = (size_t)m;
 
   gs_mark(c, 2, st);
-  const int key_bytes = g.n_tiles <= 65536 ? 2 : 4;   // tile-id sort key width
+  // tile-id sort key width (GS_TILE_KEY_BYTES=4 forces the wide path, for tests)
+  static const int forced_key = getenv("GS_TILE_KEY_BYTES") ? atoi(getenv("GS_TILE_KEY_BYTES")) : 0;
+  const int key_bytes = (g.n_tiles <= 65536 && forced_key != 4) ? 2 : 4;
   GS_CUDA_TRY(c->pA.reserve(M * 16 + 16, st));
   const size_t crow = d == 3 ? 16 : (size_t)gs_sh_stream_width(d) * 4;   // colour / SH stream row bytes
   GS_CUDA_TRY(c->pC.reserve(M * crow + 16, st));

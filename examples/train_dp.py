@@ -5,7 +5,7 @@ render one training camera, L1 loss, backward, Adam over the five parameter grou
 reference's learning-rate factors train.py:21-25,56-64) with the one change multi-GPU needs: each
 rank renders a different view and the gradients are all-reduced (one flat bucket) before the step.
 
-  python examples/train_dp.py --n 200000 --res 640x360 --iters 300
+  python examples/train_dp.py --gaussians 200000 --res 640x360 --iters 300
   python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 examples/train_dp.py ...
 
 Ground truth = renders of a "teacher" Gaussian set; the student starts from perturbed positions,
@@ -77,7 +77,7 @@ def train(sp, gts, iters, world, rank, log_every=50, lr=0.003):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=200_000)
+    ap.add_argument("--gaussians", type=int, default=200_000)
     ap.add_argument("--res", default="640x360")
     ap.add_argument("--iters", type=int, default=300)
     ap.add_argument("--views", type=int, default=8)
@@ -89,7 +89,7 @@ def main():
     if world > 1:
         torch.distributed.init_process_group("nccl", device_id=dev)
     torch.manual_seed(2023)                                           # identical torch RNG on all ranks
-    sp, gts = build(args.n, w, h, args.views, dev)
+    sp, gts = build(args.gaussians, w, h, args.views, dev)
     hist, ips = train(sp, gts, args.iters, world, rank)
     if rank == 0:
         print(f"done: {ips:.1f} it/s ({ips * world:.1f} views/s on {world} GPU), L1 {hist[0][1]:.5f} -> {hist[-1][1]:.5f}, "

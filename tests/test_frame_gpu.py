@@ -258,3 +258,29 @@ def test_training_loop_converges(gs, cuda):
     hist, ips = td.train(sp, gts, 60, 1, 0, log_every=20)
     assert hist[-1][1] < 0.6 * hist[0][1], hist
     assert hist[-1][2] > hist[0][2] + 2.0
+
+
+def test_wide_tile_keys_path_matches(gs, cuda):
+    """Images with more than 65536 tiles sort 32-bit tile keys; that path (forced through
+    GS_TILE_KEY_BYTES=4 in a fresh process) must give bit-identical results."""
+    import os
+    import subprocess
+    import sys
+    code = r"""
+import sys, torch, hashlib
+sys.path[:0] = [r'%s', r'%s', r'%s']
+import splatter, synthetic as S
+v = S.make_view(200, 120, 1); g = S.make_gaussians(5000, 200, 120, 4)
+sp = splatter.Splatter(g, [dict(width=v.width, height=v.height, focal_x=v.fx, focal_y=v.fy, rot=v.rot, tran=v.tran)])
+img = sp(0); img.backward(S.make_grad_output(120, 200, 0).cuda() * 24000)
+h = hashlib.sha1(img.detach().cpu().numpy().tobytes())
+for p in sp.gaussian_3ds.parameters(): h.update(p.grad.cpu().numpy().tobytes())
+print(h.hexdigest())
+""" % tuple(p for p in sys.path[:3])
+    outs = []
+    for kb in ("2", "4"):
+        env = dict(os.environ, GS_TILE_KEY_BYTES=kb)
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(r.stdout.strip().splitlines()[-1])
+    assert outs[0] == outs[1] and len(outs[0]) == 40
