@@ -225,6 +225,15 @@ void global_culling_backward(torch::Tensor pos, torch::Tensor quat, torch::Tenso
 struct RenderContext {
   gs_ctx* ctx = nullptr;
   int device = -1;
+  // The context holds the intermediate state of ONE forward.  Every forward gets an id; a
+  // backward that names another id is refused instead of silently using the wrong frame.
+  int64_t frame = 0;
+  int64_t frame_id() const { return frame; }
+  void check_frame(int64_t expected, const char* fn) const {
+    TORCH_CHECK(expected < 0 || expected == frame, fn, ": this RenderContext has rendered another frame (id ", frame,
+                ") since the forward being differentiated (id ", expected,
+                "); run backward before the next forward, or use one RenderContext / Splatter per in-flight frame");
+  }
   RenderContext() {
     check_rc(gs_ctx_create(&ctx), "gs_ctx_create");
     cudaGetDevice(&device);
@@ -269,6 +278,7 @@ struct RenderContext {
     check_rc(gs_render_forward(ctx, fp(pos), fp(rgb), fp(opa), fp(quat), fp(scale), (int)n, (int)rgb.size(1),
                                scale_activation, &cam, fpm(image), mask.data_ptr<int64_t>(), cur_stream()),
              "gs_render_forward");
+    ++frame;
     return {image, mask};
   }
 
@@ -315,12 +325,15 @@ struct RenderContext {
                                      scale_activation, &cam, fpm(raw), fpm(fin), mask.data_ptr<int64_t>(),
                                      cur_stream()),
              "gs_render_forward_final");
+    ++frame;
     return {fin, raw, mask};
   }
 
   void backward_final_into(torch::Tensor pos, torch::Tensor rgb, torch::Tensor opa, torch::Tensor quat,
                            torch::Tensor scale, torch::Tensor raw, torch::Tensor grad_final, torch::Tensor g_pos,
-                           torch::Tensor g_rgb, torch::Tensor g_opa, torch::Tensor g_quat, torch::Tensor g_scale) {
+                           torch::Tensor g_rgb, torch::Tensor g_opa, torch::Tensor g_quat, torch::Tensor g_scale,
+                           int64_t expected_frame) {
+    check_frame(expected_frame, "RenderContext.backward_final_into");
     GS_CHECK_F32(pos); GS_CHECK_F32(rgb); GS_CHECK_F32(opa); GS_CHECK_F32(quat); GS_CHECK_F32(scale);
     GS_CHECK_F32(raw); GS_CHECK_F32(g_pos); GS_CHECK_F32(g_rgb); GS_CHECK_F32(g_opa); GS_CHECK_F32(g_quat);
     GS_CHECK_F32(g_scale);
@@ -339,7 +352,8 @@ struct RenderContext {
 
   void backward_into(torch::Tensor pos, torch::Tensor rgb, torch::Tensor opa, torch::Tensor quat, torch::Tensor scale,
                      torch::Tensor image, torch::Tensor grad_image, torch::Tensor g_pos, torch::Tensor g_rgb,
-                     torch::Tensor g_opa, torch::Tensor g_quat, torch::Tensor g_scale) {
+                     torch::Tensor g_opa, torch::Tensor g_quat, torch::Tensor g_scale, int64_t expected_frame) {
+    check_frame(expected_frame, "RenderContext.backward_into");
     GS_CHECK_F32(pos); GS_CHECK_F32(rgb); GS_CHECK_F32(opa); GS_CHECK_F32(quat); GS_CHECK_F32(scale);
     GS_CHECK_F32(image); GS_CHECK_F32(g_pos); GS_CHECK_F32(g_rgb); GS_CHECK_F32(g_opa); GS_CHECK_F32(g_quat);
     GS_CHECK_F32(g_scale);
@@ -421,9 +435,15 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def(py::init<>())
       .def("forward", &RenderContext::forward)
       .def("backward", &RenderContext::backward)
-      .def("backward_into", &RenderContext::backward_into)
+      .def("backward_into", &RenderContext::backward_into, py::arg("pos"), py::arg("rgb"), py::arg("opa"),
+           py::arg("quat"), py::arg("scale"), py::arg("image"), py::arg("grad_image"), py::arg("g_pos"),
+           py::arg("g_rgb"), py::arg("g_opa"), py::arg("g_quat"), py::arg("g_scale"), py::arg("expected_frame") = -1)
       .def("forward_final", &RenderContext::forward_final)
-      .def("backward_final_into", &RenderContext::backward_final_into)
+      .def("backward_final_into", &RenderContext::backward_final_into, py::arg("pos"), py::arg("rgb"),
+           py::arg("opa"), py::arg("quat"), py::arg("scale"), py::arg("raw"), py::arg("grad_final"),
+           py::arg("g_pos"), py::arg("g_rgb"), py::arg("g_opa"), py::arg("g_quat"), py::arg("g_scale"),
+           py::arg("expected_frame") = -1)
+      .def("frame_id", &RenderContext::frame_id)
       .def("stats", &RenderContext::stats)
       .def("set_timing", &RenderContext::set_timing)
       .def("stage_ms", &RenderContext::stage_ms)

@@ -172,6 +172,7 @@ class _RenderFrame(torch.autograd.Function):
                                    float(focal_y), rot.detach().cpu(), tran.detach().cpu(), float(near),
                                    float(tile_thresh), SCALE_ACTIVATIONS[scale_activation])
         ctx.rctx = rctx
+        ctx.frame = rctx.frame_id()
         ctx.save_for_backward(pos, rgb, opa, quat, scale, image)
         ctx.mark_non_differentiable(mask)
         return image, mask
@@ -180,7 +181,7 @@ class _RenderFrame(torch.autograd.Function):
     def backward(ctx, grad_image, _grad_mask):
         pos, rgb, opa, quat, scale, image = ctx.saved_tensors
         outs = _flat_grads((pos, rgb, opa, quat, scale))
-        ctx.rctx.backward_into(pos, rgb, opa, quat, scale, image, _f32(grad_image), *outs)
+        ctx.rctx.backward_into(pos, rgb, opa, quat, scale, image, _f32(grad_image), *outs, ctx.frame)
         return (None, outs[0], outs[1], outs[2], outs[3], outs[4]) + (None,) * 9
 
 
@@ -200,6 +201,7 @@ class _RenderFrameFinal(torch.autograd.Function):
                                               float(focal_y), rot.detach().cpu(), tran.detach().cpu(), float(near),
                                               float(tile_thresh), SCALE_ACTIVATIONS[scale_activation])
         ctx.rctx = rctx
+        ctx.frame = rctx.frame_id()
         ctx.save_for_backward(pos, rgb, opa, quat, scale, raw)
         ctx.mark_non_differentiable(mask)
         return final, mask
@@ -208,7 +210,7 @@ class _RenderFrameFinal(torch.autograd.Function):
     def backward(ctx, grad_final, _grad_mask):
         pos, rgb, opa, quat, scale, raw = ctx.saved_tensors
         outs = _flat_grads((pos, rgb, opa, quat, scale))
-        ctx.rctx.backward_final_into(pos, rgb, opa, quat, scale, raw, _f32(grad_final), *outs)
+        ctx.rctx.backward_final_into(pos, rgb, opa, quat, scale, raw, _f32(grad_final), *outs, ctx.frame)
         return (None, outs[0], outs[1], outs[2], outs[3], outs[4]) + (None,) * 9
 
 

@@ -215,10 +215,10 @@ def run_ours(args, world, rank, local):
     import synthetic as S
     dev = torch.device("cuda", local)
     n, w, h, fwd_only = WORKLOADS[args.workload]
-    g = S.make_gaussians(n, w, h, 0)
+    g = S.make_gaussians(n, w, h, 0, sh_dim=args.colour)
     views = [S.make_view(w, h, k) for k in range(8)]
     vd = [dict(width=v.width, height=v.height, focal_x=v.fx, focal_y=v.fy, rot=v.rot, tran=v.tran) for v in views]
-    sp = splatter.Splatter(g, vd, device=dev)
+    sp = splatter.Splatter(g, vd, device=dev, use_sh_coeff=args.colour != 3)
     params = list(sp.gaussian_3ds.parameters())
     import dp
     bucket = dp.GradBucket(params)          # one NCCL all-reduce over one flat bucket (no-op at N=1)
@@ -289,7 +289,7 @@ def run_ours(args, world, rank, local):
     M, Meff = int(st["n_instances"]), int(st["n_instances_eff"])
     T = int(st["n_tiles"])
     P = int(st["width_padded"]) * int(st["height_padded"])
-    D = 3
+    D = args.colour
     peak, peak_src = measured_peak_gbs()
     bf = 4 * (7 + D) * Meff + 12 * P + 4 * (T + 1)
     bb = 8 * (7 + D) * Meff + 24 * P + 4 * (T + 1)
@@ -303,7 +303,7 @@ def run_ours(args, world, rank, local):
         "value": world * 1000.0 / ms, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {n} gaussians, {w}x{h}, RGB colour (D=3), "
+        "config": {"workload": f"{args.workload}: {n} gaussians, {w}x{h}, " + ("RGB colour (D=3), " if D == 3 else f"per-pixel SH colour (D={D}), ") +
                                f"{'forward only' if fwd_only else 'forward+backward'}, one view per GPU "
                                f"(view k = rank mod 8), seed 0 (SURVEY.md §8d generator)",
                    "tile_instances_M": M, "tile_instances_consumed_M_eff": Meff, "max_tile_count": st["max_tile_count"],
@@ -321,7 +321,7 @@ def run_ours(args, world, rank, local):
         "stage_ms": dict(zip(["project", "depth_sort+scan+readback", "emit_keys", "tile_sort", "pack", "blend_fwd",
                               "blend_bwd", "project_bwd"], [round(x, 4) for x in stage])),
         "roofline": {"bound": "hbm", "kernel": roof_kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": (achieved / peak) if achieved else None, "traffic": ncu_traffic(args.workload, roof_kernel),
+                     "frac": (achieved / peak) if achieved else None, "traffic": ncu_traffic(args.workload, roof_kernel) if D == 3 else None,
                      "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full)",
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes,
@@ -407,6 +407,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--colour", type=int, default=3, choices=[3, 27, 48],
+                    help="3 = RGB (default; the reference's published 2.4M point), 27 = per-pixel SH degree 2 "
+                         "(the reference's use_sh_coeff), 48 = SH degree 3 extension")
     args = ap.parse_args()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")

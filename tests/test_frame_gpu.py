@@ -284,3 +284,48 @@ print(h.hexdigest())
         assert r.returncode == 0, r.stderr[-2000:]
         outs.append(r.stdout.strip().splitlines()[-1])
     assert outs[0] == outs[1] and len(outs[0]) == 40
+
+
+def test_exp_scale_activation_and_extreme_gaussians(gs, cuda):
+    """scale_activation="exp" (trunc_exp, renderer.py:91-100: clamped-gradient backward) and shapes
+    that stress binning: one Gaussian covering every tile, needle-thin ones, negative raw scales."""
+    n, w, h = 1500, 128, 96
+    g, v, cam = scene(n, w, h, k=0, opa_range=(0.05, 0.8))
+    g["scale"] = torch.log(g["scale"])                       # raw = log(sigma) for the exp activation
+    g["scale"][0] = torch.log(torch.tensor([2.0, 2.0, 2.0]))  # huge: bbox covers the whole image
+    g["pos"][0] = torch.tensor([0.0, 0.0, 0.0])
+    g["scale"][1] = torch.tensor([-9.0, 1.2, -9.0])          # needle; 1.2 > 1 hits the clamp in trunc_exp's backward
+    go = S.make_grad_output(h, w, 0) * (h * w)
+    oimg, ograds, aux = _oracle_frame(g, cam, go, scale_activation="exp")
+    sp = _splatter(g, [v], cuda, scale_activation="exp")
+    img = sp(0)
+    assert abs_err(img, oimg) < IMG_ATOL
+    img.backward(go.to(cuda))
+    for name in ("pos", "rgb", "opa", "quat", "scale"):
+        assert rel_err(getattr(sp.gaussian_3ds, name).grad, ograds[name]) < GRAD_RTOL, name
+    counts = aux["accum"][1:] - aux["accum"][:-1]
+    assert int(counts.min()) >= 1                              # the huge Gaussian is in every tile
+    # abs activation with negative raw scales: |s| + 1e-4, gradient sign follows the raw value
+    g2, v2, cam2 = scene(800, 96, 64, k=0)
+    g2["scale"] = -g2["scale"]
+    oimg2, ograds2, _ = _oracle_frame(g2, cam2, S.make_grad_output(64, 96, 0) * (64 * 96))
+    sp2 = _splatter(g2, [v2], cuda)
+    img2 = sp2(0)
+    assert abs_err(img2, oimg2) < IMG_ATOL
+    img2.backward((S.make_grad_output(64, 96, 0) * (64 * 96)).to(cuda))
+    assert rel_err(sp2.gaussian_3ds.scale.grad, ograds2["scale"]) < GRAD_RTOL
+
+
+def test_stale_forward_is_refused(gs, cuda):
+    """One RenderContext holds one frame: differentiating an older frame after another forward
+    must raise instead of silently using the wrong intermediate state."""
+    g, v, cam = scene(500, 64, 48)
+    sp = _splatter(g, [v, S.make_view(64, 48, 1)], cuda)
+    img0 = sp(0)
+    with torch.no_grad():
+        sp(1)                                   # e.g. a test render between forward and backward
+    with pytest.raises(RuntimeError, match="another frame"):
+        img0.sum().backward()
+    img1 = sp(1)                                # normal use keeps working
+    img1.sum().backward()
+    assert sp.gaussian_3ds.pos.grad is not None
