@@ -148,7 +148,7 @@ def tile_rects(pos2d, cov, thresh, tile_length_x, tile_length_y, n_tiles_x, n_ti
     return tx0, tx1, ty0, ty1
 
 
-def bin_and_sort(pos_img, cov, rects, n_tiles_x, n_tiles_y):
+def bin_and_sort(pos_img, cov, rects, n_tiles_x, n_tiles_y, depth_key=None):
     """Exact (tile, depth, index) ordering of all tile-instances.
 
     The reference appends by atomics (gaussian.cu:244-247) and sorts an fp32 composite
@@ -168,7 +168,11 @@ def bin_and_sort(pos_img, cov, rects, n_tiles_x, n_tiles_y):
     rank = torch.arange(M) - start[g]
     wg = w[g]
     tile = (ty0[g] + rank // wg) * n_tiles_x + (tx0[g] + rank % wg)
-    depth = pos_img[:, 2].detach().to(torch.float32)[g]
+    # The order is defined on float32 depth keys.  Two Gaussians whose depths differ by an ulp can
+    # swap between an fp64 and an fp32 evaluation of |p_c|; tests therefore may pass the device's
+    # own fp32 depths (`depth_key`, one per row of pos_img) so that both sides sort identical keys.
+    dk = pos_img[:, 2].detach().to(torch.float32) if depth_key is None else depth_key.to(torch.float32)
+    depth = dk[g]
     # exact lexicographic (tile, depth, index): stable sorts, least-significant first
     order = torch.argsort(g, stable=True)
     order = order[torch.argsort(depth[order], stable=True)]
@@ -308,7 +312,7 @@ class Camera:
 
 
 def render(pos, rgb, opa, quat, scale, cam: Camera, thresh=0.05, scale_activation="abs",
-           use_sh_coeff=False, tiles=None, return_aux=False):
+           use_sh_coeff=False, tiles=None, return_aux=False, depth_key=None):
     """Splatter.forward (splatter.py:643-655) on raw parameters; returns the
     clamped + cropped image (differentiable wrt the five parameter tensors)."""
     dt = pos.dtype
@@ -320,7 +324,8 @@ def render(pos, rgb, opa, quat, scale, cam: Camera, thresh=0.05, scale_activatio
     p_c, c_c, rgb_c, opa_c = rp[idx], rc[idx], rgb_a[idx], opa_a[idx]          # a3 :536-542
     rects = tile_rects(p_c[:, :2], c_c, thresh, cam.tile_lx, cam.tile_ly, cam.ntx, cam.nty,
                        cam.leftmost, cam.topmost)
-    gi, accum = bin_and_sort(p_c, c_c, rects, cam.ntx, cam.nty)
+    gi, accum = bin_and_sort(p_c, c_c, rects, cam.ntx, cam.nty,
+                             None if depth_key is None else depth_key[idx])
     rays = ray_info(rot, tran, cam.Hp, cam.Wp, cam.fx, cam.fy) if use_sh_coeff else (None,) * 4
     img = draw(p_c[gi], rgb_c[gi], opa_c[gi], c_c[gi], accum, cam.Hp, cam.Wp, cam.fx, cam.fy,
                use_sh_coeff, *rays, tiles=tiles)

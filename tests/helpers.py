@@ -49,3 +49,15 @@ def load_golden(name):
         return None
     z = np.load(path)
     return {k: torch.from_numpy(z[k]) for k in z.files}
+
+
+def device_depth_keys(g, cam, dev, scale_activation="abs"):
+    """float32 depth |p_c| of every Gaussian as the CUDA path computes it (legacy
+    `global_culling`, same device function as the fused projection); culled rows are 0.  Used as
+    the oracle's sort key so that ulp-level depth ties cannot make the two sides order
+    differently (the order is only defined up to such ties - SURVEY.md hazard 4)."""
+    import renderer
+    nq, ns, _, _ = O.preactivate(g["quat"], g["scale"], g["opa"], g["rgb"], scale_activation)
+    rp, _, _ = renderer.global_culling(g["pos"].to(dev), nq.to(dev).contiguous(), ns.to(dev).contiguous(),
+                                       cam.rot.to(dev), cam.tran.to(dev), cam.near, cam.half_w, cam.half_h)
+    return rp[:, 2].detach().cpu()

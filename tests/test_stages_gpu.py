@@ -79,6 +79,8 @@ def test_global_culling_vs_reference_build(gs, ref, cuda):
         outs.append((op, oc, om, pos.grad, q.grad, s.grad))
     a, b = outs
     assert torch.equal(a[2], b[2])
+    # depth (the sort key) is bit-identical to the reference kernel's: same ordering keys
+    assert torch.equal(a[0][:, 2], b[0][:, 2])
     assert rel_err(a[0], b[0]) < 1e-5 and rel_err(a[1], b[1]) < 2e-5
     for i in (3, 4, 5):
         assert rel_err(a[i], b[i]) < 1e-4
