@@ -152,7 +152,8 @@ __global__ void __launch_bounds__(kBlock) pack_sorted_kernel(const KeyT* __restr
   pC[i] = make_float4(b.z, b.w, c.x, __uint_as_float(slot));
 }
 
-// SH variant: the third stream row is {raw coefficients rgb[g][0..d), slot, pad}
+// SH variant: the third stream row is {raw coefficients rgb[g][0..d), slot, pad}.  8 lanes per
+// instance copy the row so that both the gather and the store move 32-byte pieces.
 template <typename KeyT>
 __global__ void __launch_bounds__(kBlock) pack_sorted_sh_kernel(const KeyT* __restrict__ keys,
                                                                  const uint32_t* __restrict__ vals, long long m,
@@ -161,29 +162,33 @@ __global__ void __launch_bounds__(kBlock) pack_sorted_sh_kernel(const KeyT* __re
                                                                  const float* __restrict__ rgb, int d, int sw,
                                                                  float4* __restrict__ pA, float2* __restrict__ pB,
                                                                  float* __restrict__ pS, int* __restrict__ tile_accum) {
-  long long i = (long long)blockIdx.x * kBlock + threadIdx.x;
+  const long long t = (long long)blockIdx.x * kBlock + threadIdx.x;
+  const long long i = t >> 3;
+  const int sub = (int)(t & 7);
   if (i >= m) return;
-  uint32_t tile = keys[i];
-  if (i == 0) {
-    for (uint32_t t = 0; t <= tile; ++t) tile_accum[t] = 0;
-  } else {
-    uint32_t prev = keys[i - 1];
-    for (uint32_t t = prev + 1; t <= tile; ++t) tile_accum[t] = (int)i;
-  }
-  if (i == m - 1)
-    for (uint32_t t = tile + 1; t <= (uint32_t)n_tiles; ++t) tile_accum[t] = (int)m;
+  const uint32_t tile = keys[i];
   const uint32_t g = vals[i];
-  const GsRec* r = rec + g;
-  float4 a = r->a, b = r->b, c = r->c;
-  uint32_t rxy = __float_as_uint(c.z), rwh = __float_as_uint(c.w);
-  uint32_t tx = tile % ntx, ty = tile / ntx;
-  uint32_t slot = offsets_g[g] + (ty - (rxy >> 16)) * (rwh & 0xffffu) + (tx - (rxy & 0xffffu));
-  pA[i] = a;
-  pB[i] = make_float2(b.x, b.y);
+  if (sub == 0) {
+    if (i == 0) {
+      for (uint32_t tt = 0; tt <= tile; ++tt) tile_accum[tt] = 0;
+    } else {
+      uint32_t prev = keys[i - 1];
+      for (uint32_t tt = prev + 1; tt <= tile; ++tt) tile_accum[tt] = (int)i;
+    }
+    if (i == m - 1)
+      for (uint32_t tt = tile + 1; tt <= (uint32_t)n_tiles; ++tt) tile_accum[tt] = (int)m;
+    const GsRec* r = rec + g;
+    float4 a = r->a, b = r->b, c = r->c;
+    uint32_t rxy = __float_as_uint(c.z), rwh = __float_as_uint(c.w);
+    uint32_t tx = tile % ntx, ty = tile / ntx;
+    uint32_t slot = offsets_g[g] + (ty - (rxy >> 16)) * (rwh & 0xffffu) + (tx - (rxy & 0xffffu));
+    pA[i] = a;
+    pB[i] = make_float2(b.x, b.y);
+    pS[(size_t)i * sw + d] = __uint_as_float(slot);
+  }
   float* row = pS + (size_t)i * sw;
   const float* src = rgb + (size_t)g * d;
-  for (int q = 0; q < d; ++q) row[q] = src[q];
-  row[d] = __uint_as_float(slot);
+  for (int q = sub; q < d; q += 8) row[q] = src[q];
 }
 
 __global__ void __launch_bounds__(kBlock) iota_kernel(uint32_t* out, int n) {
@@ -197,7 +202,7 @@ cudaError_t gs_launch_pack_sorted_sh(const void* keys, int key_bytes, const uint
                                      int ntx, const GsRec* rec, const uint32_t* offsets_g, const float* rgb, int d,
                                      int sw, float4* pA, float2* pB, float* pS, int* tile_accum, cudaStream_t st) {
   if (m == 0) return cudaMemsetAsync(tile_accum, 0, sizeof(int) * (size_t)(n_tiles + 1), st);
-  const unsigned grid = (unsigned)((m + kBlock - 1) / kBlock);
+  const unsigned grid = (unsigned)((m * 8 + kBlock - 1) / kBlock);   // 8 lanes per instance
   if (key_bytes == 2)
     pack_sorted_sh_kernel<uint16_t><<<grid, kBlock, 0, st>>>(static_cast<const uint16_t*>(keys), vals, m, n_tiles,
                                                              ntx, rec, offsets_g, rgb, d, sw, pA, pB, pS, tile_accum);

@@ -165,19 +165,21 @@ __global__ void __launch_bounds__(64) blend_sh_fwd_kernel(const float4* __restri
         const float dx = px[p] - a.x;
         const float eu = fmaf(a.z, dx, -m1);
         const float alpha = gs_ex2(fmaf(-dx, eu, ev));
-        const float w = (T[p] > GS_T_STOP) ? alpha * T[p] : 0.f;
-        float col[3];
+        if (T[p] > GS_T_STOP) {          // a saturated pixel blends nothing: skip its 3K FMAs + 3 sigmoids
+          const float w = alpha * T[p];
+          float col[3];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          float acc = 0.f;
+          for (int c = 0; c < 3; ++c) {
+            float acc = 0.f;
 #pragma unroll
-          for (int q = 0; q < K; ++q) acc = fmaf(sh[p][q], cf[c * K + q], acc);
-          col[c] = sh_sigmoid(acc);
+            for (int q = 0; q < K; ++q) acc = fmaf(sh[p][q], cf[c * K + q], acc);
+            col[c] = sh_sigmoid(acc);
+          }
+          cr[p] = fmaf(col[0], w, cr[p]);
+          cg[p] = fmaf(col[1], w, cg[p]);
+          cb[p] = fmaf(col[2], w, cb[p]);
+          T[p] -= w;
         }
-        cr[p] = fmaf(col[0], w, cr[p]);
-        cg[p] = fmaf(col[1], w, cg[p]);
-        cb[p] = fmaf(col[2], w, cb[p]);
-        T[p] -= w;
       }
     }
     const bool dead = !(T[0] > GS_T_STOP) && !(T[1] > GS_T_STOP) && !(T[2] > GS_T_STOP) && !(T[3] > GS_T_STOP);
@@ -354,35 +356,36 @@ __global__ void __launch_bounds__(64) blend_sh_bwd_kernel(const float4* __restri
         const float dx = px[p] - a.x;
         const float eu = fmaf(a.z, dx, -m1);
         const float alpha = gs_ex2(fmaf(-dx, eu, ev));
-        const bool live = T[p] > GS_T_STOP;
-        const float w = live ? alpha * T[p] : 0.f;
-        float col[3];
+        if (T[p] > GS_T_STOP) {          // saturated pixels contribute exactly nothing
+          const float w = alpha * T[p];
+          float col[3];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          float t = 0.f;
+          for (int c = 0; c < 3; ++c) {
+            float t = 0.f;
 #pragma unroll
-          for (int q = 0; q < K; ++q) t = fmaf(sh[p][q], cf[c * K + q], t);
-          col[c] = sh_sigmoid(t);
-        }
-        const float gc = fmaf(gr[p], col[0], fmaf(gg[p], col[1], gb[p] * col[2]));
-        R[p] = fmaf(-gc, w, R[p]);
-        const float rc = gs_rcp(1.0000001f - alpha);
-        const float dal = fmaf(T[p], gc, -R[p] * rc);
-        const float e = live ? dal * alpha : 0.f;
-        T[p] -= w;
-        const float ex = e * dx;
-        s0 += e;
-        sx += ex;
-        sxx = fmaf(ex, dx, sxx);
-        // d colour_c / d coef[c*K+q] = sigma'(.) * SH_q      (gaussian.cu:666-674)
-        const float d0 = gr[p] * w * col[0] * (1.f - col[0]);
-        const float d1 = gg[p] * w * col[1] * (1.f - col[1]);
-        const float d2 = gb[p] * w * col[2] * (1.f - col[2]);
+            for (int q = 0; q < K; ++q) t = fmaf(sh[p][q], cf[c * K + q], t);
+            col[c] = sh_sigmoid(t);
+          }
+          const float gc = fmaf(gr[p], col[0], fmaf(gg[p], col[1], gb[p] * col[2]));
+          R[p] = fmaf(-gc, w, R[p]);
+          const float rc = gs_rcp(1.0000001f - alpha);
+          const float dal = fmaf(T[p], gc, -R[p] * rc);
+          const float e = dal * alpha;
+          T[p] -= w;
+          const float ex = e * dx;
+          s0 += e;
+          sx += ex;
+          sxx = fmaf(ex, dx, sxx);
+          // d colour_c / d coef[c*K+q] = sigma'(.) * SH_q      (gaussian.cu:666-674)
+          const float d0 = gr[p] * w * col[0] * (1.f - col[0]);
+          const float d1 = gg[p] * w * col[1] * (1.f - col[1]);
+          const float d2 = gb[p] * w * col[2] * (1.f - col[2]);
 #pragma unroll
-        for (int q = 0; q < K; ++q) {
-          acc[6 + q] = fmaf(d0, sh[p][q], acc[6 + q]);
-          acc[6 + K + q] = fmaf(d1, sh[p][q], acc[6 + K + q]);
-          acc[6 + 2 * K + q] = fmaf(d2, sh[p][q], acc[6 + 2 * K + q]);
+          for (int q = 0; q < K; ++q) {
+            acc[6 + q] = fmaf(d0, sh[p][q], acc[6 + q]);
+            acc[6 + K + q] = fmaf(d1, sh[p][q], acc[6 + K + q]);
+            acc[6 + 2 * K + q] = fmaf(d2, sh[p][q], acc[6 + 2 * K + q]);
+          }
         }
       }
       acc[0] = sx;
