@@ -370,6 +370,8 @@ struct RenderContext {
              "gs_render_backward");
   }
 
+  int64_t last_instances() { return (int64_t)gs_frame_instances(ctx); }
+
   py::dict stats() {
     gs_frame_info fi{};
     check_rc(gs_frame_stats(ctx, &fi, cur_stream()), "gs_frame_stats");
@@ -444,6 +446,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
            py::arg("g_pos"), py::arg("g_rgb"), py::arg("g_opa"), py::arg("g_quat"), py::arg("g_scale"),
            py::arg("expected_frame") = -1)
       .def("frame_id", &RenderContext::frame_id)
+      .def("last_instances", &RenderContext::last_instances)
       .def("stats", &RenderContext::stats)
       .def("set_timing", &RenderContext::set_timing)
       .def("stage_ms", &RenderContext::stage_ms)

@@ -413,6 +413,8 @@ extern "C" int gs_render_backward_final(gs_ctx* c, const float* pos, const float
                               grad_opa, grad_quat, grad_scale, stream);
 }
 
+extern "C" long long gs_frame_instances(gs_ctx* c) { return (c && c->have_forward) ? c->m : -1; }
+
 extern "C" int gs_frame_stats(gs_ctx* c, gs_frame_info* out, gs_stream_t stream) {
   if (!c || !out) return gs_set_error_msg(GS_ERR_INVALID_ARG, "gs_frame_stats: null argument");
   if (!c->have_forward) return gs_set_error_msg(GS_ERR_NO_FORWARD, "gs_frame_stats: no forward on this ctx");

@@ -218,7 +218,7 @@ def run_ours(args, world, rank, local):
     g = S.make_gaussians(n, w, h, 0, sh_dim=args.colour)
     views = [S.make_view(w, h, k) for k in range(8)]
     vd = [dict(width=v.width, height=v.height, focal_x=v.fx, focal_y=v.fy, rot=v.rot, tran=v.tran) for v in views]
-    sp = splatter.Splatter(g, vd, device=dev, use_sh_coeff=args.colour != 3)
+    sp = splatter.Splatter.from_tensors(g, vd, device=dev, use_sh_coeff=args.colour != 3)
     params = list(sp.gaussian_3ds.parameters())
     import dp
     bucket = dp.GradBucket(params)          # one NCCL all-reduce over one flat bucket (no-op at N=1)

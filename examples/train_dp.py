@@ -30,7 +30,7 @@ def build(n, w, h, n_views, dev, seed=0):
     teacher = S.make_gaussians(n, w, h, seed)
     views = [S.make_view(w, h, k) for k in range(n_views)]
     vd = [dict(width=v.width, height=v.height, focal_x=v.fx, focal_y=v.fy, rot=v.rot, tran=v.tran) for v in views]
-    sp_t = splatter.Splatter(teacher, vd, device=dev)
+    sp_t = splatter.Splatter.from_tensors(teacher, vd, device=dev)
     with torch.no_grad():
         gts = [sp_t(k).clone() for k in range(n_views)]
     g = torch.Generator().manual_seed(seed + 100)          # identical on every rank: replicas start equal
@@ -39,7 +39,7 @@ def build(n, w, h, n_views, dev, seed=0):
     student["rgb"] = torch.zeros_like(teacher["rgb"])
     student["opa"] = torch.full_like(teacher["opa"], -2.0)
     student["scale"] = teacher["scale"] * (1 + 0.2 * torch.randn(n, 3, generator=g)).clamp(0.5, 1.5)
-    return splatter.Splatter(student, vd, device=dev), gts
+    return splatter.Splatter.from_tensors(student, vd, device=dev), gts
 
 
 def make_optimizer(sp, lr=0.003):

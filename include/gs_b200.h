@@ -175,6 +175,10 @@ int gs_render_backward_final(gs_ctx* ctx, const float* pos, const float* rgb, co
 int gs_ctx_set_timing(gs_ctx* ctx, int enable);
 int gs_frame_stage_ms(gs_ctx* ctx, float* out_host, gs_stream_t stream);
 
+/* M (tile-instances) of the last forward on ctx, -1 if none; no synchronisation (the forward
+ * already read it back). */
+long long gs_frame_instances(gs_ctx* ctx);
+
 /* Statistics of the last forward on ctx (host struct; synchronises `stream` for M_eff). */
 int gs_frame_stats(gs_ctx* ctx, gs_frame_info* out_host, gs_stream_t stream);
 

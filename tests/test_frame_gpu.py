@@ -2,6 +2,8 @@
 the CPU oracle, the committed golden fixtures and the reference build's whole pipeline;
 plus size-independent properties at BASELINE.json's full sizes (P3/P5/P6 of SURVEY.md §8c).
 """
+import os
+
 import pytest
 import torch
 
@@ -18,7 +20,7 @@ GRAD_RTOL = 1e-3
 def _splatter(g, views, dev, **kw):
     import splatter
     vs = [dict(width=v.width, height=v.height, focal_x=v.fx, focal_y=v.fy, rot=v.rot, tran=v.tran) for v in views]
-    return splatter.Splatter(g, vs, device=dev, **kw)
+    return splatter.Splatter.from_tensors(g, vs, device=dev, **kw)
 
 
 def _oracle_frame(g, cam, grad_out, dtype=torch.float64, **kw):
@@ -264,7 +266,7 @@ import sys, torch, hashlib
 sys.path[:0] = [r'%s', r'%s', r'%s']
 import splatter, synthetic as S
 v = S.make_view(200, 120, 1); g = S.make_gaussians(5000, 200, 120, 4)
-sp = splatter.Splatter(g, [dict(width=v.width, height=v.height, focal_x=v.fx, focal_y=v.fy, rot=v.rot, tran=v.tran)])
+sp = splatter.Splatter.from_tensors(g, [dict(width=v.width, height=v.height, focal_x=v.fx, focal_y=v.fy, rot=v.rot, tran=v.tran)])
 img = sp(0); img.backward(S.make_grad_output(120, 200, 0).cuda() * 24000)
 h = hashlib.sha1(img.detach().cpu().numpy().tobytes())
 for p in sp.gaussian_3ds.parameters(): h.update(p.grad.cpu().numpy().tobytes())
@@ -330,3 +332,74 @@ def test_stale_forward_is_refused(gs, cuda):
     img1 = sp(1)                                # normal use keeps working
     img1.sum().backward()
     assert sp.gaussian_3ds.pos.grad is not None
+
+
+def test_splatter_reference_constructor_on_colmap_dataset(gs, cuda, tmp_path):
+    """The reference's own construction path (train.py:374-392): Splatter(colmap_dir, image_dir,
+    <reference kwargs>) on a synthetic COLMAP model + PNG images, then the train-step surface
+    train.py uses: forward(camera_id) vs ground_truth, backward, culling_mask accumulation,
+    adaptive_control + optimizer rebuild, reset_opa, n_tile_gaussians / n_gaussians."""
+    import cv2
+    import numpy as np
+    import colmap_io as C
+    import splatter
+    w, h, n_views = 160, 96, 4
+    teacher = S.make_gaussians(4000, w, h, 0)
+    views = [S.make_view(w, h, k) for k in range(n_views)]
+    vd = [dict(width=v.width, height=v.height, focal_x=v.fx, focal_y=v.fy, rot=v.rot, tran=v.tran) for v in views]
+    sp_t = splatter.Splatter.from_tensors(teacher, vd, device=cuda)
+    sparse, imgdir = tmp_path / "sparse" / "0", tmp_path / "images_1"
+    os.makedirs(sparse), os.makedirs(imgdir)
+    cams = {1: C.Camera(1, "PINHOLE", w, h, np.array([views[0].fx, views[0].fy, w / 2, h / 2]))}
+    imgs = {}
+    for k, v in enumerate(views):
+        with torch.no_grad():
+            im = (sp_t(k).clamp(0, 1) * 255).byte().cpu().numpy()
+        cv2.imwrite(str(imgdir / f"v{k}.png"), im[..., ::-1])
+        imgs[k + 1] = C.Image(k + 1, C.rotmat_to_qvec(v.rot.numpy()), v.tran.numpy(), 1, f"v{k}.png")
+    pts = {i: C.Point3D(i, teacher["pos"][i].numpy(), (torch.sigmoid(teacher["rgb"][i]) * 255).byte().numpy(), 0.0)
+           for i in range(0, 4000, 2)}
+    C.write_cameras_binary(sparse / "cameras.bin", cams)
+    C.write_images_binary(sparse / "images.bin", imgs)
+    C.write_points3d_binary(sparse / "points3D.bin", pts)
+
+    sp = splatter.Splatter(str(sparse), str(imgdir), render_weight_normalize=False, render_downsample=1,
+                           use_sh_coeff=False, scale_init_value=0.5, opa_init_value=0.3, tile_culling_method="prob2",
+                           tile_culling_dist_thresh=0.5, tile_culling_prob_thresh=0.05, debug=0, scale_activation="abs",
+                           cudaculling=1, load_ckpt=None, fast_drawing=True, test=False)
+    assert len(sp.imgs) == n_views and sp.gaussian_3ds.pos.shape == (2000, 3) and sp.gaussian_3ds.quat.shape == (2000, 4)
+    assert torch.allclose(sp.views[2]["rot"], views[2].rot, atol=1e-5) and abs(sp.views[0]["focal_x"] - views[0].fx) < 1e-3
+    g3 = sp.gaussian_3ds
+
+    def make_opt():
+        return torch.optim.Adam([{"params": g3.opa, "lr": 0.03}, {"params": g3.rgb, "lr": 0.03},
+                                 {"params": g3.pos, "lr": 0.003}, {"params": g3.scale, "lr": 0.003},
+                                 {"params": g3.quat, "lr": 0.003}], betas=(0.9, 0.99))
+    opt = make_opt()
+    accum = torch.zeros_like(g3.pos)
+    counter = torch.zeros(g3.pos.shape[0], device=cuda)
+    losses = []
+    for it in range(40):
+        opt.zero_grad()
+        img = sp(it % n_views)
+        assert img.shape == (h, w, 3) and sp.ground_truth.shape == (h, w, 3) and sp.ground_truth.dtype == torch.float16
+        loss = (img - sp.ground_truth).abs().mean()             # train.py:99
+        loss.backward()
+        opt.step()
+        accum += g3.pos.grad.abs()                              # train.py:149-150
+        counter += sp.culling_mask.to(torch.float32)
+        losses.append(float(loss))
+        assert sp.n_tile_gaussians > 0 and sp.n_gaussians == g3.pos.shape[0]
+    assert losses[-1] < losses[0]
+    n0 = g3.pos.shape[0]
+    info = g3.adaptive_control(accum / (counter + 1e-3).unsqueeze(-1), taus=0.02, delete_thresh=1.5,
+                               scale_activation=sp.scale_activation, grad_thresh=1e-7, use_clone=True, use_split=True,
+                               grad_aggregation="max", clone_dt=0.01)
+    assert info["total"] == g3.pos.shape[0] == n0 - info["deleted"] + info["cloned"] + info["split"]
+    assert info["cloned"] + info["split"] > 0
+    opt = make_opt()                                            # train.py:173-181
+    g3.reset_opa()
+    img = sp(0)
+    (img - sp.ground_truth).abs().mean().backward()
+    opt.step()
+    assert g3.pos.grad.shape[0] == info["total"] and bool(torch.isfinite(g3.pos).all())

@@ -302,3 +302,72 @@ def test_draw_sh_vs_reference_build(gs, ref, cuda):
     for k in ("rgb", "opa", "cov"):
         assert rel_err(a_g[k], b_g[k]) < GRAD_RTOL, k
     assert rel_err(a_g["pos"][:, :2], b_g["pos"][:, :2]) < GRAD_RTOL
+
+
+# ---- legacy tile-culling methods 0 ("dist") and 1 ("prob"): brute force over (Gaussian, tile) ----
+def _tile_bounds(cam, dev):
+    left = torch.linspace(-cam.Wp / 2, cam.Wp / 2, cam.ntx + 1)[:-1]
+    top = torch.linspace(-cam.Hp / 2, cam.Hp / 2, cam.nty + 1)[:-1]
+    l = (left / cam.fx).repeat(cam.nty)
+    r = ((left + 16) / cam.fx).repeat(cam.nty)
+    t = (top / cam.fy).repeat_interleave(cam.ntx)
+    b = ((top + 16) / cam.fy).repeat_interleave(cam.ntx)
+    return [x.float().contiguous().to(dev) for x in (t, b, l, r)]
+
+
+def _legacy_lists(gmod, method, pos, cov, cam, thresh, dev):
+    T = cam.ntx * cam.nty
+    n = pos.shape[0]
+    cnt = torch.zeros(T, dtype=torch.int32, device=dev)
+    lst = torch.full((T, n), -1, dtype=torch.int32, device=dev)
+    cobj = gmod.Gaussian3ds()
+    cobj.pos, cobj.cov = pos.to(dev).contiguous(), cov.to(dev).contiguous()
+    cobj.rgb, cobj.opa = torch.zeros(n, 3, device=dev), torch.zeros(n, device=dev)
+    tiles = gmod.Tiles()
+    tiles.top, tiles.bottom, tiles.left, tiles.right = _tile_bounds(cam, dev)
+    gmod.calc_tile_list(cobj, tiles, cnt, lst, thresh, method, cam.tile_lx, cam.tile_ly, cam.ntx, cam.nty, cam.leftmost,
+                        cam.topmost)
+    return _per_tile_sets(cnt, lst)
+
+
+def _small_projected_scene():
+    g, v, cam = scene(1500, 160, 96, k=0)
+    nq, ns, _, _ = O.preactivate(g["quat"], g["scale"], g["opa"], g["rgb"])
+    rp, rc, m = O.global_culling(g["pos"], nq, ns, cam.rot, cam.tran, cam.near, cam.half_w, cam.half_h)
+    idx = torch.nonzero(m.bool()).squeeze(-1)
+    return rp[idx].contiguous(), rc[idx].contiguous(), cam
+
+
+def test_tile_methods_dist_and_prob_vs_torch(gs, cuda):
+    gaussian, _ = gs
+    pos, cov, cam = _small_projected_scene()
+    t, b, l, r = [x.cpu() for x in _tile_bounds(cam, cuda)]
+    # method 0 "dist" (gaussian.cu:101-136): centre distance^2 to the tile centre < thresh
+    thresh0 = (cam.tile_lx / 0.5) ** 2                                       # splatter.py:576
+    cx, cy = (l + r) / 2, (t + b) / 2
+    d2 = (pos[:, 0:1] - cx[None]) ** 2 + (pos[:, 1:2] - cy[None]) ** 2        # [n, T]
+    want0 = [sorted(torch.nonzero(d2[:, k] < thresh0).squeeze(-1).tolist()) for k in range(t.numel())]
+    got0 = _legacy_lists(gaussian, 0, pos, cov, cam, thresh0, cuda)
+    flips0 = sum(len(set(a) ^ set(w)) for a, w in zip(got0, want0))
+    assert sum(map(len, want0)) > 0 and flips0 <= 2
+    # method 1 "prob" (gaussian.cu:138-195): bbox of the thresh-ellipse overlaps the tile
+    a, bb, c, d = cov.reshape(-1, 4).unbind(-1)
+    det = a * d - bb * c
+    t2 = -2 * torch.log(torch.tensor(0.05))
+    sx = torch.sqrt(a / (det + 1e-14) * t2 * det)
+    sy = torch.sqrt(d / (det + 1e-14) * t2 * det)
+    hit = ~((r[None] < (pos[:, 0:1] - sx[:, None])) | ((pos[:, 0:1] + sx[:, None]) < l[None]) |
+            (b[None] < (pos[:, 1:2] - sy[:, None])) | ((pos[:, 1:2] + sy[:, None]) < t[None])) & (det > 0)[:, None]
+    want1 = [sorted(torch.nonzero(hit[:, k]).squeeze(-1).tolist()) for k in range(t.numel())]
+    got1 = _legacy_lists(gaussian, 1, pos, cov, cam, 0.05, cuda)
+    flips1 = sum(len(set(a_) ^ set(w)) for a_, w in zip(got1, want1))
+    assert sum(map(len, want1)) > 0 and flips1 <= 2
+
+
+def test_tile_methods_dist_and_prob_vs_reference_build(gs, ref, cuda):
+    gaussian, _ = gs
+    gref, _ = ref
+    pos, cov, cam = _small_projected_scene()
+    for method, thresh in ((0, (cam.tile_lx / 0.5) ** 2), (1, 0.05)):
+        assert _legacy_lists(gaussian, method, pos, cov, cam, thresh, cuda) == \
+            _legacy_lists(gref, method, pos, cov, cam, thresh, cuda), method
