@@ -60,3 +60,18 @@ def test_shim_rejects_cpu_tensors():
     import gaussian
     with pytest.raises(RuntimeError):
         gaussian.world2camera(torch.zeros(4, 3), torch.eye(3), torch.zeros(3), torch.zeros(4, 3))
+
+
+def test_product_path_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing under the package may import, call or link it, and
+    the package must not carry a CPU fallback for the kernels."""
+    bad = []
+    for root, _, files in os.walk(PKG):
+        if "build" in root.split(os.sep):
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                txt = open(os.path.join(root, f), errors="ignore").read()
+                if re.search(r"gs_oracle|ref_pipeline|import\s+oracle|from\s+oracle|oracle/", txt):
+                    bad.append(os.path.join(root, f))
+    assert not bad, bad

@@ -403,3 +403,56 @@ def test_splatter_reference_constructor_on_colmap_dataset(gs, cuda, tmp_path):
     (img - sp.ground_truth).abs().mean().backward()
     opt.step()
     assert g3.pos.grad.shape[0] == info["total"] and bool(torch.isfinite(g3.pos).all())
+
+
+def test_c_abi_host_buffer_entry_point(gs, cuda):
+    """gs_render_forward_backward_host called straight through ctypes (no torch types in the
+    signature): device-resident parameters, HOST image / gradient buffers; must reproduce the
+    Python path bit for bit."""
+    import ctypes
+    pkg = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "3d-gaussian-splatting_b200")
+    lib = ctypes.CDLL(os.path.join(pkg, "libgs_b200.so"))
+
+    class Cam(ctypes.Structure):
+        _fields_ = [("width", ctypes.c_int), ("height", ctypes.c_int), ("focal_x", ctypes.c_float),
+                    ("focal_y", ctypes.c_float), ("rot", ctypes.c_float * 9), ("tran", ctypes.c_float * 3),
+                    ("near_plane", ctypes.c_float), ("tile_thresh", ctypes.c_float)]
+    n, w, h = 3000, 112, 80                                  # padded to 112 x 80
+    g, v, cam = scene(n, w, h, k=1)
+    sp = _splatter(g, [v], cuda)
+    gpad = torch.zeros(cam.Hp, cam.Wp, 3)
+    gpad[:h, :w] = S.make_grad_output(h, w, 0) * (h * w)
+    raw = sp.render_padded()
+    raw.backward(gpad.to(cuda))
+    want = [p.grad.clone() for p in sp.gaussian_3ds.parameters()]
+
+    P = ctypes.c_void_p
+    lib.gs_last_error.restype = ctypes.c_char_p
+    ctx = P()
+    assert lib.gs_ctx_create(ctypes.byref(ctx)) == 0
+    c = Cam(w, h, v.fx, v.fy, (ctypes.c_float * 9)(*v.rot.flatten().tolist()), (ctypes.c_float * 3)(*v.tran.tolist()),
+            0.3, 0.05)
+    dev = {k: t.to(cuda).contiguous() for k, t in g.items()}
+    grads = {k: torch.empty_like(t) for k, t in dev.items()}
+    gimg_host = gpad.contiguous().pin_memory()
+    img_host = torch.empty(cam.Hp, cam.Wp, 3).pin_memory()
+    lib.gs_render_forward_backward_host.argtypes = [P] * 6 + [ctypes.c_int] * 3 + [ctypes.POINTER(Cam)] + [P] * 8
+    torch.cuda.synchronize()
+    rc = lib.gs_render_forward_backward_host(
+        ctx, dev["pos"].data_ptr(), dev["rgb"].data_ptr(), dev["opa"].data_ptr(), dev["quat"].data_ptr(),
+        dev["scale"].data_ptr(), n, 3, 0, ctypes.byref(c), gimg_host.data_ptr(), img_host.data_ptr(),
+        grads["pos"].data_ptr(), grads["rgb"].data_ptr(), grads["opa"].data_ptr(), grads["quat"].data_ptr(),
+        grads["scale"].data_ptr(), None)
+    assert rc == 0, lib.gs_last_error()
+    assert torch.equal(img_host, raw.detach().cpu())
+    for a, b in zip((grads[k] for k in ("pos", "rgb", "opa", "quat", "scale")), want):
+        assert torch.equal(a, b)
+    # error conventions: unsupported colour width -> GS_ERR_UNSUPPORTED (-2) with a message, no crash
+    rc = lib.gs_render_forward_backward_host(
+        ctx, dev["pos"].data_ptr(), dev["rgb"].data_ptr(), dev["opa"].data_ptr(), dev["quat"].data_ptr(),
+        dev["scale"].data_ptr(), n, 5, 0, ctypes.byref(c), gimg_host.data_ptr(), img_host.data_ptr(),
+        grads["pos"].data_ptr(), grads["rgb"].data_ptr(), grads["opa"].data_ptr(), grads["quat"].data_ptr(),
+        grads["scale"].data_ptr(), None)
+    assert rc == -2 and b"colour width" in lib.gs_last_error()
+    lib.gs_ctx_destroy.argtypes = [P]
+    lib.gs_ctx_destroy(ctx)
