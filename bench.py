@@ -354,9 +354,12 @@ def run_reference(args, world, rank, local):
                 "cpu_baseline": cb,
                 "e2e": {"value": cb["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     dev = torch.device("cuda", local)
-    g = S.make_gaussians(n, w, h, 0)
+    if args.colour == 48:
+        return {"impl": "reference", "unavailable": "the reference has no SH degree-3 path (calc_sh is called with 9 bases only)"}
+    g = S.make_gaussians(n, w, h, 0, sh_dim=args.colour)
     v = S.make_view(w, h, 0)
-    frame = ref_pipeline.LegacyFrame(gref, rref, w, h, v.fx, v.fy, v.rot.to(dev), v.tran.to(dev))
+    frame = ref_pipeline.LegacyFrame(gref, rref, w, h, v.fx, v.fy, v.rot.to(dev), v.tran.to(dev),
+                                     use_sh_coeff=args.colour != 3)
     p = {k: t.to(dev).clone().requires_grad_(True) for k, t in g.items()}
     go = S.make_grad_output(h, w, 0).to(dev)
 
@@ -381,7 +384,7 @@ def run_reference(args, world, rank, local):
             "value": fps, "unit": "frames/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {n} gaussians, {w}x{h}, RGB, "
+            "config": {"workload": f"{args.workload}: {n} gaussians, {w}x{h}, {'RGB' if args.colour == 3 else 'SH-27'}, "
                                    f"{'forward only' if fwd_only else 'forward+backward'}, view 0",
                        "impl": "reference CUDA build (oracle/_ref: unmodified gaussian.cu + bindings.cpp + renderer.py, "
                                "-std=c++17 flag only) driven with the call sequence of reference splatter.py:513-655",
