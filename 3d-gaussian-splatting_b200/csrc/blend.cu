@@ -194,7 +194,8 @@ __global__ void __launch_bounds__(32 * WARPS) blend_bwd_kernel(const float4* __r
                                                                 const float* __restrict__ image,
                                                                 const float* __restrict__ grad_image,
                                                                 float* __restrict__ grad_inst, int grad_is_final,
-                                                                GsCrop crop) {
+                                                                GsCrop crop, uint32_t* __restrict__ row_epoch,
+                                                                uint32_t epoch) {
   constexpr int THREADS = 32 * WARPS;
   constexpr int PX = 256 / THREADS;          // 8 (1 warp) or 4 (2 warps)
   constexpr int TPR = GS_TILE / PX;          // threads per pixel row
@@ -370,6 +371,7 @@ __global__ void __launch_bounds__(32 * WARPS) blend_bwd_kernel(const float4* __r
                            -GS_LN2 * s[2], GS_LN2 * s[3]);
       out[1] = make_float4(-GS_LN2 * s[4], GS_LN2 * s[5], s[6], s[7]);
       out[2] = make_float4(s[8], 0.f, 0.f, 0.f);
+      if (row_epoch) row_epoch[slot] = epoch;      // marks the row as written in this frame
     }
     bool dead = true;
 #pragma unroll
@@ -388,7 +390,9 @@ __global__ void __launch_bounds__(32 * WARPS) blend_bwd_kernel(const float4* __r
     for (int kk = k + 1; kk < nchunks && kk < k + BWD_STAGES; ++kk)
       gs_mbar_wait(&sm.full[kk % BWD_STAGES], (uint32_t)((kk / BWD_STAGES) & 1));
   }
-  // the unread tail of a saturated tile has zero gradient
+  // the unread tail of a saturated tile has zero gradient: with an epoch array the rows are simply
+  // left stale (the consumer skips rows whose tag is not this frame's); otherwise write zeros
+  if (row_epoch) return;
   for (int t = consumed + tid; t < cnt; t += THREADS) {
     const uint32_t slot = __float_as_uint(pC[start + t].w);
     float4* out = reinterpret_cast<float4*>(grad_inst + (size_t)slot * GS_GREC);
@@ -525,14 +529,15 @@ cudaError_t gs_launch_blend_fwd(const float4* pA, const float2* pB, const float4
 
 cudaError_t gs_launch_blend_bwd(const float4* pA, const float2* pB, const float4* pC, const int* tile_accum,
                                 const GsFrameGeom& g, const float* image, const float* grad_image, float* grad_inst,
-                                int grad_is_final, const GsCrop& crop, cudaStream_t st) {
+                                int grad_is_final, const GsCrop& crop, uint32_t* row_epoch, uint32_t epoch,
+                                cudaStream_t st) {
   static const int warps = getenv("GS_BWD_WARPS") ? atoi(getenv("GS_BWD_WARPS")) : 2;   // A/B knob: 1 = one warp x 8 px
   if (warps == 2)
     blend_bwd_kernel<2><<<g.n_tiles, 64, 0, st>>>(pA, pB, pC, tile_accum, g.wp, g.hp, g.ntx, g.fx, g.fy, image,
-                                                  grad_image, grad_inst, grad_is_final, crop);
+                                                  grad_image, grad_inst, grad_is_final, crop, row_epoch, epoch);
   else
     blend_bwd_kernel<1><<<g.n_tiles, 32, 0, st>>>(pA, pB, pC, tile_accum, g.wp, g.hp, g.ntx, g.fx, g.fy, image,
-                                                  grad_image, grad_inst, grad_is_final, crop);
+                                                  grad_image, grad_inst, grad_is_final, crop, row_epoch, epoch);
   return cudaGetLastError();
 }
 
@@ -621,13 +626,13 @@ extern "C" int gs_draw_bwd(const float* pos, const float* rgb, const float* opa,
   g.fy = focal_y;
   if (d == 3) {
     GS_CUDA_TRY(gs_launch_blend_bwd(ws.pA, ws.pB, ws.pC, tile_n_point_accum, g, image, grad_image, ws.grad_inst, 0,
-                                    GsCrop{}, st));
+                                    GsCrop{}, nullptr, 0u, st));
     legacy_unpack_grads_kernel<<<(m + 255) / 256, 256, 0, st>>>(ws.grad_inst, opa, cov, m, grad_pos, grad_rgb,
                                                               grad_opa, grad_cov);
   } else {
     GsRayPtrs r{rays_o, lefttop, vec_dx, vec_dy};
     GS_CUDA_TRY(gs_launch_blend_sh_bwd(ws.pA, ws.pB, reinterpret_cast<float*>(ws.pC), d, tile_n_point_accum, g, r,
-                                       image, grad_image, ws.grad_inst, 0, GsCrop{}, st));
+                                       image, grad_image, ws.grad_inst, 0, GsCrop{}, nullptr, 0u, st));
     legacy_unpack_grads_sh_kernel<<<(m + 255) / 256, 256, 0, st>>>(ws.grad_inst, gs_sh_grad_width(d), opa, cov, m, d,
                                                                  grad_pos, grad_rgb, grad_opa, grad_cov);
   }

@@ -37,7 +37,7 @@ cudaError_t gs_launch_blend_sh_fwd(const float4* pA, const float2* pB, const flo
 cudaError_t gs_launch_blend_sh_bwd(const float4* pA, const float2* pB, const float* pS, int d, const int* tile_accum,
                                    const GsFrameGeom& g, const GsRayPtrs& r, const float* image,
                                    const float* grad_image, float* grad_inst, int grad_is_final, const GsCrop& crop,
-                                   cudaStream_t st);
+                                   uint32_t* row_epoch, uint32_t epoch, cudaStream_t st);
 
 // ---- project.cu ------------------------------------------------------------------------
 cudaError_t gs_launch_fused_project(const float* pos, const float* rgb, const float* opa, const float* quat,
@@ -49,7 +49,8 @@ cudaError_t gs_launch_fused_project(const float* pos, const float* rgb, const fl
 cudaError_t gs_launch_fused_project_bwd(const float* pos, const float* rgb, const float* opa, const float* quat,
                                         const float* scale, int n, int d, int scale_act, const GsCam& cam,
                                         float near_plane, float half_w, float half_h, const uint32_t* offsets_g,
-                                        const uint32_t* count, const float* grad_inst, float* g_pos, float* g_rgb, float* g_opa,
+                                        const uint32_t* count, const float* grad_inst, const uint32_t* row_epoch, uint32_t epoch,
+                                        float* g_pos, float* g_rgb, float* g_opa,
                                         float* g_quat, float* g_scale, cudaStream_t st);
 
 // ---- binning.cu ------------------------------------------------------------------------
@@ -73,4 +74,5 @@ cudaError_t gs_launch_blend_fwd(const float4* pA, const float2* pB, const float4
 cudaError_t gs_launch_blend_bwd(const float4* pA, const float2* pB, const float4* pC, const int* tile_accum,
                                 const GsFrameGeom& g, const float* image, const float* grad_image,
                                 float* grad_inst /*[M,GS_GREC] rows addressed by C.w slot*/, int grad_is_final,
-                                const GsCrop& crop, cudaStream_t st);
+                                const GsCrop& crop, uint32_t* row_epoch /*nullable*/, uint32_t epoch,
+                                cudaStream_t st);

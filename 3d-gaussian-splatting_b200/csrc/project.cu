@@ -98,7 +98,8 @@ __global__ void __launch_bounds__(kBlock) fused_project_bwd_kernel(
     const float* __restrict__ pos, const float* __restrict__ rgb, const float* __restrict__ opa,
     const float* __restrict__ quat, const float* __restrict__ scale, int n, int scale_act, GsCam cam,
     float near_plane, float half_w, float half_h, const uint32_t* __restrict__ offsets_g,
-    const uint32_t* __restrict__ count, const float* __restrict__ grad_inst, float* __restrict__ g_pos,
+    const uint32_t* __restrict__ count, const float* __restrict__ grad_inst,
+    const uint32_t* __restrict__ row_epoch, uint32_t epoch, float* __restrict__ g_pos,
     float* __restrict__ g_rgb, float* __restrict__ g_opa, float* __restrict__ g_quat, float* __restrict__ g_scale) {
   int i = blockIdx.x * kBlock + threadIdx.x;
   if (i >= n) return;
@@ -110,20 +111,29 @@ __global__ void __launch_bounds__(kBlock) fused_project_bwd_kernel(
   const uint32_t cnt = count[i];
   if (cnt > 0) {
     const uint32_t o0 = offsets_g[i], o1 = o0 + cnt;   // this Gaussian's contiguous gradient rows
-    for (uint32_t r = o0; r < o1; ++r) {
-      const float4* row = reinterpret_cast<const float4*>(grad_inst + (size_t)r * GW);
-#pragma unroll
-      for (int q = 0; q < GW / 4; ++q) {
-        const float4 v = row[q];
-        acc[4 * q] += v.x;
-        acc[4 * q + 1] += v.y;
-        acc[4 * q + 2] += v.z;
-        acc[4 * q + 3] += v.w;
-      }
-    }
+    // issue the parameter loads BEFORE the row loop so that both round trips to HBM overlap
     float p[3] = {pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]};
     float q[4], s[3], raw_s[3], qn;
     load_activated(quat, scale, i, scale_act, q, s, raw_s, qn);
+    const float opa_raw = opa[i];
+    float rgb_raw[3] = {0.f, 0.f, 0.f};
+    if (D == 3) {
+      rgb_raw[0] = rgb[3 * i];
+      rgb_raw[1] = rgb[3 * i + 1];
+      rgb_raw[2] = rgb[3 * i + 2];
+    }
+    for (uint32_t r = o0; r < o1; ++r) {
+      if (row_epoch[r] != epoch) continue;     // instance not reached by its (saturated) tile: zero gradient
+      const float4* row = reinterpret_cast<const float4*>(grad_inst + (size_t)r * GW);
+#pragma unroll
+      for (int qq = 0; qq < GW / 4; ++qq) {
+        const float4 v = row[qq];
+        acc[4 * qq] += v.x;
+        acc[4 * qq + 1] += v.y;
+        acc[4 * qq + 2] += v.z;
+        acc[4 * qq + 3] += v.w;
+      }
+    }
     GsProj o = gs_project(cam, p, q, s, near_plane, half_w, half_h);
     // conic (ca, cb, cc) = (d, b+c, a) * sc,  sc = log2e / (2 det + 1e-14)
     float det = o.a * o.d - o.b * o.c;
@@ -150,13 +160,13 @@ __global__ void __launch_bounds__(kBlock) fused_project_bwd_kernel(
       else
         gs_raw[k] = gsv[k] * expf(fminf(fmaxf(raw_s[k], -1.f), 1.f));   // renderer.py:98-100
     }
-    float op = gs_sigmoid(opa[i]);
+    float op = gs_sigmoid(opa_raw);
     // l2o = log2(op):  d/d logit = d_l2o / (op ln2) * op (1-op) = d_l2o (1-op) / ln2
     go = acc[5] * (1.f - op) / GS_LN2;
     if (D == 3) {
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        float c = gs_sigmoid(rgb[3 * i + k]);
+        float c = gs_sigmoid(rgb_raw[k]);
         acc[6 + k] *= c * (1.f - c);
       }
     }
@@ -325,13 +335,15 @@ cudaError_t gs_launch_fused_project(const float* pos, const float* rgb, const fl
 cudaError_t gs_launch_fused_project_bwd(const float* pos, const float* rgb, const float* opa, const float* quat,
                                         const float* scale, int n, int d, int scale_act, const GsCam& cam,
                                         float near_plane, float half_w, float half_h, const uint32_t* offsets_g,
-                                        const uint32_t* count, const float* grad_inst, float* g_pos, float* g_rgb, float* g_opa,
+                                        const uint32_t* count, const float* grad_inst, const uint32_t* row_epoch, uint32_t epoch,
+                                        float* g_pos, float* g_rgb, float* g_opa,
                                         float* g_quat, float* g_scale, cudaStream_t st) {
   if (n == 0) return cudaSuccess;
 #define GS_LAUNCH_PBWD(D, GW)                                                                                     \
   fused_project_bwd_kernel<D, GW><<<grid_for(n), kBlock, 0, st>>>(pos, rgb, opa, quat, scale, n, scale_act, cam,  \
                                                                   near_plane, half_w, half_h, offsets_g, count,  \
-                                                                  grad_inst, g_pos, g_rgb, g_opa, g_quat, g_scale)
+                                                                  grad_inst, row_epoch, epoch, g_pos, g_rgb, g_opa,   \
+                                                                  g_quat, g_scale)
   if (d == 3) GS_LAUNCH_PBWD(3, GS_GREC);
   else if (d == 27) GS_LAUNCH_PBWD(27, 36);
   else GS_LAUNCH_PBWD(48, 56);

@@ -74,7 +74,8 @@ struct gs_ctx {
   DevBuf rec, count, offsets, dkey_in, dkey_out, perm, iota, offsets_g;
   size_t iota_n = 0;
   // per instance
-  DevBuf keys_in, keys_out, vals_in, vals_out, pA, pB, pC, grad_inst;
+  DevBuf keys_in, keys_out, vals_in, vals_out, pA, pB, pC, grad_inst, row_epoch;
+  uint32_t epoch = 0;                      // tag of the current backward in row_epoch[]
   // per tile / misc
   DevBuf tile_accum, tile_neff, cub_tmp, counters, img_dev, gimg_dev, rays;
   float* host_rays = nullptr;             // pinned: rays_o, lefttop, dx, dy (SH colour only)
@@ -121,7 +122,7 @@ extern "C" void gs_ctx_destroy(gs_ctx* c) {
   if (!c) return;
   cudaDeviceSynchronize();
   DevBuf* bufs[] = {&c->rec, &c->count, &c->offsets, &c->dkey_in, &c->dkey_out, &c->perm, &c->iota, &c->offsets_g, &c->keys_in, &c->keys_out,
-                    &c->vals_in, &c->vals_out, &c->pA, &c->pB, &c->pC, &c->grad_inst, &c->tile_accum, &c->tile_neff,
+                    &c->vals_in, &c->vals_out, &c->pA, &c->pB, &c->pC, &c->grad_inst, &c->row_epoch, &c->tile_accum, &c->tile_neff,
                     &c->cub_tmp, &c->counters, &c->img_dev, &c->gimg_dev, &c->rays};
   for (DevBuf* b : bufs) b->release();
   if (c->host_m) cudaFreeHost(c->host_m);
@@ -371,6 +372,17 @@ static int render_backward_impl(gs_ctx* c, const float* pos, const float* rgb, c
   const int d = c->d;
   const size_t grow = d == 3 ? (size_t)GS_GREC * 4 : (size_t)gs_sh_grad_width(d) * 4;
   GS_CUDA_TRY(c->grad_inst.reserve(M * grow + 16, st));
+  {
+    // one u32 tag per gradient row: rows written by this backward carry `epoch`; the tails of
+    // saturated tiles are never written nor read (saves ~0.2 GB of HBM writes + reads at C3)
+    void* before = c->row_epoch.p;
+    GS_CUDA_TRY(c->row_epoch.reserve(M * 4 + 16, st));
+    if (c->row_epoch.p != before || c->epoch == 0xffffffffu) {
+      GS_CUDA_TRY(cudaMemsetAsync(c->row_epoch.p, 0, c->row_epoch.cap, st));
+      c->epoch = 0;
+    }
+    ++c->epoch;
+  }
   c->ev_bwd_valid = false;
   GsCrop crop{(c->geom.wp - c->geom.width) / 2, (c->geom.hp - c->geom.height) / 2, c->geom.width, c->geom.height};
   gs_mark(c, 7, st);
@@ -378,19 +390,20 @@ static int render_backward_impl(gs_ctx* c, const float* pos, const float* rgb, c
     if (d == 3) {
       GS_CUDA_TRY(gs_launch_blend_bwd(c->pA.as<float4>(), c->pB.as<float2>(), c->pC.as<float4>(),
                                       c->tile_accum.as<int>(), c->geom, image, grad_image, c->grad_inst.as<float>(),
-                                      grad_is_final, crop, st));
+                                      grad_is_final, crop, c->row_epoch.as<uint32_t>(), c->epoch, st));
     } else {
       const float* rp = c->rays.as<float>();
       GsRayPtrs rays{rp, rp + 3, rp + 6, rp + 9};
       GS_CUDA_TRY(gs_launch_blend_sh_bwd(c->pA.as<float4>(), c->pB.as<float2>(), c->pC.as<float>(), d,
                                          c->tile_accum.as<int>(), c->geom, rays, image, grad_image,
-                                         c->grad_inst.as<float>(), grad_is_final, crop, st));
+                                         c->grad_inst.as<float>(), grad_is_final, crop,
+                                         c->row_epoch.as<uint32_t>(), c->epoch, st));
     }
   }
   gs_mark(c, 8, st);
   GS_CUDA_TRY(gs_launch_fused_project_bwd(pos, rgb, opa, quat, scale, c->n, d, c->scale_act, c->cam, c->near_plane,
                                           c->half_w, c->half_h, c->offsets_g.as<uint32_t>(), c->count.as<uint32_t>(),
-                                          c->grad_inst.as<float>(),
+                                          c->grad_inst.as<float>(), c->row_epoch.as<uint32_t>(), c->epoch,
                                           grad_pos, grad_rgb, grad_opa, grad_quat, grad_scale, st));
   gs_mark(c, 9, st);
   c->ev_bwd_valid = c->timing && c->ev_ok;
