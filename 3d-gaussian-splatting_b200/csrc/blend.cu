@@ -25,9 +25,9 @@ namespace {
 // =======================================================================================
 constexpr int FWD_THREADS = 64;    // 2 warps per tile; each thread owns a row of 4 adjacent pixels
 constexpr int FWD_PX = 4;
-constexpr int FWD_CH = 128;
 constexpr int FWD_STAGES = 2;
 
+template <int FWD_CH>
 struct FwdSmem {
   float4 A[FWD_STAGES][FWD_CH];
   float4 C[FWD_STAGES][FWD_CH];
@@ -51,6 +51,7 @@ __device__ __forceinline__ void issue_chunk(SM& sm, int stage, const float4* __r
 // Per (thread, instance): 3 broadcast LDS + 4 row-shared FP32 ops (dy, cb*dy, cc*dy, l2o-cc*dy^2)
 // + 4 pixels x (dx, u, exponent, MUFU.EX2, setp, mul, sel, 3 FFMA colour, T update) = 12.75
 // issue slots per (pixel, instance) instead of 17-18 with one pixel per thread.
+template <int FWD_CH>
 __global__ void __launch_bounds__(FWD_THREADS) blend_fwd_kernel(const float4* __restrict__ pA,
                                                                  const float2* __restrict__ pB,
                                                                  const float4* __restrict__ pC,
@@ -59,7 +60,7 @@ __global__ void __launch_bounds__(FWD_THREADS) blend_fwd_kernel(const float4* __
                                                                  float* __restrict__ image,
                                                                  int* __restrict__ tile_neff,
                                                                  float* __restrict__ final_img, GsCrop crop) {
-  __shared__ __align__(16) FwdSmem sm;
+  __shared__ __align__(16) FwdSmem<FWD_CH> sm;
   const int tile = blockIdx.x;
   const int tid = threadIdx.x;
   const int tx = tile % ntx, ty = tile / ntx;
@@ -83,7 +84,7 @@ __global__ void __launch_bounds__(FWD_THREADS) blend_fwd_kernel(const float4* __
   __syncthreads();
   if (tid == 0) {
     for (int k = 0; k < FWD_STAGES && k < nchunks; ++k)
-      issue_chunk<FwdSmem, FWD_CH>(sm, k, pA, pB, pC, start + k * FWD_CH, min(FWD_CH, cnt - k * FWD_CH), shift);
+      issue_chunk<FwdSmem<FWD_CH>, FWD_CH>(sm, k, pA, pB, pC, start + k * FWD_CH, min(FWD_CH, cnt - k * FWD_CH), shift);
   }
 
   float T[FWD_PX], cr[FWD_PX], cg[FWD_PX], cb[FWD_PX];
@@ -144,7 +145,7 @@ __global__ void __launch_bounds__(FWD_THREADS) blend_fwd_kernel(const float4* __
     }
     if (tid == 0 && k + FWD_STAGES < nchunks) {
       const int kn = k + FWD_STAGES;
-      issue_chunk<FwdSmem, FWD_CH>(sm, stage, pA, pB, pC, start + kn * FWD_CH, min(FWD_CH, cnt - kn * FWD_CH), shift);
+      issue_chunk<FwdSmem<FWD_CH>, FWD_CH>(sm, stage, pA, pB, pC, start + kn * FWD_CH, min(FWD_CH, cnt - kn * FWD_CH), shift);
     }
   }
   // drain copies that were issued but never consumed (early exit) before the CTA retires
@@ -168,11 +169,10 @@ __global__ void __launch_bounds__(FWD_THREADS) blend_fwd_kernel(const float4* __
 // =======================================================================================
 // backward
 // =======================================================================================
-constexpr int BWD_CH = 64;
 constexpr int BWD_STAGES = 2;
 constexpr int BWD_NV = 9;   // Sx Sy Sxx Sxy Syy S0 Cr Cg | Cb
 
-template <int WARPS>
+template <int WARPS, int BWD_CH>
 struct BwdSmem {
   float4 A[BWD_STAGES][BWD_CH];
   float4 C[BWD_STAGES][BWD_CH];
@@ -185,7 +185,7 @@ struct BwdSmem {
 // horizontally adjacent pixels, so dy and every dy-only factor is shared by its pixels:
 // per pixel only S0 += e, Sx += e dx, Sxx += e dx^2 are accumulated and
 // Sy = dy S0, Sxy = dy Sx, Syy = dy^2 S0 are formed once per (thread, instance).
-template <int WARPS>
+template <int WARPS, int BWD_CH>
 __global__ void __launch_bounds__(32 * WARPS) blend_bwd_kernel(const float4* __restrict__ pA,
                                                                 const float2* __restrict__ pB,
                                                                 const float4* __restrict__ pC,
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(32 * WARPS) blend_bwd_kernel(const float4* __r
   constexpr int THREADS = 32 * WARPS;
   constexpr int PX = 256 / THREADS;          // 8 (1 warp) or 4 (2 warps)
   constexpr int TPR = GS_TILE / PX;          // threads per pixel row
-  using Smem = BwdSmem<WARPS>;
+  using Smem = BwdSmem<WARPS, BWD_CH>;
   __shared__ __align__(16) Smem sm;
   const int tile = blockIdx.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -522,8 +522,14 @@ inline size_t legacy_ws_layout(int m, int d, LegacyWs* ws, char* base) {
 cudaError_t gs_launch_blend_fwd(const float4* pA, const float2* pB, const float4* pC, const int* tile_accum,
                                 const GsFrameGeom& g, float* image, int* tile_neff, float* final_img,
                                 const GsCrop& crop, cudaStream_t st) {
-  blend_fwd_kernel<<<g.n_tiles, FWD_THREADS, 0, st>>>(pA, pB, pC, tile_accum, g.wp, g.hp, g.ntx, g.fx, g.fy, image,
-                                                      tile_neff, final_img, crop);
+  static const int ch = getenv("GS_FWD_CH") ? atoi(getenv("GS_FWD_CH")) : 256;   // A/B knob (staging chunk)
+#define GS_FWD_LAUNCH(CH)                                                                                       \
+  blend_fwd_kernel<CH><<<g.n_tiles, FWD_THREADS, 0, st>>>(pA, pB, pC, tile_accum, g.wp, g.hp, g.ntx, g.fx, g.fy, \
+                                                          image, tile_neff, final_img, crop)
+  if (ch == 64) GS_FWD_LAUNCH(64);
+  else if (ch == 256) GS_FWD_LAUNCH(256);
+  else GS_FWD_LAUNCH(128);
+#undef GS_FWD_LAUNCH
   return cudaGetLastError();
 }
 
@@ -532,12 +538,15 @@ cudaError_t gs_launch_blend_bwd(const float4* pA, const float2* pB, const float4
                                 int grad_is_final, const GsCrop& crop, uint32_t* row_epoch, uint32_t epoch,
                                 cudaStream_t st) {
   static const int warps = getenv("GS_BWD_WARPS") ? atoi(getenv("GS_BWD_WARPS")) : 2;   // A/B knob: 1 = one warp x 8 px
-  if (warps == 2)
-    blend_bwd_kernel<2><<<g.n_tiles, 64, 0, st>>>(pA, pB, pC, tile_accum, g.wp, g.hp, g.ntx, g.fx, g.fy, image,
-                                                  grad_image, grad_inst, grad_is_final, crop, row_epoch, epoch);
-  else
-    blend_bwd_kernel<1><<<g.n_tiles, 32, 0, st>>>(pA, pB, pC, tile_accum, g.wp, g.hp, g.ntx, g.fx, g.fy, image,
-                                                  grad_image, grad_inst, grad_is_final, crop, row_epoch, epoch);
+  static const int ch = getenv("GS_BWD_CH") ? atoi(getenv("GS_BWD_CH")) : 64;            // A/B knob (staging chunk)
+#define GS_BWD_LAUNCH(W, CH)                                                                                         \
+  blend_bwd_kernel<W, CH><<<g.n_tiles, 32 * W, 0, st>>>(pA, pB, pC, tile_accum, g.wp, g.hp, g.ntx, g.fx, g.fy, image, \
+                                                        grad_image, grad_inst, grad_is_final, crop, row_epoch, epoch)
+  if (warps == 1) GS_BWD_LAUNCH(1, 64);
+  else if (ch == 32) GS_BWD_LAUNCH(2, 32);
+  else if (ch == 128) GS_BWD_LAUNCH(2, 128);
+  else GS_BWD_LAUNCH(2, 64);
+#undef GS_BWD_LAUNCH
   return cudaGetLastError();
 }
 
