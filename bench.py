@@ -238,16 +238,13 @@ def run_ours(args, world, rank, local):
             img.backward(go_dev)
             bucket.allreduce()
 
-    ms = timed_loop(step_resident, args.steps, args.warmup, world, dev)
-
-    # clocks are sampled during a second identical timed region so that nvidia-smi polling
-    # cannot perturb the headline number
+    # clocks / throttle reasons are sampled DURING the timed region (nvidia-smi -lms 20 in a side
+    # process; the sampler is started, and has delivered its first row, before the warm-up)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms_b = timed_loop(step_resident, args.steps, 0, world, dev)
+    ms = timed_loop(step_resident, args.steps, args.warmup, world, dev)
     clocks = sampler.stop() if rank == 0 else {}
-    ms = min(ms, ms_b)
 
     # per-stage device times of the last frame (CUDA events on the launching stream)
     stage = sp._rctx.stage_ms()
@@ -374,11 +371,9 @@ def run_reference(args, world, rank, local):
             img.backward(go)
 
     sampler = ClockSampler(local)
-    ms = timed_loop(step, args.steps, args.warmup, 1, dev)
     sampler.start()
-    ms2 = timed_loop(step, args.steps, 0, 1, dev)
+    ms = timed_loop(step, args.steps, args.warmup, 1, dev)
     clocks = sampler.stop()
-    ms = min(ms, ms2)
     fps = 1000.0 / ms
     return {"impl": "reference", "metric": METRIC if args.workload == "C3" else f"FPS ({args.workload})",
             "value": fps, "unit": "frames/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
