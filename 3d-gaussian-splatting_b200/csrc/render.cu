@@ -80,6 +80,7 @@ struct gs_ctx {
   DevBuf tile_accum, tile_neff, cub_tmp, counters, img_dev, gimg_dev, rays;
   float* host_rays = nullptr;             // pinned: rays_o, lefttop, dx, dy (SH colour only)
   unsigned long long* host_m = nullptr;   // pinned: {M}
+  cudaEvent_t ev_m = nullptr;             // marks the completion of the M read-back
   // state of the last forward
   bool have_forward = false;
   int n = 0, d = 3, scale_act = 0;
@@ -110,6 +111,7 @@ extern "C" int gs_ctx_create(gs_ctx** out) {
   GS_CUDA_TRY(cudaGetDevice(&c->device));
   cudaError_t e = cudaMallocHost(reinterpret_cast<void**>(&c->host_m), 64);
   if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&c->host_rays), 64);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_m, cudaEventDisableTiming);
   if (e != cudaSuccess) {
     delete c;
     return gs_set_error(e, "cudaMallocHost");
@@ -127,6 +129,7 @@ extern "C" void gs_ctx_destroy(gs_ctx* c) {
   for (DevBuf* b : bufs) b->release();
   if (c->host_m) cudaFreeHost(c->host_m);
   if (c->host_rays) cudaFreeHost(c->host_rays);
+  if (c->ev_m) cudaEventDestroy(c->ev_m);
   if (c->ev_ok)
     for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
   delete c;
@@ -250,15 +253,18 @@ static int render_forward_impl(gs_ctx* c, const float* pos, const float* rgb, co
   GS_CUDA_TRY(c->cub_tmp.reserve(tmp_bytes, st));
   GS_CUDA_TRY(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp3, c->count.as<uint32_t>(), c->offsets_g.as<uint32_t>(),
                                             n + 1, st));
+  // the one host round trip of the frame: M = offsets_g[N] is known right after the first scan, so
+  // its read-back is enqueued BEFORE the depth sort and the host waits on an event recorded there -
+  // the GPU keeps sorting while the host wakes up and enqueues the rest of the frame (no bubble)
+  *c->host_m = 0;
+  GS_CUDA_TRY(cudaMemcpyAsync(c->host_m, c->offsets_g.as<uint32_t>() + N, 4, cudaMemcpyDeviceToHost, st));
+  GS_CUDA_TRY(cudaEventRecord(c->ev_m, st));
   if (n > 0)
     GS_CUDA_TRY(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp_bytes, c->dkey_in.as<uint32_t>(),
                                                 c->dkey_out.as<uint32_t>(), c->iota.as<uint32_t>(),
                                                 c->perm.as<uint32_t>(), n, 0, 32, st));
   GS_CUDA_TRY(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp2, cnt_it, c->offsets.as<uint32_t>(), n + 1, st));
-  // the one host round trip of the frame
-  *c->host_m = 0;
-  GS_CUDA_TRY(cudaMemcpyAsync(c->host_m, c->offsets.as<uint32_t>() + N, 4, cudaMemcpyDeviceToHost, st));
-  GS_CUDA_TRY(cudaStreamSynchronize(st));
+  GS_CUDA_TRY(cudaEventSynchronize(c->ev_m));
   long long m = (long long)(*c->host_m & 0xffffffffull);
   if (m >= (1ll << 31)) return gs_set_error_msg(GS_ERR_UNSUPPORTED, "gs_render_forward: more than 2^31 tile instances");
   size_t M = (size_t)m;
