@@ -106,7 +106,9 @@ int gs_jacobian(const float* pos_cam, int n, float* jac /*[n,3,3]*/, gs_stream_t
  * autograd glue around it): parameters -> image, grad_image -> parameter gradients.
  * ------------------------------------------------------------------------------------- */
 
-typedef struct gs_ctx gs_ctx; /* owns device workspaces; one per (device, in-flight frame) */
+typedef struct gs_ctx gs_ctx; /* owns device workspaces; one per (device, in-flight frame).  NOT thread-safe:
+                                 use a context from one host thread / one stream at a time; it holds the
+                                 intermediate state of its LAST forward only. */
 
 typedef struct gs_camera {
   int width, height;          /* un-padded image size; render target is padded to x16 */
