@@ -400,6 +400,25 @@ struct RenderContext {
   }
 };
 
+// fused Adam over flat buffers; seg_ends / lrs are small host lists
+void adam_step(torch::Tensor param, torch::Tensor grad, torch::Tensor exp_avg, torch::Tensor exp_avg_sq,
+               std::vector<int64_t> seg_ends, std::vector<double> lrs, double beta1, double beta2, double eps,
+               int64_t step) {
+  GS_CHECK_F32(param); GS_CHECK_F32(grad); GS_CHECK_F32(exp_avg); GS_CHECK_F32(exp_avg_sq);
+  int64_t n = param.numel();
+  TORCH_CHECK(grad.numel() == n && exp_avg.numel() == n && exp_avg_sq.numel() == n, "adam_step: size mismatch");
+  TORCH_CHECK(seg_ends.size() == lrs.size() && !seg_ends.empty() && seg_ends.back() == n,
+              "adam_step: segments must cover the flat buffer");
+  for (auto* t : {&param, &grad, &exp_avg, &exp_avg_sq})
+    TORCH_CHECK(reinterpret_cast<uintptr_t>(t->data_ptr()) % 16 == 0, "adam_step: buffers must be 16-byte aligned");
+  std::vector<long long> ends(seg_ends.begin(), seg_ends.end());
+  std::vector<float> lr(lrs.begin(), lrs.end());
+  c10::cuda::CUDAGuard guard(param.device());
+  check_rc(gs_adam_step(fpm(param), fp(grad), fpm(exp_avg), fpm(exp_avg_sq), n, ends.data(), lr.data(), (int)ends.size(),
+                        (float)beta1, (float)beta2, (float)eps, (int)step, cur_stream()),
+           "gs_adam_step");
+}
+
 }  // namespace gsb200
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
@@ -451,5 +470,6 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def("set_timing", &RenderContext::set_timing)
       .def("stage_ms", &RenderContext::stage_ms)
       .def("sorted_instances", &RenderContext::sorted_instances);
+  m.def("adam_step", &adam_step, "fused Adam over flat parameter / gradient buffers (CUDA)");
   m.attr("abi_version") = gs_abi_version();
 }

@@ -22,6 +22,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "3d-gaussian-splatting_b200"))
 
 import dp  # noqa: E402
+import optim  # noqa: E402
 import splatter  # noqa: E402
 import synthetic as S  # noqa: E402
 
@@ -42,15 +43,16 @@ def build(n, w, h, n_views, dev, seed=0):
     return splatter.Splatter.from_tensors(student, vd, device=dev), gts
 
 
-def make_optimizer(sp, lr=0.003):
+def make_optimizer(sp, lr=0.003, fused=True):
     g = sp.gaussian_3ds
-    return torch.optim.Adam([                                        # train.py:56-64
+    cls = optim.FlatAdam if fused else torch.optim.Adam             # FlatAdam: one kernel over the flat bucket
+    return cls([                                                     # train.py:56-64
         {"params": g.opa, "lr": lr * 10}, {"params": g.rgb, "lr": lr * 10}, {"params": g.pos, "lr": lr},
         {"params": g.scale, "lr": lr}, {"params": g.quat, "lr": lr}], betas=(0.9, 0.99))
 
 
-def train(sp, gts, iters, world, rank, log_every=50, lr=0.003):
-    opt = make_optimizer(sp, lr)
+def train(sp, gts, iters, world, rank, log_every=50, lr=0.003, fused_adam=True):
+    opt = make_optimizer(sp, lr, fused_adam)
     params = list(sp.gaussian_3ds.parameters())
     bucket = dp.GradBucket(params, average=True)
     hist = []
@@ -81,6 +83,7 @@ def main():
     ap.add_argument("--res", default="640x360")
     ap.add_argument("--iters", type=int, default=300)
     ap.add_argument("--views", type=int, default=8)
+    ap.add_argument("--torch-adam", action="store_true", help="use torch.optim.Adam instead of the fused flat Adam")
     args = ap.parse_args()
     w, h = (int(x) for x in args.res.split("x"))
     world, rank, local = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0))
@@ -90,7 +93,7 @@ def main():
         torch.distributed.init_process_group("nccl", device_id=dev)
     torch.manual_seed(2023)                                           # identical torch RNG on all ranks
     sp, gts = build(args.gaussians, w, h, args.views, dev)
-    hist, ips = train(sp, gts, args.iters, world, rank)
+    hist, ips = train(sp, gts, args.iters, world, rank, fused_adam=not args.torch_adam)
     if rank == 0:
         print(f"done: {ips:.1f} it/s ({ips * world:.1f} views/s on {world} GPU), L1 {hist[0][1]:.5f} -> {hist[-1][1]:.5f}, "
               f"PSNR {hist[0][2]:.2f} -> {hist[-1][2]:.2f} dB")

@@ -199,6 +199,17 @@ int gs_render_forward_backward_host(gs_ctx* ctx, const float* pos, const float* 
                                     float* grad_pos, float* grad_rgb, float* grad_opa,
                                     float* grad_quat, float* grad_scale, gs_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Next-row widening: fused Adam over the flat parameter / gradient buckets.
+ * Replaces torch.optim.Adam over the five parameter groups of reference train.py:56-64 (same
+ * update as torch's single-tensor Adam, no weight decay / amsgrad).  `param`, `grad`, `exp_avg`,
+ * `exp_avg_sq` are flat device buffers of n floats (n % 4 == 0) split into n_seg (<= 8) segments
+ * ending at seg_end_host[s] (ascending multiples of 4) with learning rate lr_host[s]; `step` is
+ * the 1-based step count used for the bias corrections. */
+int gs_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
+                 const long long* seg_end_host, const float* lr_host, int n_seg, float beta1, float beta2,
+                 float eps, int step, gs_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
