@@ -32,6 +32,25 @@ for _p in ("3d-gaussian-splatting_b200", "oracle"):
 
 import torch  # noqa: E402
 
+
+def _ensure_built():
+    """In-tree .so files normally travel with the snapshot; build them on a bare checkout."""
+    import glob
+    pkg = os.path.join(ROOT, "3d-gaussian-splatting_b200")
+    if glob.glob(os.path.join(pkg, "gaussian*.so")) and os.path.exists(os.path.join(pkg, "libgs_b200.so")):
+        return
+    if int(os.environ.get("RANK", "0")) == 0:
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("gs_b200_build", os.path.join(pkg, "build.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        mod.build_all()
+    else:                                   # other ranks wait for rank 0's build
+        t0 = time.time()
+        while not glob.glob(os.path.join(pkg, "gaussian*.so")) and time.time() - t0 < 900:
+            time.sleep(2)
+        time.sleep(5)
+
 WORKLOADS = {
     # name: (N gaussians, width, height, forward_only)
     "C2": (500_000, 1920, 1080, False),
@@ -411,6 +430,8 @@ def main():
     args = ap.parse_args()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
+    if args.impl != "reference":
+        _ensure_built()
     world, rank, local = dist_setup(args.gpus)
     if args.impl == "reference":
         out = run_reference(args, world, rank, local)
