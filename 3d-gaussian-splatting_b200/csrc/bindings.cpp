@@ -419,6 +419,22 @@ void adam_step(torch::Tensor param, torch::Tensor grad, torch::Tensor exp_avg, t
            "gs_adam_step");
 }
 
+// NVLS in-place all-reduce of a symmetric flat buffer (multicast address as an integer)
+void allreduce_multimem(int64_t multicast_ptr, int64_t n_floats, int rank, int world, int device) {
+  c10::cuda::CUDAGuard guard(c10::Device(c10::kCUDA, (c10::DeviceIndex)device));
+  check_rc(gs_allreduce_multimem_f32(reinterpret_cast<void*>(static_cast<uintptr_t>(multicast_ptr)), n_floats, rank,
+                                     world, cur_stream()),
+           "gs_allreduce_multimem_f32");
+}
+
+void allreduce_p2p(std::vector<int64_t> peer_ptrs, int64_t n_floats, int rank, int world, int device) {
+  c10::cuda::CUDAGuard guard(c10::Device(c10::kCUDA, (c10::DeviceIndex)device));
+  TORCH_CHECK((int)peer_ptrs.size() == world, "allreduce_p2p: need one pointer per rank");
+  std::vector<void*> ptrs;
+  for (int64_t p : peer_ptrs) ptrs.push_back(reinterpret_cast<void*>(static_cast<uintptr_t>(p)));
+  check_rc(gs_allreduce_p2p_f32(ptrs.data(), n_floats, rank, world, cur_stream()), "gs_allreduce_p2p_f32");
+}
+
 }  // namespace gsb200
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
@@ -470,6 +486,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def("set_timing", &RenderContext::set_timing)
       .def("stage_ms", &RenderContext::stage_ms)
       .def("sorted_instances", &RenderContext::sorted_instances);
+  m.def("allreduce_p2p", &allreduce_p2p, "peer-to-peer two-shot in-place all-reduce of a symmetric buffer");
+  m.def("allreduce_multimem", &allreduce_multimem, "NVLS multimem in-place all-reduce of a symmetric buffer");
   m.def("adam_step", &adam_step, "fused Adam over flat parameter / gradient buffers (CUDA)");
   m.attr("abi_version") = gs_abi_version();
 }

@@ -139,6 +139,18 @@ global_culling = _GlobalCulling.apply
 SCALE_ACTIVATIONS = {"abs": 0, "exp": 1}
 
 
+_flat_grad_allocator = None
+
+
+def set_flat_grad_allocator(fn):
+    """Install `fn(numel, device) -> 1-D fp32 tensor (16-byte aligned)` as the source of the flat
+    gradient bucket the fused backward writes into (None restores torch.empty).  Data-parallel
+    runs use it to place the bucket in symmetric memory so the gradient exchange runs in place over
+    NVLink (dp.NvlsGradBucket): the backward kernel's stores ARE the collective's send buffer."""
+    global _flat_grad_allocator
+    _flat_grad_allocator = fn
+
+
 def _flat_grads(tensors):
     """Five gradient views carved out of ONE flat buffer (order pos, rgb, opa, quat, scale; each
     segment 16-byte aligned for the kernel's float4 stores) so that the data-parallel all-reduce
@@ -148,7 +160,11 @@ def _flat_grads(tensors):
     for n in sizes:
         starts.append(o)
         o += (n + 3) // 4 * 4
-    flat = torch.empty(o, device=tensors[0].device, dtype=torch.float32)
+    if _flat_grad_allocator is not None:
+        flat = _flat_grad_allocator(o, tensors[0].device)
+        assert flat.numel() >= o and flat.dtype == torch.float32 and flat.data_ptr() % 16 == 0
+    else:
+        flat = torch.empty(o, device=tensors[0].device, dtype=torch.float32)
     outs = []
     for t, n, b in zip(tensors, sizes, starts):
         outs.append(flat[b:b + n].view(t.shape))

@@ -240,7 +240,13 @@ def run_ours(args, world, rank, local):
     sp = splatter.Splatter.from_tensors(g, vd, device=dev, use_sh_coeff=args.colour != 3)
     params = list(sp.gaussian_3ds.parameters())
     import dp
-    bucket = dp.GradBucket(params)          # one NCCL all-reduce over one flat bucket (no-op at N=1)
+    # N>1: in-place sum of the symmetric gradient bucket the backward writes into, by our own
+    # kernel over NVLink peer memory (p2p at N=2, NVSwitch multimem at N>=4); falls back to one NCCL
+    # all-reduce of the same flat bucket when symmetric memory is unavailable or --exchange nccl is
+    # given (no-op at N=1)
+    bucket = dp.make_grad_bucket(params, exchange=args.exchange)
+    exchange = "none" if world == 1 else (f"own kernel over symmetric memory ({bucket.mode})"
+                                          if isinstance(bucket, dp.SymmetricGradBucket) else "NCCL all-reduce")
     view_id = rank % 8
     go_host = S.make_grad_output(h, w, 0).pin_memory()
     go_dev = go_host.to(dev)
@@ -325,7 +331,7 @@ def run_ours(args, world, rank, local):
                    "tile_instances_M": M, "tile_instances_consumed_M_eff": Meff, "max_tile_count": st["max_tile_count"],
                    "n_visible": st["n_visible"], "l2": "inputs larger than L2 (per-frame working set "
                                                        f"{(M * 112 + n * 56) / 1e6:.0f} MB >> 126 MB)",
-                   "parallelism": f"dp{world} over views, NCCL all-reduce of the gradient bucket"},
+                   "parallelism": f"dp{world} over views, gradient bucket exchange: {exchange}"},
         "clocks": clocks,
         "e2e": {"value": world * 1000.0 / ms_e2e, "unit": "frames/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": int(go_host.numel() * 4 + 48), "d2h_bytes_per_step": int(img_host.numel() * 4),
@@ -424,6 +430,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "multimem", "p2p", "nccl"],
+                    help="N>1 gradient exchange: own multimem / p2p kernel on a symmetric bucket, NCCL all-reduce, "
+                         "or auto (p2p at N=2, multimem at N>=4, NCCL if symmetric memory is unavailable)")
     ap.add_argument("--colour", type=int, default=3, choices=[3, 27, 48],
                     help="3 = RGB (default; the reference's published 2.4M point), 27 = per-pixel SH degree 2 "
                          "(the reference's use_sh_coeff), 48 = SH degree 3 extension")

@@ -54,7 +54,7 @@ def make_optimizer(sp, lr=0.003, fused=True):
 def train(sp, gts, iters, world, rank, log_every=50, lr=0.003, fused_adam=True):
     opt = make_optimizer(sp, lr, fused_adam)
     params = list(sp.gaussian_3ds.parameters())
-    bucket = dp.GradBucket(params, average=True)
+    bucket = dp.make_grad_bucket(params, average=True)   # peer-memory exchange when available, else NCCL
     hist = []
     torch.cuda.synchronize()
     t0 = time.time()

@@ -210,6 +210,24 @@ int gs_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg
                  const long long* seg_end_host, const float* lr_host, int n_seg, float beta1, float beta2,
                  float eps, int step, gs_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Multi-GPU exchange step (new - the reference is single-GPU): in-place SUM of
+ * the flat gradient bucket across `world` GPUs of one NVSwitch domain through an NVLS multicast
+ * mapping.  `multicast_ptr` is the multicast address of a symmetric buffer holding each rank's
+ * n_floats (multiple of 4) gradients at the same offset; rank r reduces and re-broadcasts slice r
+ * (multimem.ld_reduce + multimem.st).  The caller orders it between two cross-rank barriers
+ * (all buckets written before; all slices visible after).  No synchronisation inside. */
+int gs_allreduce_multimem_f32(void* multicast_ptr, long long n_floats, int rank, int world,
+                              gs_stream_t stream);
+
+/* The same exchange over plain peer mappings (no multicast needed): `peer_ptrs` is a HOST array
+ * of `world` (2, 4 or 8) device pointers, entry p = rank p's copy of the bucket as mapped into
+ * this process (entry `rank` = the local copy).  Rank r sums slice r over all copies and stores
+ * the sum into all of them.  Same barrier contract as above. */
+#define GS_MAX_PEERS 8
+int gs_allreduce_p2p_f32(void* const* peer_ptrs, long long n_floats, int rank, int world,
+                         gs_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
