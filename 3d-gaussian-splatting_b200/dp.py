@@ -83,8 +83,10 @@ class SymmetricGradBucket:
                        peer; moves 2 (W-1)/W bucket sizes per direction - the least for W = 2.
       mode "auto":     p2p for W = 2, multimem otherwise (p2p if there is no multicast mapping).
 
-    Measured on B200 for the 134 MB bucket of 2.4 M Gaussians, W = 2: p2p 0.214 ms, multimem
-    0.357 ms, NCCL all-reduce 0.292 ms (profiles/r1_exchange.md).
+    Measured on B200 for the 134 MB bucket of 2.4 M Gaussians (profiles/r1_exchange.md), exchange
+    alone: W = 2: p2p 0.214 ms, multimem 0.357, NCCL 0.292; W = 8: multimem 0.330, p2p 0.394,
+    NCCL 0.394.  Inside the training step only the W = 2 gain survives (rank skew dominates at
+    W >= 4), which is why `make_grad_bucket("auto")` picks this class for W = 2 only.
 
     `allocator` must be installed with `renderer.set_flat_grad_allocator` (make_grad_bucket does
     it).  A change of the bucket size (densification changes N on every rank at the same step)
@@ -167,8 +169,9 @@ class SymmetricGradBucket:
 def make_grad_bucket(params: Sequence[torch.Tensor], average: bool = False, group=None, exchange: str = "auto"):
     """The gradient exchange for `params`: `exchange` (env GS_DP_EXCHANGE overrides) is
     "nccl" (portable `GradBucket`), "multimem" / "p2p" (required `SymmetricGradBucket` mode) or
-    "auto": a `SymmetricGradBucket` (installed as the backward's bucket allocator) when the group
-    is NCCL with world > 1 on CUDA and symmetric memory works, else `GradBucket`."""
+    "auto": a p2p `SymmetricGradBucket` (installed as the backward's bucket allocator) when the
+    group is NCCL with world == 2 on CUDA and symmetric memory works - the one case where it
+    measurably beats NCCL inside the step - else `GradBucket`."""
     import os
     import sys
     exchange = os.environ.get("GS_DP_EXCHANGE", exchange)
@@ -176,6 +179,8 @@ def make_grad_bucket(params: Sequence[torch.Tensor], average: bool = False, grou
     params = list(params)
     usable = (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
               and len(params) > 0 and params[0].is_cuda and dist.get_backend(group) == "nccl")
+    if exchange == "auto" and usable and dist.get_world_size(group) != 2:
+        exchange = "nccl"
     if exchange != "nccl" and usable:
         try:
             import renderer

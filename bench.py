@@ -241,9 +241,9 @@ def run_ours(args, world, rank, local):
     params = list(sp.gaussian_3ds.parameters())
     import dp
     # N>1: in-place sum of the symmetric gradient bucket the backward writes into, by our own
-    # kernel over NVLink peer memory (p2p at N=2, NVSwitch multimem at N>=4); falls back to one NCCL
-    # all-reduce of the same flat bucket when symmetric memory is unavailable or --exchange nccl is
-    # given (no-op at N=1)
+    # kernel over NVLink peer memory at N=2 (p2p; measured faster than NCCL inside the step); one NCCL
+    # all-reduce of the same flat bucket at N>=4, where --exchange multimem|p2p showed no gain
+    # (profiles/r1_exchange.md), or when symmetric memory is unavailable (no-op at N=1)
     bucket = dp.make_grad_bucket(params, exchange=args.exchange)
     exchange = "none" if world == 1 else (f"own kernel over symmetric memory ({bucket.mode})"
                                           if isinstance(bucket, dp.SymmetricGradBucket) else "NCCL all-reduce")
@@ -432,7 +432,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", default="auto", choices=["auto", "multimem", "p2p", "nccl"],
                     help="N>1 gradient exchange: own multimem / p2p kernel on a symmetric bucket, NCCL all-reduce, "
-                         "or auto (p2p at N=2, multimem at N>=4, NCCL if symmetric memory is unavailable)")
+                         "or auto (p2p at N=2, NCCL otherwise)")
     ap.add_argument("--colour", type=int, default=3, choices=[3, 27, 48],
                     help="3 = RGB (default; the reference's published 2.4M point), 27 = per-pixel SH degree 2 "
                          "(the reference's use_sh_coeff), 48 = SH degree 3 extension")
