@@ -308,6 +308,7 @@ def run_ours(args, world, rank, local):
 
     if rank != 0:
         return None
+    own_exchange = (not fwd_only) and isinstance(bucket, dp.SymmetricGradBucket)
     M, Meff = int(st["n_instances"]), int(st["n_instances_eff"])
     T = int(st["n_tiles"])
     P = int(st["width_padded"]) * int(st["height_padded"])
@@ -336,9 +337,10 @@ def run_ours(args, world, rank, local):
         "e2e": {"value": world * 1000.0 / ms_e2e, "unit": "frames/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": int(go_host.numel() * 4 + 48), "d2h_bytes_per_step": int(img_host.numel() * 4),
                 "api": "Splatter.forward(camera_id) + image.backward(grad) with pinned host grad / image buffers"},
-        "gpu_launches": int((4 if fwd_only else 6) * args.steps),
+        "gpu_launches": int(((4 if fwd_only else 6) + int(own_exchange)) * args.steps),
         "gpu_launches_note": "our kernels per step: fused_project, emit_keys, pack_sorted, blend_fwd"
-                             + ("" if fwd_only else ", blend_bwd, fused_project_bwd") +
+                             + ("" if fwd_only else ", blend_bwd, fused_project_bwd")
+                             + (", p2p/multimem allreduce" if own_exchange else "") +
                              "; plus CUB scan (2) and onesweep radix sort (8) library kernels",
         "stage_ms": dict(zip(["project", "depth_sort+scan+readback", "emit_keys", "tile_sort", "pack", "blend_fwd",
                               "blend_bwd", "project_bwd"], [round(x, 4) for x in stage])),
