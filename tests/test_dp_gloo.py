@@ -54,6 +54,15 @@ def _worker(rank, world, port, out):
     dp.GradBucket(params).allreduce()
     ok = ok and bool((flat[0:150] == 3.0).all()) and bool((params[2].grad == 3.0).all()) \
         and params[0].grad.untyped_storage().data_ptr() == flat.untyped_storage().data_ptr()
+    # exchange selection: a gloo / CPU group always gets the portable bucket; forcing a peer-memory
+    # mode there is an error, not a silent fallback
+    ok = ok and type(dp.make_grad_bucket(params)) is dp.GradBucket \
+        and type(dp.make_grad_bucket(params, exchange="nccl")) is dp.GradBucket
+    try:
+        dp.make_grad_bucket(params, exchange="p2p")
+        ok = False
+    except RuntimeError:
+        pass
     out[rank] = (ok, views, bucket.nbytes())
     dist.destroy_process_group()
 
