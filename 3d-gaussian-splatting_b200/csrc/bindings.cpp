@@ -268,7 +268,8 @@ struct RenderContext {
     GS_CHECK_F32(pos); GS_CHECK_F32(rgb); GS_CHECK_F32(opa); GS_CHECK_F32(quat); GS_CHECK_F32(scale);
     int64_t n = pos.size(0);
     TORCH_CHECK(pos.dim() == 2 && pos.size(1) == 3 && opa.numel() == n && quat.numel() == n * 4 &&
-                    scale.numel() == n * 3 && rgb.dim() == 2 && rgb.size(0) == n, "RenderContext.forward: bad shapes");
+                    scale.numel() == n * 3 && rgb.dim() == 2 && rgb.size(0) == n && n < (int64_t(1) << 31),
+                "RenderContext.forward: bad shapes");
     TORCH_CHECK(pos.device().index() == device, "RenderContext was created on another device");
     c10::cuda::CUDAGuard guard(pos.device());
     gs_camera cam = make_cam(width, height, fx, fy, rot, tran, near, thresh);
@@ -313,7 +314,8 @@ struct RenderContext {
     GS_CHECK_F32(pos); GS_CHECK_F32(rgb); GS_CHECK_F32(opa); GS_CHECK_F32(quat); GS_CHECK_F32(scale);
     int64_t n = pos.size(0);
     TORCH_CHECK(pos.dim() == 2 && pos.size(1) == 3 && opa.numel() == n && quat.numel() == n * 4 &&
-                    scale.numel() == n * 3 && rgb.dim() == 2 && rgb.size(0) == n, "RenderContext.forward: bad shapes");
+                    scale.numel() == n * 3 && rgb.dim() == 2 && rgb.size(0) == n && n < (int64_t(1) << 31),
+                "RenderContext.forward: bad shapes");
     TORCH_CHECK(pos.device().index() == device, "RenderContext was created on another device");
     c10::cuda::CUDAGuard guard(pos.device());
     gs_camera cam = make_cam(width, height, fx, fy, rot, tran, near, thresh);

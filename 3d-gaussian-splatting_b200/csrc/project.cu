@@ -52,13 +52,13 @@ __global__ void __launch_bounds__(kBlock) fused_project_kernel(
     unsigned int* __restrict__ n_visible) {
   int i = blockIdx.x * kBlock + threadIdx.x;
   bool vis = false;
+  uint32_t cnt = 0;
   if (i < n) {
     float p[3] = {pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]};
     float q[4], s[3], raw_s[3], qn;
     load_activated(quat, scale, i, scale_act, q, s, raw_s, qn);
     GsProj o = gs_project(cam, p, q, s, near_plane, half_w, half_h);
     vis = o.visible;
-    uint32_t cnt = 0;
     if (mask) mask[i] = o.visible ? 1 : 0;
     if (o.visible) {
       uint32_t tx0, tx1, ty0, ty1;
@@ -85,8 +85,22 @@ __global__ void __launch_bounds__(kBlock) fused_project_kernel(
     // depth sort key: positive float bits order like the floats; Gaussians without instances last
     dkey[i] = cnt ? __float_as_uint(o.depth) : 0xffffffffu;
   }
+  // 64-bit instance total next to the visible count (counters[2..3]): the u32 scans that follow
+  // would wrap silently for M >= 2^32 (e.g. diverged scales: every Gaussian on every tile); the
+  // host sizes the frame from this total and refuses instead
+  __shared__ unsigned long long wsum[kBlock / 32];
+  unsigned long long c64 = cnt;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) c64 += __shfl_xor_sync(0xffffffffu, c64, o);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c64;
   int nv = __syncthreads_count(vis);
-  if (threadIdx.x == 0 && nv) atomicAdd(n_visible, (unsigned int)nv);
+  if (threadIdx.x == 0) {
+    unsigned long long tot = 0;
+#pragma unroll
+    for (int w = 0; w < kBlock / 32; ++w) tot += wsum[w];
+    if (nv) atomicAdd(n_visible, (unsigned int)nv);
+    if (tot) atomicAdd(reinterpret_cast<unsigned long long*>(n_visible + 2), tot);
+  }
 }
 
 // Segment-sums the per-instance gradient records of each Gaussian (its instances occupy the

@@ -135,6 +135,19 @@ extern "C" void gs_ctx_destroy(gs_ctx* c) {
   delete c;
 }
 
+// a ctx owns buffers on the device that was current at gs_ctx_create; using it under another
+// current device would launch on the wrong GPU
+static int gs_check_device(int want, const char* who) {
+  int dev = -1;
+  GS_CUDA_TRY(cudaGetDevice(&dev));
+  if (dev != want) {
+    char msg[160];
+    snprintf(msg, sizeof(msg), "%s: ctx belongs to device %d but device %d is current", who, want, dev);
+    return gs_set_error_msg(GS_ERR_INVALID_ARG, msg);
+  }
+  return 0;
+}
+
 static int ceil_log2(unsigned v) {
   int b = 0;
   while ((1u << b) < v) ++b;
@@ -149,6 +162,11 @@ static int render_forward_impl(gs_ctx* c, const float* pos, const float* rgb, co
     return gs_set_error_msg(GS_ERR_UNSUPPORTED, "gs_render_forward: colour width must be 3 (RGB), 27 (SH deg 2) or 48 (SH deg 3)");
   if (cam->width <= 0 || cam->height <= 0 || !(cam->focal_x > 0.f) || !(cam->focal_y > 0.f))
     return gs_set_error_msg(GS_ERR_INVALID_ARG, "gs_render_forward: bad camera");
+  if (!(cam->tile_thresh > 0.f && cam->tile_thresh < 1.f))
+    return gs_set_error_msg(GS_ERR_INVALID_ARG, "gs_render_forward: tile_thresh must be in (0, 1)");
+  if (!image || (n > 0 && (!pos || !rgb || !opa || !quat || !scale)))
+    return gs_set_error_msg(GS_ERR_INVALID_ARG, "gs_render_forward: null tensor pointer");
+  if (int rc = gs_check_device(c->device, "gs_render_forward")) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   c->have_forward = false;
 
@@ -257,7 +275,7 @@ static int render_forward_impl(gs_ctx* c, const float* pos, const float* rgb, co
   // its read-back is enqueued BEFORE the depth sort and the host waits on an event recorded there -
   // the GPU keeps sorting while the host wakes up and enqueues the rest of the frame (no bubble)
   *c->host_m = 0;
-  GS_CUDA_TRY(cudaMemcpyAsync(c->host_m, c->offsets_g.as<uint32_t>() + N, 4, cudaMemcpyDeviceToHost, st));
+  GS_CUDA_TRY(cudaMemcpyAsync(c->host_m, c->counters.as<unsigned int>() + 2, 8, cudaMemcpyDeviceToHost, st));
   GS_CUDA_TRY(cudaEventRecord(c->ev_m, st));
   if (n > 0)
     GS_CUDA_TRY(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp_bytes, c->dkey_in.as<uint32_t>(),
@@ -265,8 +283,11 @@ static int render_forward_impl(gs_ctx* c, const float* pos, const float* rgb, co
                                                 c->perm.as<uint32_t>(), n, 0, 32, st));
   GS_CUDA_TRY(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp2, cnt_it, c->offsets.as<uint32_t>(), n + 1, st));
   GS_CUDA_TRY(cudaEventSynchronize(c->ev_m));
-  long long m = (long long)(*c->host_m & 0xffffffffull);
-  if (m >= (1ll << 31)) return gs_set_error_msg(GS_ERR_UNSUPPORTED, "gs_render_forward: more than 2^31 tile instances");
+  // 64-bit total accumulated by the projection kernel (== offsets_g[N] whenever the u32 scans did
+  // not wrap); instance indices are 32-bit from here on
+  if (*c->host_m >= (1ull << 31))
+    return gs_set_error_msg(GS_ERR_UNSUPPORTED, "gs_render_forward: more than 2^31 tile instances");
+  long long m = (long long)*c->host_m;
   size_t M = (size_t)m;
 
   gs_mark(c, 2, st);
@@ -373,6 +394,10 @@ static int render_backward_impl(gs_ctx* c, const float* pos, const float* rgb, c
                                 float* grad_scale, gs_stream_t stream) {
   if (!c) return gs_set_error_msg(GS_ERR_INVALID_ARG, "gs_render_backward: null ctx");
   if (!c->have_forward) return gs_set_error_msg(GS_ERR_NO_FORWARD, "gs_render_backward: no forward on this ctx");
+  if (!image || !grad_image || !grad_pos || !grad_rgb || !grad_opa || !grad_quat || !grad_scale ||
+      (c->n > 0 && (!pos || !rgb || !opa || !quat || !scale)))
+    return gs_set_error_msg(GS_ERR_INVALID_ARG, "gs_render_backward: null tensor pointer");
+  if (int rc = gs_check_device(c->device, "gs_render_backward")) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   size_t M = (size_t)c->m;
   const int d = c->d;
@@ -491,7 +516,10 @@ extern "C" int gs_render_forward_backward_host(gs_ctx* c, const float* pos, cons
                                                const float* grad_image_host, float* image_host, float* grad_pos,
                                                float* grad_rgb, float* grad_opa, float* grad_quat, float* grad_scale,
                                                gs_stream_t stream) {
-  if (!c || !cam) return gs_set_error_msg(GS_ERR_INVALID_ARG, "gs_render_forward_backward_host: null argument");
+  if (!c || !cam || !grad_image_host || !image_host)
+    return gs_set_error_msg(GS_ERR_INVALID_ARG, "gs_render_forward_backward_host: null argument");
+  if (cam->width <= 0 || cam->height <= 0)
+    return gs_set_error_msg(GS_ERR_INVALID_ARG, "gs_render_forward_backward_host: bad camera");
   cudaStream_t st = (cudaStream_t)stream;
   int wp = (cam->width + GS_TILE - 1) / GS_TILE * GS_TILE, hp = (cam->height + GS_TILE - 1) / GS_TILE * GS_TILE;
   size_t img_bytes = (size_t)wp * hp * 3 * sizeof(float);

@@ -319,6 +319,32 @@ def test_exp_scale_activation_and_extreme_gaussians(gs, cuda):
     assert rel_err(sp2.gaussian_3ds.scale.grad, ograds2["scale"]) < GRAD_RTOL
 
 
+def test_instance_count_overflow_is_refused(gs, cuda):
+    """Diverged scales (every Gaussian on every tile) make M = N*T exceed the 32-bit instance index:
+    2^31 <= M < 2^32, and M >= 2^32 where a u32 scan would wrap to a small, plausible value.  Both
+    must raise (the reference silently truncates at N/20 per tile) and leave the context usable."""
+    w, h = 1920, 1080                                          # T = 8160
+    for n in (300_000, 600_000):                               # M = 2.4e9 (>2^31), 4.9e9 (>2^32)
+        g = {"pos": torch.zeros(n, 3), "rgb": torch.zeros(n, 3), "opa": torch.zeros(n),
+             "quat": torch.tensor([[1.0, 0.0, 0.0, 0.0]]).repeat(n, 1), "scale": torch.full((n, 3), 30.0)}
+        v = S.make_view(w, h, 0)
+        sp = _splatter(g, [v], cuda)
+        with pytest.raises(RuntimeError, match="2\\^31 tile instances"):
+            with torch.no_grad():
+                sp(0)
+    small, vs, _ = scene(500, 64, 48)
+    sp = _splatter(small, [vs], cuda)
+    assert bool(torch.isfinite(sp(0)).all())
+
+
+def test_bad_arguments_are_refused(gs, cuda):
+    g, v, cam = scene(100, 64, 48)
+    for thresh in (0.0, 1.0, -1.0):
+        sp = _splatter(g, [v], cuda, tile_culling_prob_thresh=thresh)
+        with pytest.raises(RuntimeError, match="tile_thresh"):
+            sp(0)
+
+
 def test_stale_forward_is_refused(gs, cuda):
     """One RenderContext holds one frame: differentiating an older frame after another forward
     must raise instead of silently using the wrong intermediate state."""
