@@ -299,6 +299,19 @@ struct RenderContext {
     return {g_pos, g_rgb, g_opa, g_quat, g_scale};
   }
 
+  // data-parallel gradient push (gs_grad_push): pointers as integers (symmetric-memory mappings)
+  void set_grad_push(int64_t bucket_ptr, std::vector<int64_t> staging_ptrs, int64_t per, int rank) {
+    gs_grad_push p{};
+    p.world = (int)staging_ptrs.size();
+    TORCH_CHECK(p.world <= GS_MAX_PEERS, "set_grad_push: at most ", GS_MAX_PEERS, " ranks");
+    p.rank = rank;
+    p.per = per;
+    p.bucket = reinterpret_cast<float*>(static_cast<uintptr_t>(bucket_ptr));
+    for (int k = 0; k < p.world; ++k) p.staging[k] = reinterpret_cast<float*>(static_cast<uintptr_t>(staging_ptrs[k]));
+    check_rc(gs_ctx_set_grad_push(ctx, &p), "gs_ctx_set_grad_push");
+  }
+  void clear_grad_push() { check_rc(gs_ctx_set_grad_push(ctx, nullptr), "gs_ctx_set_grad_push"); }
+
   void set_timing(bool on) { check_rc(gs_ctx_set_timing(ctx, on ? 1 : 0), "gs_ctx_set_timing"); }
   std::vector<float> stage_ms() {
     std::vector<float> v(GS_N_STAGES, -1.f);
@@ -437,6 +450,17 @@ void allreduce_p2p(std::vector<int64_t> peer_ptrs, int64_t n_floats, int rank, i
   check_rc(gs_allreduce_p2p_f32(ptrs.data(), n_floats, rank, world, cur_stream()), "gs_allreduce_p2p_f32");
 }
 
+void allreduce_push_finish(std::vector<int64_t> bucket_ptrs, int64_t staging_local, int64_t n_floats, int64_t per,
+                           int rank, int world, int device) {
+  c10::cuda::CUDAGuard guard(c10::Device(c10::kCUDA, (c10::DeviceIndex)device));
+  TORCH_CHECK((int)bucket_ptrs.size() == world, "allreduce_push_finish: need one bucket pointer per rank");
+  std::vector<void*> ptrs;
+  for (int64_t p : bucket_ptrs) ptrs.push_back(reinterpret_cast<void*>(static_cast<uintptr_t>(p)));
+  check_rc(gs_allreduce_push_finish_f32(ptrs.data(), reinterpret_cast<const float*>(static_cast<uintptr_t>(staging_local)),
+                                        n_floats, per, rank, world, cur_stream()),
+           "gs_allreduce_push_finish_f32");
+}
+
 }  // namespace gsb200
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
@@ -486,8 +510,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def("last_instances", &RenderContext::last_instances)
       .def("stats", &RenderContext::stats)
       .def("set_timing", &RenderContext::set_timing)
+      .def("set_grad_push", &RenderContext::set_grad_push)
+      .def("clear_grad_push", &RenderContext::clear_grad_push)
       .def("stage_ms", &RenderContext::stage_ms)
       .def("sorted_instances", &RenderContext::sorted_instances);
+  m.def("allreduce_push_finish", &allreduce_push_finish, "second half of the pushed gradient exchange");
   m.def("allreduce_p2p", &allreduce_p2p, "peer-to-peer two-shot in-place all-reduce of a symmetric buffer");
   m.def("allreduce_multimem", &allreduce_multimem, "NVLS multimem in-place all-reduce of a symmetric buffer");
   m.def("adam_step", &adam_step, "fused Adam over flat parameter / gradient buffers (CUDA)");

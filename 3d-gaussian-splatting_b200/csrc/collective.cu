@@ -70,6 +70,32 @@ __global__ void __launch_bounds__(512) p2p_allreduce_kernel(GsPeers peers, long 
   }
 }
 
+// Second half of the pushed exchange (gs_grad_push): the owner of a slice sums its own bucket
+// slice with the W-1 contributions its peers stored into its staging slots during THEIR projection
+// backward (local HBM reads only) and stores the sum into all W buckets over NVLink.
+template <int W>
+__global__ void __launch_bounds__(512) push_finish_kernel(GsPeers buckets, const float4* __restrict__ own,
+                                                          const float4* __restrict__ staging, long long per4,
+                                                          int rank, long long begin4, long long end4) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = begin4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < end4; i += stride) {
+    const long long j = i - begin4;
+    float4 v[W];
+#pragma unroll
+    for (int p = 0; p < W; ++p) v[p] = p == rank ? own[i] : ld_sys(staging + p * per4 + j);
+    float4 acc = v[0];
+#pragma unroll
+    for (int p = 1; p < W; ++p) {
+      acc.x += v[p].x;
+      acc.y += v[p].y;
+      acc.z += v[p].z;
+      acc.w += v[p].w;
+    }
+#pragma unroll
+    for (int p = 0; p < W; ++p) st_sys(buckets.p[p] + i, acc);
+  }
+}
+
 int nvls_max_grid() {
   static const int g = [] {
     const char* e = getenv("GS_NVLS_GRID");          // tuning knob (CTAs), default 4 per SM
@@ -102,6 +128,33 @@ extern "C" int gs_allreduce_p2p_f32(void* const* peer_ptrs, long long n_floats, 
   if (world == 2) p2p_allreduce_kernel<2><<<grid, 512, 0, st>>>(peers, begin4, end4);
   else if (world == 4) p2p_allreduce_kernel<4><<<grid, 512, 0, st>>>(peers, begin4, end4);
   else p2p_allreduce_kernel<8><<<grid, 512, 0, st>>>(peers, begin4, end4);
+  GS_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gs_allreduce_push_finish_f32(void* const* peer_buckets, const float* staging_local, long long n_floats,
+                                            long long per, int rank, int world, gs_stream_t stream) {
+  if (!peer_buckets || !staging_local || n_floats < 0 || (n_floats % 4) || per <= 0 || (per % 4) || rank < 0 ||
+      rank >= world || !(world == 2 || world == 4 || world == 8) || per * world < n_floats ||
+      reinterpret_cast<uintptr_t>(staging_local) % 16)
+    return gs_set_error_msg(GS_ERR_INVALID_ARG, "gs_allreduce_push_finish_f32: bad arguments");
+  GsPeers peers{};
+  for (int p = 0; p < world; ++p) {
+    if (!peer_buckets[p] || reinterpret_cast<uintptr_t>(peer_buckets[p]) % 16)
+      return gs_set_error_msg(GS_ERR_INVALID_ARG, "gs_allreduce_push_finish_f32: bucket pointers must be 16-byte aligned");
+    peers.p[p] = static_cast<float4*>(peer_buckets[p]);
+  }
+  const long long n4 = n_floats / 4, per4 = per / 4;
+  const long long begin4 = per4 * rank;
+  const long long end4 = begin4 + per4 < n4 ? begin4 + per4 : n4;
+  if (end4 <= begin4) return 0;
+  int grid = (int)((end4 - begin4 + 511) / 512);
+  if (grid > nvls_max_grid()) grid = nvls_max_grid();
+  cudaStream_t st = (cudaStream_t)stream;
+  const float4* sg = reinterpret_cast<const float4*>(staging_local);
+  if (world == 2) push_finish_kernel<2><<<grid, 512, 0, st>>>(peers, peers.p[rank], sg, per4, rank, begin4, end4);
+  else if (world == 4) push_finish_kernel<4><<<grid, 512, 0, st>>>(peers, peers.p[rank], sg, per4, rank, begin4, end4);
+  else push_finish_kernel<8><<<grid, 512, 0, st>>>(peers, peers.p[rank], sg, per4, rank, begin4, end4);
   GS_CUDA_TRY(cudaGetLastError());
   return 0;
 }

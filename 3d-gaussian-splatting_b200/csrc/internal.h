@@ -46,12 +46,20 @@ cudaError_t gs_launch_fused_project(const float* pos, const float* rgb, const fl
                                     GsRec* rec, uint32_t* count, uint32_t* dkey, int64_t* mask,
                                     unsigned int* n_visible, cudaStream_t st);
 
+// Data-parallel gradient push (device view of gs_grad_push): world == 0 disables it.
+struct GsGradPush {
+  float* bucket;                  // this rank's flat gradient bucket (the five grad pointers lie inside)
+  float* staging[GS_MAX_PEERS];   // staging[p] = rank p's staging buffer [world][per] as mapped here
+  uint32_t per;                   // floats per slice (multiple of 4)
+  int rank, world;
+};
+
 cudaError_t gs_launch_fused_project_bwd(const float* pos, const float* rgb, const float* opa, const float* quat,
                                         const float* scale, int n, int d, int scale_act, const GsCam& cam,
                                         float near_plane, float half_w, float half_h, const uint32_t* offsets_g,
                                         const uint32_t* count, const float* grad_inst, const uint32_t* row_epoch, uint32_t epoch,
                                         float* g_pos, float* g_rgb, float* g_opa,
-                                        float* g_quat, float* g_scale, cudaStream_t st);
+                                        float* g_quat, float* g_scale, const GsGradPush& push, cudaStream_t st);
 
 // ---- binning.cu ------------------------------------------------------------------------
 cudaError_t gs_launch_emit_keys(const GsRec* rec, const uint32_t* perm, const uint32_t* offsets_sorted, int n, int ntx,

@@ -107,14 +107,47 @@ __global__ void __launch_bounds__(kBlock) fused_project_kernel(
 // contiguous rows offsets_g[i] .. + count[i]) and chains them to the RAW parameters.  No
 // atomics anywhere: the result is deterministic.  Row layout (GW floats): d/d{x, y, ca, cb, cc,
 // l2o} then D colour gradients (activated RGB for D == 3, raw SH coefficients otherwise).
-template <int D, int GW>
+// Destination of a run of `cnt` consecutive gradient floats that would land at `local` in this
+// rank's flat bucket.  W == 0: the bucket itself.  W > 0 (data-parallel push): the
+// bucket is cut into W slices of `per` floats owned by rank 0..W-1; floats of another rank's slice
+// are stored straight into slot `rank` of that owner's staging buffer over NVLink, so the reduce
+// half of the gradient exchange overlaps this kernel.  Returns nullptr when the run straddles two
+// slices (the caller then stores element by element).
+template <int W>
+__device__ __forceinline__ float* push_dst(const GsGradPush& P, float* local, int cnt) {
+  if (W == 0) return local;
+  const uint32_t idx = (uint32_t)(local - P.bucket);
+  const uint32_t owner = idx / P.per;
+  if (cnt > 1 && (idx + (uint32_t)cnt - 1) / P.per != owner) return nullptr;
+  if (owner == (uint32_t)P.rank) return local;
+  float* st = P.staging[0];
+#pragma unroll
+  for (int p = 1; p < (W > 0 ? W : 1); ++p)
+    if (owner == (uint32_t)p) st = P.staging[p];
+  return st + (size_t)P.rank * P.per + (idx - owner * P.per);
+}
+
+template <int W, int CNT>
+__device__ __forceinline__ void push_store(const GsGradPush& P, float* local, const float* v) {
+  float* dst = push_dst<W>(P, local, CNT);
+  if (dst) {
+#pragma unroll
+    for (int k = 0; k < CNT; ++k) dst[k] = v[k];
+  } else {
+#pragma unroll
+    for (int k = 0; k < CNT; ++k) *push_dst<W>(P, local + k, 1) = v[k];
+  }
+}
+
+template <int D, int GW, int W>
 __global__ void __launch_bounds__(kBlock) fused_project_bwd_kernel(
     const float* __restrict__ pos, const float* __restrict__ rgb, const float* __restrict__ opa,
     const float* __restrict__ quat, const float* __restrict__ scale, int n, int scale_act, GsCam cam,
     float near_plane, float half_w, float half_h, const uint32_t* __restrict__ offsets_g,
     const uint32_t* __restrict__ count, const float* __restrict__ grad_inst,
     const uint32_t* __restrict__ row_epoch, uint32_t epoch, float* __restrict__ g_pos,
-    float* __restrict__ g_rgb, float* __restrict__ g_opa, float* __restrict__ g_quat, float* __restrict__ g_scale) {
+    float* __restrict__ g_rgb, float* __restrict__ g_opa, float* __restrict__ g_quat, float* __restrict__ g_scale,
+    GsGradPush push) {
   int i = blockIdx.x * kBlock + threadIdx.x;
   if (i >= n) return;
   float gp[3] = {0.f, 0.f, 0.f}, gq_raw[4] = {0.f, 0.f, 0.f, 0.f}, gs_raw[3] = {0.f, 0.f, 0.f};
@@ -185,15 +218,26 @@ __global__ void __launch_bounds__(kBlock) fused_project_bwd_kernel(
       }
     }
   }
+  if (W == 0) {
 #pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    g_pos[3 * i + k] = gp[k];
-    g_scale[3 * i + k] = gs_raw[k];
+    for (int k = 0; k < 3; ++k) {
+      g_pos[3 * i + k] = gp[k];
+      g_scale[3 * i + k] = gs_raw[k];
+    }
+#pragma unroll
+    for (int k = 0; k < D; ++k) g_rgb[(size_t)i * D + k] = acc[6 + k];
+    reinterpret_cast<float4*>(g_quat)[i] = make_float4(gq_raw[0], gq_raw[1], gq_raw[2], gq_raw[3]);
+    g_opa[i] = go;
+  } else {
+    push_store<W, 3>(push, g_pos + 3 * (size_t)i, gp);
+    push_store<W, 3>(push, g_scale + 3 * (size_t)i, gs_raw);
+    push_store<W, D>(push, g_rgb + (size_t)i * D, acc + 6);
+    // a quaternion is 4 floats at a 16-byte aligned bucket offset and `per` is a multiple of 4:
+    // it never straddles two slices
+    *reinterpret_cast<float4*>(push_dst<W>(push, g_quat + 4 * (size_t)i, 1)) =
+        make_float4(gq_raw[0], gq_raw[1], gq_raw[2], gq_raw[3]);
+    push_store<W, 1>(push, g_opa + i, &go);
   }
-#pragma unroll
-  for (int k = 0; k < D; ++k) g_rgb[(size_t)i * D + k] = acc[6 + k];
-  reinterpret_cast<float4*>(g_quat)[i] = make_float4(gq_raw[0], gq_raw[1], gq_raw[2], gq_raw[3]);
-  g_opa[i] = go;
 }
 
 }  // namespace
@@ -351,16 +395,25 @@ cudaError_t gs_launch_fused_project_bwd(const float* pos, const float* rgb, cons
                                         float near_plane, float half_w, float half_h, const uint32_t* offsets_g,
                                         const uint32_t* count, const float* grad_inst, const uint32_t* row_epoch, uint32_t epoch,
                                         float* g_pos, float* g_rgb, float* g_opa,
-                                        float* g_quat, float* g_scale, cudaStream_t st) {
+                                        float* g_quat, float* g_scale, const GsGradPush& push, cudaStream_t st) {
   if (n == 0) return cudaSuccess;
-#define GS_LAUNCH_PBWD(D, GW)                                                                                     \
-  fused_project_bwd_kernel<D, GW><<<grid_for(n), kBlock, 0, st>>>(pos, rgb, opa, quat, scale, n, scale_act, cam,  \
-                                                                  near_plane, half_w, half_h, offsets_g, count,  \
-                                                                  grad_inst, row_epoch, epoch, g_pos, g_rgb, g_opa,   \
-                                                                  g_quat, g_scale)
-  if (d == 3) GS_LAUNCH_PBWD(3, GS_GREC);
-  else if (d == 27) GS_LAUNCH_PBWD(27, 36);
-  else GS_LAUNCH_PBWD(48, 56);
+#define GS_LAUNCH_PBWD(D, GW, W)                                                                                    \
+  fused_project_bwd_kernel<D, GW, W><<<grid_for(n), kBlock, 0, st>>>(pos, rgb, opa, quat, scale, n, scale_act, cam, \
+                                                                     near_plane, half_w, half_h, offsets_g, count, \
+                                                                     grad_inst, row_epoch, epoch, g_pos, g_rgb,    \
+                                                                     g_opa, g_quat, g_scale, push)
+#define GS_LAUNCH_PBWD_W(D, GW)                  \
+  switch (push.world) {                          \
+    case 0: GS_LAUNCH_PBWD(D, GW, 0); break;     \
+    case 2: GS_LAUNCH_PBWD(D, GW, 2); break;     \
+    case 4: GS_LAUNCH_PBWD(D, GW, 4); break;     \
+    case 8: GS_LAUNCH_PBWD(D, GW, 8); break;     \
+    default: return cudaErrorInvalidValue;       \
+  }
+  if (d == 3) { GS_LAUNCH_PBWD_W(3, GS_GREC) }
+  else if (d == 27) { GS_LAUNCH_PBWD_W(27, 36) }
+  else { GS_LAUNCH_PBWD_W(48, 56) }
+#undef GS_LAUNCH_PBWD_W
 #undef GS_LAUNCH_PBWD
   return cudaGetLastError();
 }

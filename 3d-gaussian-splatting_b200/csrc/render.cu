@@ -95,6 +95,8 @@ struct gs_ctx {
   cudaEvent_t ev[GS_N_STAGES + 2] = {};
   bool ev_ok = false;
   bool ev_fwd_valid = false, ev_bwd_valid = false;
+  // data-parallel gradient push (gs_ctx_set_grad_push); world == 0: off
+  GsGradPush push{};
 };
 
 // stage boundaries: event i is recorded BEFORE stage i; stage i lasts ev[i+1]-ev[i]
@@ -432,10 +434,23 @@ static int render_backward_impl(gs_ctx* c, const float* pos, const float* rgb, c
     }
   }
   gs_mark(c, 8, st);
+  if (c->push.world) {
+    // every gradient segment must lie inside the sliced bucket, quaternions on 16-byte offsets
+    const float* lo = c->push.bucket;
+    const float* hi = lo + (size_t)c->push.world * c->push.per;
+    const size_t nn = (size_t)c->n;
+    const float* seg[5] = {grad_pos, grad_rgb, grad_opa, grad_quat, grad_scale};
+    const size_t len[5] = {3 * nn, (size_t)d * nn, nn, 4 * nn, 3 * nn};
+    for (int k = 0; k < 5; ++k)
+      if (seg[k] < lo || seg[k] + len[k] > hi)
+        return gs_set_error_msg(GS_ERR_INVALID_ARG, "gs_render_backward: gradient buffers are not inside the push bucket");
+    if ((grad_quat - lo) % 4)
+      return gs_set_error_msg(GS_ERR_INVALID_ARG, "gs_render_backward: grad_quat must sit on a 16-byte bucket offset");
+  }
   GS_CUDA_TRY(gs_launch_fused_project_bwd(pos, rgb, opa, quat, scale, c->n, d, c->scale_act, c->cam, c->near_plane,
                                           c->half_w, c->half_h, c->offsets_g.as<uint32_t>(), c->count.as<uint32_t>(),
                                           c->grad_inst.as<float>(), c->row_epoch.as<uint32_t>(), c->epoch,
-                                          grad_pos, grad_rgb, grad_opa, grad_quat, grad_scale, st));
+                                          grad_pos, grad_rgb, grad_opa, grad_quat, grad_scale, c->push, st));
   gs_mark(c, 9, st);
   c->ev_bwd_valid = c->timing && c->ev_ok;
   return 0;
@@ -455,6 +470,30 @@ extern "C" int gs_render_backward_final(gs_ctx* c, const float* pos, const float
                                         float* grad_quat, float* grad_scale, gs_stream_t stream) {
   return render_backward_impl(c, pos, rgb, opa, quat, scale, image_raw_padded, grad_final, 1, grad_pos, grad_rgb,
                               grad_opa, grad_quat, grad_scale, stream);
+}
+
+extern "C" int gs_ctx_set_grad_push(gs_ctx* c, const gs_grad_push* p) {
+  if (!c) return gs_set_error_msg(GS_ERR_INVALID_ARG, "gs_ctx_set_grad_push: null ctx");
+  if (!p) {
+    c->push = GsGradPush{};
+    return 0;
+  }
+  if (!(p->world == 2 || p->world == 4 || p->world == 8) || p->rank < 0 || p->rank >= p->world || p->per <= 0 ||
+      (p->per % 4) || (unsigned long long)p->per * (unsigned)p->world >= (1ull << 32) || !p->bucket ||
+      reinterpret_cast<uintptr_t>(p->bucket) % 16)
+    return gs_set_error_msg(GS_ERR_INVALID_ARG, "gs_ctx_set_grad_push: bad configuration");
+  GsGradPush g{};
+  g.bucket = p->bucket;
+  g.per = (uint32_t)p->per;
+  g.rank = p->rank;
+  g.world = p->world;
+  for (int k = 0; k < p->world; ++k) {
+    if (!p->staging[k] || reinterpret_cast<uintptr_t>(p->staging[k]) % 16)
+      return gs_set_error_msg(GS_ERR_INVALID_ARG, "gs_ctx_set_grad_push: staging pointers must be 16-byte aligned");
+    g.staging[k] = p->staging[k];
+  }
+  c->push = g;
+  return 0;
 }
 
 extern "C" long long gs_frame_instances(gs_ctx* c) { return (c && c->have_forward) ? c->m : -1; }

@@ -81,12 +81,20 @@ class SymmetricGradBucket:
                        sizes per direction - the least for W >= 4.
       mode "p2p":      system-scope loads of the slice from every peer, stores of the sum to every
                        peer; moves 2 (W-1)/W bucket sizes per direction - the least for W = 2.
-      mode "auto":     p2p for W = 2, multimem otherwise (p2p if there is no multicast mapping).
+      mode "push":     the exchange starts INSIDE the backward: `fused_project_bwd_kernel` stores every
+                       gradient float that belongs to another rank's slice straight into that owner's
+                       staging slot over NVLink (gs_grad_push), so the reduce half overlaps the
+                       kernel; after the barrier the owner sums its slice with W-1 local staging
+                       slots and stores the sum to every bucket (gs_allreduce_push_finish_f32).
+                       (W-1)/W bucket sizes per direction hidden under the backward + the same
+                       again exposed.  The bucket is only complete after `allreduce()`.
+      mode "auto":     push for W = 2, multimem otherwise (p2p if there is no multicast mapping).
 
     Measured on B200 for the 134 MB bucket of 2.4 M Gaussians (profiles/r1_exchange.md), exchange
     alone: W = 2: p2p 0.214 ms, multimem 0.357, NCCL 0.292; W = 8: multimem 0.330, p2p 0.394,
-    NCCL 0.394.  Inside the training step only the W = 2 gain survives (rank skew dominates at
-    W >= 4), which is why `make_grad_bucket("auto")` picks this class for W = 2 only.
+    NCCL 0.394.  Whole step at W = 2: push 2.30 ms, p2p 2.40, NCCL 2.50 (one GPU: 2.16).
+    `make_grad_bucket("auto")` picks push for W = 2 (validated against NCCL on 2 GPUs) and keeps
+    NCCL for W >= 4, where push measured 2.35 ms vs 2.56 at W = 4 but is not yet parity-tested.
 
     `allocator` must be installed with `renderer.set_flat_grad_allocator` (make_grad_bucket does
     it).  A change of the bucket size (densification changes N on every rank at the same step)
@@ -102,10 +110,13 @@ class SymmetricGradBucket:
         self.group = group if group is not None else dist.group.WORLD
         self.world = dist.get_world_size(self.group)
         self.rank = dist.get_rank(self.group)
-        assert mode in ("auto", "multimem", "p2p")
+        assert mode in ("auto", "multimem", "p2p", "push")
         self.mode = mode
         self.buf = None
         self.hdl = None
+        self.staging = None
+        self.staging_hdl = None
+        self.per = 0
         self._probe()
 
     def _alloc(self, numel, device):
@@ -120,7 +131,11 @@ class SymmetricGradBucket:
         buf, hdl = self._alloc(1024, dev)
         has_mc = bool(getattr(hdl, "multicast_ptr", 0))
         p2p_ok = self.world in (2, 4, 8)
+        push = self.mode == "push"
+        if push:
+            self.mode = "p2p"                  # the self-check below runs the plain p2p kernel
         if self.mode == "auto":
+            push = self.world == 2
             self.mode = "p2p" if (self.world == 2 or not has_mc) else "multimem"
         if self.mode == "multimem" and not has_mc:
             raise RuntimeError("symmetric memory has no multicast mapping (NVLS unavailable)")
@@ -131,10 +146,16 @@ class SymmetricGradBucket:
         want = self.world * (self.world + 1) / 2
         if not bool((buf == want).all()):
             raise RuntimeError("peer-memory all-reduce self-check failed")
+        if push:
+            self.mode = "push"
 
     def _reduce(self, buf, hdl, numel):
-        hdl.barrier(channel=0)                  # every rank's bucket is written
-        if self.mode == "multimem":
+        hdl.barrier(channel=0)                  # every rank's bucket is written (push: and every pushed slice)
+        if self.mode == "push":
+            self._gaussian.allreduce_push_finish([int(p) for p in hdl.buffer_ptrs], int(self.staging.data_ptr()),
+                                                 int(numel), int(self.per), self.rank, self.world,
+                                                 buf.device.index)
+        elif self.mode == "multimem":
             self._gaussian.allreduce_multimem(int(hdl.multicast_ptr), int(numel), self.rank, self.world,
                                               buf.device.index)
         else:
@@ -146,6 +167,14 @@ class SymmetricGradBucket:
         numel = (numel + 3) // 4 * 4
         if self.buf is None or self.buf.numel() != numel or self.buf.device != device:
             self.buf, self.hdl = self._alloc(numel, device)
+            if self.mode == "push":
+                self.per = (numel // 4 + self.world - 1) // self.world * 4
+                self.staging, self.staging_hdl = self._alloc(self.world * self.per, device)
+                self.staging.zero_()                    # pad floats are never pushed: keep them finite
+                self.hdl.barrier(channel=0)             # nobody pushes into a buffer that is still being zeroed
+        if self.mode == "push":
+            return self.buf, (int(self.buf.data_ptr()), [int(p) for p in self.staging_hdl.buffer_ptrs], int(self.per),
+                              self.rank)
         return self.buf
 
     def nbytes(self) -> int:
@@ -168,14 +197,14 @@ class SymmetricGradBucket:
 
 def make_grad_bucket(params: Sequence[torch.Tensor], average: bool = False, group=None, exchange: str = "auto"):
     """The gradient exchange for `params`: `exchange` (env GS_DP_EXCHANGE overrides) is
-    "nccl" (portable `GradBucket`), "multimem" / "p2p" (required `SymmetricGradBucket` mode) or
-    "auto": a p2p `SymmetricGradBucket` (installed as the backward's bucket allocator) when the
-    group is NCCL with world == 2 on CUDA and symmetric memory works - the one case where it
-    measurably beats NCCL inside the step - else `GradBucket`."""
+    "nccl" (portable `GradBucket`), "multimem" / "p2p" / "push" (required `SymmetricGradBucket` mode) or
+    "auto": a push-mode `SymmetricGradBucket` (installed as the backward's bucket allocator) when
+    the group is NCCL with world == 2 on CUDA and symmetric memory works - the configuration
+    validated against NCCL - else `GradBucket`."""
     import os
     import sys
     exchange = os.environ.get("GS_DP_EXCHANGE", exchange)
-    assert exchange in ("auto", "nccl", "multimem", "p2p"), exchange
+    assert exchange in ("auto", "nccl", "multimem", "p2p", "push"), exchange
     params = list(params)
     usable = (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
               and len(params) > 0 and params[0].is_cuda and dist.get_backend(group) == "nccl")
@@ -191,7 +220,7 @@ def make_grad_bucket(params: Sequence[torch.Tensor], average: bool = False, grou
             if exchange != "auto":
                 raise
             print(f"[dp] peer-memory gradient exchange unavailable ({e}); using NCCL all-reduce", file=sys.stderr)
-    elif exchange in ("multimem", "p2p") and dist.is_initialized() and dist.get_world_size(group) > 1:
+    elif exchange in ("multimem", "p2p", "push") and dist.is_initialized() and dist.get_world_size(group) > 1:
         raise RuntimeError("peer-memory gradient exchange needs an initialised NCCL group on CUDA")
     return GradBucket(params, average=average, group=group)
 

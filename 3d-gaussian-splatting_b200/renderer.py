@@ -143,7 +143,8 @@ _flat_grad_allocator = None
 
 
 def set_flat_grad_allocator(fn):
-    """Install `fn(numel, device) -> 1-D fp32 tensor (16-byte aligned)` as the source of the flat
+    """Install `fn(numel, device) -> 1-D fp32 tensor (16-byte aligned)` (or `(tensor, push)` with
+    push = (bucket_ptr, staging_ptrs, per, rank) for `RenderContext.set_grad_push`) as the source of the flat
     gradient bucket the fused backward writes into (None restores torch.empty).  Data-parallel
     runs use it to place the bucket in symmetric memory so the gradient exchange runs in place over
     NVLink (dp.NvlsGradBucket): the backward kernel's stores ARE the collective's send buffer."""
@@ -160,8 +161,11 @@ def _flat_grads(tensors):
     for n in sizes:
         starts.append(o)
         o += (n + 3) // 4 * 4
+    push = None
     if _flat_grad_allocator is not None:
         flat = _flat_grad_allocator(o, tensors[0].device)
+        if isinstance(flat, tuple):                      # (bucket, push configuration) - see dp.py
+            flat, push = flat
         assert flat.numel() >= o and flat.dtype == torch.float32 and flat.data_ptr() % 16 == 0
     else:
         flat = torch.empty(o, device=tensors[0].device, dtype=torch.float32)
@@ -170,7 +174,16 @@ def _flat_grads(tensors):
         outs.append(flat[b:b + n].view(t.shape))
         if n % 4:
             flat[b + n:b + (n + 3) // 4 * 4].zero_()     # keep the (<= 3 float) pads finite
-    return outs
+    return outs, push
+
+
+def _apply_push(rctx, push):
+    """Route this backward's gradient stores: plain bucket, or (data-parallel push) other ranks'
+    slices straight into their owners' staging buffers over NVLink (gs_grad_push)."""
+    if push is None:
+        rctx.clear_grad_push()
+    else:
+        rctx.set_grad_push(*push)
 
 
 class _RenderFrame(torch.autograd.Function):
@@ -196,7 +209,8 @@ class _RenderFrame(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_image, _grad_mask):
         pos, rgb, opa, quat, scale, image = ctx.saved_tensors
-        outs = _flat_grads((pos, rgb, opa, quat, scale))
+        outs, push = _flat_grads((pos, rgb, opa, quat, scale))
+        _apply_push(ctx.rctx, push)
         ctx.rctx.backward_into(pos, rgb, opa, quat, scale, image, _f32(grad_image), *outs, ctx.frame)
         return (None, outs[0], outs[1], outs[2], outs[3], outs[4]) + (None,) * 9
 
@@ -225,7 +239,8 @@ class _RenderFrameFinal(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_final, _grad_mask):
         pos, rgb, opa, quat, scale, raw = ctx.saved_tensors
-        outs = _flat_grads((pos, rgb, opa, quat, scale))
+        outs, push = _flat_grads((pos, rgb, opa, quat, scale))
+        _apply_push(ctx.rctx, push)
         ctx.rctx.backward_final_into(pos, rgb, opa, quat, scale, raw, _f32(grad_final), *outs, ctx.frame)
         return (None, outs[0], outs[1], outs[2], outs[3], outs[4]) + (None,) * 9
 

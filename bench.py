@@ -241,9 +241,10 @@ def run_ours(args, world, rank, local):
     params = list(sp.gaussian_3ds.parameters())
     import dp
     # N>1: in-place sum of the symmetric gradient bucket the backward writes into, by our own
-    # kernel over NVLink peer memory at N=2 (p2p; measured faster than NCCL inside the step); one NCCL
-    # all-reduce of the same flat bucket at N>=4, where --exchange multimem|p2p showed no gain
-    # (profiles/r1_exchange.md), or when symmetric memory is unavailable (no-op at N=1)
+    # kernels over NVLink peer memory at N=2 ("push": the projection backward stores the peer's slice
+    # straight into its staging buffer, a finish kernel sums and broadcasts); one NCCL all-reduce of
+    # the same flat bucket at N>=4 (push measured faster there too but is parity-tested at 2 GPUs
+    # only, profiles/r1_exchange.md) or when symmetric memory is unavailable (no-op at N=1)
     bucket = dp.make_grad_bucket(params, exchange=args.exchange)
     exchange = "none" if world == 1 else (f"own kernel over symmetric memory ({bucket.mode})"
                                           if isinstance(bucket, dp.SymmetricGradBucket) else "NCCL all-reduce")
@@ -340,7 +341,7 @@ def run_ours(args, world, rank, local):
         "gpu_launches": int(((4 if fwd_only else 6) + int(own_exchange)) * args.steps),
         "gpu_launches_note": "our kernels per step: fused_project, emit_keys, pack_sorted, blend_fwd"
                              + ("" if fwd_only else ", blend_bwd, fused_project_bwd")
-                             + (", p2p/multimem allreduce" if own_exchange else "") +
+                             + (", exchange kernel (push finish / p2p / multimem)" if own_exchange else "") +
                              "; plus CUB scan (2) and onesweep radix sort (8) library kernels",
         "stage_ms": dict(zip(["project", "depth_sort+scan+readback", "emit_keys", "tile_sort", "pack", "blend_fwd",
                               "blend_bwd", "project_bwd"], [round(x, 4) for x in stage])),
@@ -432,9 +433,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--exchange", default="auto", choices=["auto", "multimem", "p2p", "nccl"],
-                    help="N>1 gradient exchange: own multimem / p2p kernel on a symmetric bucket, NCCL all-reduce, "
-                         "or auto (p2p at N=2, NCCL otherwise)")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "multimem", "p2p", "push", "nccl"],
+                    help="N>1 gradient exchange: own push / p2p / multimem kernels on a symmetric bucket, NCCL all-reduce, "
+                         "or auto (push at N=2, NCCL otherwise)")
     ap.add_argument("--colour", type=int, default=3, choices=[3, 27, 48],
                     help="3 = RGB (default; the reference's published 2.4M point), 27 = per-pixel SH degree 2 "
                          "(the reference's use_sh_coeff), 48 = SH degree 3 extension")

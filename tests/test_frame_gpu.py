@@ -500,7 +500,7 @@ def test_fused_flat_adam_matches_torch_adam(gs, cuda):
     oa = optim.FlatAdam([{"params": pa[k], "lr": lrs[k]} for k in order], betas=(0.9, 0.99))
     ob = torch.optim.Adam([{"params": pb[k], "lr": lrs[k]} for k in order], betas=(0.9, 0.99))
     for it in range(6):
-        grads = renderer._flat_grads(tuple(pa[k] for k in ("pos", "rgb", "opa", "quat", "scale")))
+        grads, _ = renderer._flat_grads(tuple(pa[k] for k in ("pos", "rgb", "opa", "quat", "scale")))
         for gv, k in zip(grads, ("pos", "rgb", "opa", "quat", "scale")):
             gv.copy_(torch.randn_like(gv) * (0.1 + it))
             pa[k].grad = gv
