@@ -3,6 +3,7 @@ import os
 import socket
 import sys
 
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -86,3 +87,47 @@ def test_gradient_bucket_allreduce_world2():
     assert all(out[r][0] for r in range(world))
     assert out[0][1] == [0, 2, 4, 6] and out[1][1] == [1, 3, 5, 7]
     assert out[0][2] == (150 + 50 + 200) * 4
+
+
+def test_symmetric_bucket_mode_resolution():
+    """Mode selection of SymmetricGradBucket without GPUs: the symmetric-memory allocation and the
+    exchange kernels are replaced by stand-ins; only the host logic (auto -> push at 2 ranks,
+    multimem/p2p beyond, slice size, allocator contract) runs."""
+    sys.path.insert(0, os.path.join(ROOT, "3d-gaussian-splatting_b200"))
+    import dp
+
+    class Hdl:
+        def __init__(self, t, mc):
+            self.buffer_ptrs = [t.data_ptr(), t.data_ptr() + 1 << 20]
+            self.multicast_ptr = mc
+
+        def barrier(self, channel=0):
+            pass
+
+    def make(world, mode, mc=1234):
+        b = dp.SymmetricGradBucket.__new__(dp.SymmetricGradBucket)
+        b.params = [torch.nn.Parameter(torch.zeros(4))]
+        b.average, b.group, b.world, b.rank = False, None, world, 0
+        b.mode, b.buf, b.hdl, b.staging, b.staging_hdl, b.per = mode, None, None, None, None, 0
+        b._alloc = lambda numel, device: (lambda t: (t, Hdl(t, mc)))(torch.zeros(numel))
+        b._reduce = lambda buf, hdl, numel: buf.fill_(world * (world + 1) / 2)
+        b._probe()
+        return b
+
+    assert make(2, "auto").mode == "push"
+    assert make(4, "auto").mode == "multimem"
+    assert make(8, "auto", mc=0).mode == "p2p"
+    assert make(2, "p2p").mode == "p2p" and make(4, "push").mode == "push"
+    with pytest.raises(RuntimeError):
+        make(4, "multimem", mc=0)
+    with pytest.raises(RuntimeError):
+        make(3, "p2p")
+    b = make(2, "push")
+    out = b.allocator(4 * 10 + 2, torch.device("cpu"))       # rounded up to 44 floats
+    assert isinstance(out, tuple) and out[0].numel() == 44
+    bucket_ptr, staging_ptrs, per, rank = out[1]
+    assert per % 4 == 0 and per * 2 >= 44 and b.staging.numel() == 2 * per and len(staging_ptrs) == 2 and rank == 0
+    assert bool((b.staging == 0).all())
+    assert b.allocator(42, torch.device("cpu"))[0] is out[0]  # persistent across steps
+    p = make(2, "p2p")
+    assert isinstance(p.allocator(40, torch.device("cpu")), torch.Tensor)
