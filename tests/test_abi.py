@@ -75,3 +75,48 @@ def test_product_path_never_touches_the_oracle():
                 if re.search(r"gs_oracle|ref_pipeline|import\s+oracle|from\s+oracle|oracle/", txt):
                     bad.append(os.path.join(root, f))
     assert not bad, bad
+
+
+def test_argument_validation_needs_no_gpu():
+    """Every entry point validates its arguments before touching CUDA: bad calls return
+    GS_ERR_INVALID_ARG (-1) / GS_ERR_UNSUPPORTED (-2) with a message in gs_last_error()."""
+    lib = ctypes.CDLL(os.path.join(PKG, "libgs_b200.so"))
+    lib.gs_last_error.restype = ctypes.c_char_p
+    P, LL, I = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int
+
+    def err():
+        return lib.gs_last_error().decode()
+
+    # gradient exchange kernels
+    lib.gs_allreduce_multimem_f32.argtypes = [P, LL, I, I, P]
+    assert lib.gs_allreduce_multimem_f32(None, 16, 0, 2, None) == -1 and "bad arguments" in err()
+    assert lib.gs_allreduce_multimem_f32(0x1000, 15, 0, 2, None) == -1          # not a multiple of 4 floats
+    assert lib.gs_allreduce_multimem_f32(0x1008, 16, 0, 2, None) == -1 and "16-byte" in err()
+    assert lib.gs_allreduce_multimem_f32(0x1000, 16, 2, 2, None) == -1          # rank out of range
+    ptrs = (P * 3)(0x1000, 0x2000, 0x3000)
+    lib.gs_allreduce_p2p_f32.argtypes = [ctypes.POINTER(P), LL, I, I, P]
+    assert lib.gs_allreduce_p2p_f32(ptrs, 16, 0, 3, None) == -1 and "2, 4 or 8" in err()
+    bad = (P * 2)(0x1000, 0x2004)
+    assert lib.gs_allreduce_p2p_f32(bad, 16, 0, 2, None) == -1 and "16-byte" in err()
+    lib.gs_allreduce_push_finish_f32.argtypes = [ctypes.POINTER(P), P, LL, LL, I, I, P]
+    two = (P * 2)(0x1000, 0x2000)
+    assert lib.gs_allreduce_push_finish_f32(two, 0x3000, 64, 16, 0, 2, None) == -1   # 2 * per < n
+    assert lib.gs_allreduce_push_finish_f32(two, 0x3000, 64, 30, 0, 2, None) == -1   # per not a multiple of 4
+    assert lib.gs_allreduce_push_finish_f32(two, None, 64, 32, 0, 2, None) == -1
+    # contexts / frames
+    lib.gs_ctx_set_grad_push.argtypes = [P, P]
+    assert lib.gs_ctx_set_grad_push(None, None) == -1 and "null ctx" in err()
+    lib.gs_ctx_create.argtypes = [P]
+    assert lib.gs_ctx_create(None) == -1
+    lib.gs_frame_instances.argtypes = [P]
+    lib.gs_frame_instances.restype = LL
+    assert lib.gs_frame_instances(None) == -1
+    lib.gs_render_backward.argtypes = [P] * 14
+    assert lib.gs_render_backward(*([None] * 14)) == -1 and "null ctx" in err()
+    # optimizer
+    lib.gs_adam_step.argtypes = [P, P, P, P, LL, P, P, I, ctypes.c_float, ctypes.c_float, ctypes.c_float, I, P]
+    ends = (LL * 1)(16)
+    lrs = (ctypes.c_float * 1)(1e-3)
+    assert lib.gs_adam_step(0x1000, 0x2000, 0x3000, 0x4000, 16, ends, lrs, 1, 0.9, 0.99, 1e-8, 0, None) == -1  # step 0
+    assert lib.gs_adam_step(0x1000, 0x2000, 0x3000, 0x4000, 15, ends, lrs, 1, 0.9, 0.99, 1e-8, 1, None) == -1  # n % 4
+    assert lib.gs_adam_step(0x1000, 0x2000, 0x3000, 0x4000, 16, ends, lrs, 9, 0.9, 0.99, 1e-8, 1, None) == -1  # > 8 segments
