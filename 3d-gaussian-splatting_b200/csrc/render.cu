@@ -124,6 +124,9 @@ extern "C" int gs_ctx_create(gs_ctx** out) {
 
 extern "C" void gs_ctx_destroy(gs_ctx* c) {
   if (!c) return;
+  // the buffers live on the device that was current at creation, which need not be current now
+  int cur = -1;
+  const bool switched = cudaGetDevice(&cur) == cudaSuccess && cur != c->device && cudaSetDevice(c->device) == cudaSuccess;
   cudaDeviceSynchronize();
   DevBuf* bufs[] = {&c->rec, &c->count, &c->offsets, &c->dkey_in, &c->dkey_out, &c->perm, &c->iota, &c->offsets_g, &c->keys_in, &c->keys_out,
                     &c->vals_in, &c->vals_out, &c->pA, &c->pB, &c->pC, &c->grad_inst, &c->row_epoch, &c->tile_accum, &c->tile_neff,
@@ -134,6 +137,7 @@ extern "C" void gs_ctx_destroy(gs_ctx* c) {
   if (c->ev_m) cudaEventDestroy(c->ev_m);
   if (c->ev_ok)
     for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
+  if (switched) cudaSetDevice(cur);
   delete c;
 }
 
