@@ -413,6 +413,15 @@ struct RenderContext {
              "gs_frame_sorted");
     return {idx, accum};
   }
+
+  // consumed instances per tile [T] int32 of the last forward (M_eff = sum)
+  torch::Tensor tile_consumed() {
+    gs_frame_info fi{};
+    check_rc(gs_frame_stats(ctx, &fi, cur_stream()), "gs_frame_stats");
+    auto out = torch::empty({(int64_t)fi.n_tiles}, torch::TensorOptions().device(torch::kCUDA, device).dtype(at::kInt));
+    check_rc(gs_frame_tile_consumed(ctx, out.data_ptr<int>(), cur_stream()), "gs_frame_tile_consumed");
+    return out;
+  }
 };
 
 // fused Adam over flat buffers; seg_ends / lrs are small host lists
@@ -513,7 +522,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def("set_grad_push", &RenderContext::set_grad_push)
       .def("clear_grad_push", &RenderContext::clear_grad_push)
       .def("stage_ms", &RenderContext::stage_ms)
-      .def("sorted_instances", &RenderContext::sorted_instances);
+      .def("sorted_instances", &RenderContext::sorted_instances)
+      .def("tile_consumed", &RenderContext::tile_consumed);
   m.def("allreduce_push_finish", &allreduce_push_finish, "second half of the pushed gradient exchange");
   m.def("allreduce_p2p", &allreduce_p2p, "peer-to-peer two-shot in-place all-reduce of a symmetric buffer");
   m.def("allreduce_multimem", &allreduce_multimem, "NVLS multimem in-place all-reduce of a symmetric buffer");

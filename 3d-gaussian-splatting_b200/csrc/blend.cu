@@ -441,7 +441,7 @@ __global__ void __launch_bounds__(256) legacy_unpack_grads_kernel(const float* _
   g_pos[3 * i + 1] = v0.y;                                    // z column untouched (gaussian.cu:785-786)
   reinterpret_cast<float4*>(g_cov)[i] = make_float4(v1.x * sc - gsc * kk * cv.w, v0.w * sc + gsc * kk * cv.z,
                                                     v0.w * sc + gsc * kk * cv.y, v0.z * sc - gsc * kk * cv.x);
-  g_opa[i] = v1.y / (opa[i] * GS_LN2);
+  g_opa[i] = opa[i] > 0.f ? v1.y / (opa[i] * GS_LN2) : 0.f;   // opacity exactly 0: alpha == 0 everywhere, log2 undefined
   g_rgb[3 * i] = v1.z;
   g_rgb[3 * i + 1] = v1.w;
   g_rgb[3 * i + 2] = v2.x;
@@ -487,7 +487,7 @@ __global__ void __launch_bounds__(256) legacy_unpack_grads_sh_kernel(const float
   g_pos[3 * i + 1] = row[1];
   reinterpret_cast<float4*>(g_cov)[i] = make_float4(d_cc * sc - gsc * kk * cv.w, d_cb * sc + gsc * kk * cv.z,
                                                     d_cb * sc + gsc * kk * cv.y, d_ca * sc - gsc * kk * cv.x);
-  g_opa[i] = row[5] / (opa[i] * GS_LN2);
+  g_opa[i] = opa[i] > 0.f ? row[5] / (opa[i] * GS_LN2) : 0.f;
   for (int q = 0; q < d; ++q) g_rgb[(size_t)i * d + q] = row[6 + q];
 }
 

@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(512) p2p_allreduce_kernel(GsPeers peers, long 
 // slice with the W-1 contributions its peers stored into its staging slots during THEIR projection
 // backward (local HBM reads only) and stores the sum into all W buckets over NVLink.
 template <int W>
-__global__ void __launch_bounds__(512) push_finish_kernel(GsPeers buckets, const float4* __restrict__ own,
+__global__ void __launch_bounds__(512) push_finish_kernel(GsPeers buckets, const float4* own /* == buckets.p[rank]: no restrict */,
                                                           const float4* __restrict__ staging, long long per4,
                                                           int rank, long long begin4, long long end4) {
   const long long stride = (long long)gridDim.x * blockDim.x;

@@ -553,6 +553,14 @@ extern "C" int gs_frame_sorted(gs_ctx* c, int* gauss_idx, long long capacity, in
   return 0;
 }
 
+extern "C" int gs_frame_tile_consumed(gs_ctx* c, int* tile_consumed, gs_stream_t stream) {
+  if (!c || !tile_consumed) return gs_set_error_msg(GS_ERR_INVALID_ARG, "gs_frame_tile_consumed: null argument");
+  if (!c->have_forward) return gs_set_error_msg(GS_ERR_NO_FORWARD, "gs_frame_tile_consumed: no forward on this ctx");
+  GS_CUDA_TRY(cudaMemcpyAsync(tile_consumed, c->tile_neff.p, sizeof(int) * (size_t)c->geom.n_tiles,
+                              cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return 0;
+}
+
 extern "C" int gs_render_forward_backward_host(gs_ctx* c, const float* pos, const float* rgb, const float* opa,
                                                const float* quat, const float* scale, int n, int d,
                                                int scale_activation, const gs_camera* cam,

@@ -165,6 +165,18 @@ class SymmetricGradBucket:
 
     def allocator(self, numel: int, device) -> torch.Tensor:
         numel = (numel + 3) // 4 * 4
+        # The bucket is ONE persistent buffer and `.grad` tensors are views of it: a second backward
+        # while a `.grad` still aliases it would overwrite that gradient and autograd would then add
+        # the buffer to itself (silently 2 x the last gradient).  Gradient accumulation therefore
+        # needs zero_grad(set_to_none=True) between backwards - refuse anything else.
+        if self.buf is not None:
+            lo, hi = self.buf.data_ptr(), self.buf.data_ptr() + self.buf.numel() * 4
+            for p in self.params:
+                if p.grad is not None and lo <= p.grad.data_ptr() < hi:
+                    raise RuntimeError("SymmetricGradBucket: a parameter's .grad still aliases the symmetric bucket "
+                                       "while a new backward wants to write it; clear gradients with "
+                                       "zero_grad(set_to_none=True) / p.grad = None before every backward "
+                                       "(gradient accumulation over several backwards is not supported in this mode)")
         if self.buf is None or self.buf.numel() != numel or self.buf.device != device:
             self.buf, self.hdl = self._alloc(numel, device)
             if self.mode == "push":

@@ -101,16 +101,18 @@ class Gaussian3ds(nn.Module):
                     lst.append(t.clone())
             if use_split and bool(split_mask.any()):
                 n_split = int(split_mask.sum())
-                if scale_activation == "abs":
-                    scale[split_mask] /= 1.6
-                else:
-                    scale[split_mask] -= math.log(1.6)
+                # the two positions are drawn from the ORIGINAL (un-shrunk) Gaussian: the reference builds
+                # the covariance from self.scale (splatter.py:204-205) and only the stored scale is / 1.6
                 R = quat_to_rotmat(quat[split_mask])
                 s = scale[split_mask].abs() + EPS if scale_activation == "abs" else torch.exp(scale[split_mask])
                 RS = R * s.unsqueeze(-2)
                 cov = RS @ RS.transpose(-1, -2)
                 dist = torch.distributions.MultivariateNormal(pos[split_mask], cov)      # utils.py:391-402
                 p1, p2 = dist.sample(), dist.sample()
+                if scale_activation == "abs":
+                    scale[split_mask] /= 1.6
+                else:
+                    scale[split_mask] -= math.log(1.6)
                 pos[split_mask] = p1
                 for lst, t in zip(new, (p2, rgb[split_mask], opa[split_mask], quat[split_mask], scale[split_mask])):
                     lst.append(t.clone())
@@ -183,7 +185,8 @@ class Splatter(nn.Module):
         to = dict(device=self.device, dtype=torch.float32)
         self.gaussian_3ds = Gaussian3ds(*(params[k].detach().to(**to).contiguous()
                                          for k in ("pos", "rgb", "opa", "quat", "scale")))
-        self._rctx = gaussian.RenderContext()
+        with torch.cuda.device(self.device):                      # the context lives on self.device, not on the current one
+            self._rctx = gaussian.RenderContext()
         self.ground_truth = None
         self.culling_mask = None
         self.n_tile_gaussians = 0

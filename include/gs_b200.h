@@ -189,6 +189,11 @@ int gs_frame_stats(gs_ctx* ctx, gs_frame_info* out_host, gs_stream_t stream);
  * T+1 entries into tile_accum (device int32).  Either pointer may be NULL. */
 int gs_frame_sorted(gs_ctx* ctx, int* gauss_idx, long long capacity, int* tile_accum, gs_stream_t stream);
 
+/* Per-tile consumed instance counts of the last forward (device int32 [T]): tile t's blend stopped
+ * after tile_consumed[t] of its tile_accum[t+1]-tile_accum[t] instances because every pixel had
+ * saturated (M_eff = their sum).  For parity tests / roofline accounting. */
+int gs_frame_tile_consumed(gs_ctx* ctx, int* tile_consumed, gs_stream_t stream);
+
 /* End-to-end convenience with HOST buffers (bench `e2e` leg and plain-C callers): copies
  * the camera + grad_image from host, runs forward + backward on device-resident parameters,
  * copies the padded image back.  Host buffers should be pinned.  Synchronises. */
