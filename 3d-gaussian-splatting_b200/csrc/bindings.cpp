@@ -443,6 +443,28 @@ void adam_step(torch::Tensor param, torch::Tensor grad, torch::Tensor exp_avg, t
            "gs_adam_step");
 }
 
+// fused L1 + SSIM loss (reference train.py:99-107): returns (out3 = {total, l1, ssim}, grad_image)
+std::tuple<torch::Tensor, torch::Tensor> loss_l1_ssim(torch::Tensor image, torch::Tensor target, double w_l1,
+                                                      double w_ssim, double bias, bool want_grad) {
+  GS_CHECK_F32(image);
+  TORCH_CHECK(target.is_cuda() && target.is_contiguous() &&
+                  (target.scalar_type() == at::kFloat || target.scalar_type() == at::kHalf),
+              "loss_l1_ssim: target must be a contiguous float32 / float16 CUDA tensor");
+  TORCH_CHECK(image.dim() == 3 && image.size(2) == 3 && target.sizes() == image.sizes(),
+              "loss_l1_ssim: image and target must both be [H, W, 3]");
+  TORCH_CHECK(image.size(0) > 10 && image.size(1) > 10, "loss_l1_ssim: the image must be larger than the 11x11 window");
+  c10::cuda::CUDAGuard guard(image.device());
+  const int h = (int)image.size(0), w = (int)image.size(1);
+  auto ws = torch::empty({(int64_t)gs_loss_workspace_bytes(h, w)}, image.options().dtype(at::kByte));
+  auto out3 = torch::empty({3}, image.options());
+  torch::Tensor grad = want_grad ? torch::empty_like(image) : torch::Tensor();
+  check_rc(gs_loss_l1_ssim(fp(image), target.data_ptr(), target.scalar_type() == at::kHalf ? 1 : 0, h, w, (float)w_l1,
+                           (float)w_ssim, (float)bias, want_grad ? fpm(grad) : nullptr, fpm(out3), ws.data_ptr(),
+                           (size_t)ws.numel(), cur_stream()),
+           "gs_loss_l1_ssim");
+  return {out3, grad};
+}
+
 // NVLS in-place all-reduce of a symmetric flat buffer (multicast address as an integer)
 void allreduce_multimem(int64_t multicast_ptr, int64_t n_floats, int rank, int world, int device) {
   c10::cuda::CUDAGuard guard(c10::Device(c10::kCUDA, (c10::DeviceIndex)device));
@@ -527,6 +549,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("allreduce_push_finish", &allreduce_push_finish, "second half of the pushed gradient exchange");
   m.def("allreduce_p2p", &allreduce_p2p, "peer-to-peer two-shot in-place all-reduce of a symmetric buffer");
   m.def("allreduce_multimem", &allreduce_multimem, "NVLS multimem in-place all-reduce of a symmetric buffer");
+  m.def("loss_l1_ssim", &loss_l1_ssim, "fused L1 + SSIM loss, forward + image gradient (CUDA)");
   m.def("adam_step", &adam_step, "fused Adam over flat parameter / gradient buffers (CUDA)");
   m.attr("abi_version") = gs_abi_version();
 }

@@ -404,6 +404,419 @@ __global__ void __launch_bounds__(32 * WARPS) blend_bwd_kernel(const float4* __r
 }
 
 // =======================================================================================
+// warp-specialised kernels (default): one PRODUCER warp issues the bulk-async copies of the tile's
+// sorted range, chunk by chunk, into a ring of shared-memory stages guarded by full / empty
+// mbarriers; the CONSUMER warps only ever wait on `full`, blend, and release with one arrive on
+// `empty`.  Consumers synchronise among themselves on a named barrier the producer never joins.
+// =======================================================================================
+constexpr int WS_CH = 64;          // instances per staging chunk (40 B each: 2.5 KB per stage)
+
+template <int STAGES>
+struct WsRing {
+  float4 A[STAGES][WS_CH];
+  float4 C[STAGES][WS_CH];
+  float2 B[STAGES][WS_CH + 2];
+  uint64_t full[STAGES], empty[STAGES], done;
+  volatile int stop, consumed_chunks;
+};
+
+template <typename SM, int STAGES>
+__device__ __forceinline__ void ws_init(SM& sm, int tid) {
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      gs_mbar_init(&sm.full[s], 1);
+      gs_mbar_init(&sm.empty[s], 1);
+    }
+    gs_mbar_init(&sm.done, 1);
+    sm.stop = 0;
+    sm.consumed_chunks = 0;
+    gs_fence_barrier_init();
+  }
+  __syncthreads();
+}
+
+// Producer warp (one elected lane): keeps up to STAGES chunks in flight; stops as soon as the
+// consumers report that every pixel of the tile is saturated, and drains copies that were issued
+// but never consumed before the CTA may retire (their destination is this CTA's shared memory).
+template <typename SM, int STAGES>
+__device__ __forceinline__ void ws_producer(SM& sm, const float4* __restrict__ pA, const float2* __restrict__ pB,
+                                            const float4* __restrict__ pC, int start, int cnt, int nchunks) {
+  const int shift = start & 1;
+  int k = 0;
+  for (; k < nchunks; ++k) {
+    const int s = k % STAGES;
+    if (k >= STAGES) gs_mbar_wait(&sm.empty[s], (uint32_t)(((k / STAGES) - 1) & 1));
+    if (sm.stop) break;
+    issue_chunk<SM, WS_CH>(sm, s, pA, pB, pC, start + k * WS_CH, min(WS_CH, cnt - k * WS_CH), shift);
+  }
+  gs_mbar_wait(&sm.done, 0u);
+  for (int kk = sm.consumed_chunks; kk < k; ++kk) gs_mbar_wait(&sm.full[kk % STAGES], (uint32_t)((kk / STAGES) & 1));
+}
+
+// ---- forward ---------------------------------------------------------------------------
+constexpr int WSF_STAGES = 4;
+constexpr int WSF_CONS = 64;       // consumer threads: 2 warps, each thread a row of 4 adjacent pixels
+
+__global__ void __launch_bounds__(WSF_CONS + 32) blend_fwd_ws_kernel(const float4* __restrict__ pA,
+                                                                      const float2* __restrict__ pB,
+                                                                      const float4* __restrict__ pC,
+                                                                      const int* __restrict__ tile_accum, int wp,
+                                                                      int hp, int ntx, float fx, float fy,
+                                                                      float* __restrict__ image,
+                                                                      int* __restrict__ tile_neff,
+                                                                      float* __restrict__ final_img, GsCrop crop) {
+  using Smem = WsRing<WSF_STAGES>;
+  __shared__ __align__(16) Smem sm;
+  const int tile = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int start = tile_accum[tile];
+  const int cnt = tile_accum[tile + 1] - start;
+  const int nchunks = (cnt + WS_CH - 1) / WS_CH;
+  ws_init<Smem, WSF_STAGES>(sm, tid);
+  if (tid >= WSF_CONS) {
+    if (tid == WSF_CONS && nchunks > 0) ws_producer<Smem, WSF_STAGES>(sm, pA, pB, pC, start, cnt, nchunks);
+    return;
+  }
+  const int tx = tile % ntx, ty = tile / ntx;
+  const int ix0 = tx * GS_TILE + (tid & 3) * FWD_PX;
+  const int iy = ty * GS_TILE + (tid >> 2);
+  float px[FWD_PX];
+#pragma unroll
+  for (int p = 0; p < FWD_PX; ++p) px[p] = gs_pixel_coord(ix0 + p, wp, fx);
+  const float py = gs_pixel_coord(iy, hp, fy);
+  const int shift = start & 1;
+
+  float T[FWD_PX], cr[FWD_PX], cg[FWD_PX], cb[FWD_PX];
+#pragma unroll
+  for (int p = 0; p < FWD_PX; ++p) {
+    T[p] = 1.f;
+    cr[p] = cg[p] = cb[p] = 0.f;
+  }
+  int consumed = cnt;
+  for (int k = 0; k < nchunks; ++k) {
+    const int stage = k % WSF_STAGES;
+    gs_mbar_wait(&sm.full[stage], (uint32_t)((k / WSF_STAGES) & 1));
+    const int n = min(WS_CH, cnt - k * WS_CH);
+    const float4* __restrict__ sA = sm.A[stage];
+    const float4* __restrict__ sC = sm.C[stage];
+    const float2* __restrict__ sB = sm.B[stage] + shift;
+#define GS_FWD_BODY(J)                                                                      \
+  {                                                                                         \
+    const float4 a = sA[J];                                                                 \
+    const float2 b = sB[J];                                                                 \
+    const float4 c = sC[J];                                                                 \
+    const float dy = py - a.y;                                                              \
+    const float m1 = a.w * dy;                                                              \
+    const float ev = fmaf(-b.x * dy, dy, b.y);                                              \
+    _Pragma("unroll") for (int p = 0; p < FWD_PX; ++p) {                                    \
+      const float dx = px[p] - a.x;                                                         \
+      const float eu = fmaf(a.z, dx, -m1);                                                  \
+      const float alpha = gs_ex2(fmaf(-dx, eu, ev));                                        \
+      const float w = (T[p] > GS_T_STOP) ? alpha * T[p] : 0.f;                              \
+      cr[p] = fmaf(c.x, w, cr[p]);                                                          \
+      cg[p] = fmaf(c.y, w, cg[p]);                                                          \
+      cb[p] = fmaf(c.z, w, cb[p]);                                                          \
+      T[p] -= w;                                                                            \
+    }                                                                                       \
+  }
+    int j = 0;
+    bool warp_dead = false;
+    for (; j + 4 <= n; j += 4) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) GS_FWD_BODY(j + u)
+      const bool dead = !(T[0] > GS_T_STOP) && !(T[1] > GS_T_STOP) && !(T[2] > GS_T_STOP) && !(T[3] > GS_T_STOP);
+      if (__all_sync(0xffffffffu, dead)) {
+        warp_dead = true;
+        break;
+      }
+    }
+    if (!warp_dead)
+      for (; j < n; ++j) GS_FWD_BODY(j)
+#undef GS_FWD_BODY
+    const bool dead = !(T[0] > GS_T_STOP) && !(T[1] > GS_T_STOP) && !(T[2] > GS_T_STOP) && !(T[3] > GS_T_STOP);
+    const int all_dead = gs_bar_red_and(1, WSF_CONS, dead);       // also: both warps are done with the stage
+    if (all_dead) {
+      consumed = min(cnt, (k + 1) * WS_CH);
+      if (tid == 0) {
+        sm.consumed_chunks = k + 1;
+        sm.stop = 1;
+        gs_mbar_arrive(&sm.empty[stage]);
+      }
+      break;
+    }
+    if (tid == 0) {
+      sm.consumed_chunks = k + 1;
+      gs_mbar_arrive(&sm.empty[stage]);
+    }
+  }
+  if (tid == 0 && nchunks > 0) gs_mbar_arrive(&sm.done);
+  float4* o = reinterpret_cast<float4*>(image + ((size_t)iy * wp + ix0) * 3);
+  o[0] = make_float4(cr[0], cg[0], cb[0], cr[1]);
+  o[1] = make_float4(cg[1], cb[1], cr[2], cg[2]);
+  o[2] = make_float4(cb[2], cr[3], cg[3], cb[3]);
+  if (final_img) {
+#pragma unroll
+    for (int p = 0; p < FWD_PX; ++p)
+      gs_store_final(final_img, ix0 + p, iy, crop.left, crop.top, crop.width, crop.height, cr[p], cg[p], cb[p]);
+  }
+  if (tile_neff && tid == 0) tile_neff[tile] = consumed;
+}
+
+// ---- backward ----------------------------------------------------------------------------
+// Cross-thread reduction WITHOUT shuffles: every consumer thread accumulates, over its own row of
+// PX pixels, six partial sums per instance (S0, Sx, Sxx, Cr, Cg, Cb; dy is shared by the row) and
+// stores them to shared memory ([instance][quarter][thread][6], strides chosen so that both the
+// 8-byte stores and the 8-byte loads of the second phase are bank-conflict free).  After R = NT/4
+// instances a second phase gives each instance to 4 threads: each sums one quarter of the source
+// threads (4 pixel rows: Sy = sum dy S0, Sxy = sum dy Sx, Syy = sum dy^2 S0 are formed per row), two
+// xor-shuffles combine the quarters, and each of the 4 lanes stores one 16-byte piece of the
+// instance's gradient record.  ~13 instructions per (thread, instance) instead of ~42 for the
+// recursive-halving shuffle network; fixed summation order => bit-deterministic.
+template <int PX>
+struct Bwd2Cfg {
+  static constexpr int NT = 256 / PX;                        // consumer threads (64 or 32)
+  static constexpr int TPR = GS_TILE / PX;                   // threads per pixel row
+  static constexpr int R = NT / 4;                           // instances per reduction round
+  static constexpr int SQ = NT / 4;                          // source threads per quarter (= 4 pixel rows)
+  static constexpr int QS = SQ * 6 + (SQ == 16 ? 8 : 24);    // quarter stride, floats: = 8 (mod 32)
+  static constexpr int IS = 4 * QS + 2;                      // instance stride, floats: = 2 (mod 32)
+  static constexpr int STAGES = 3;
+};
+
+template <int PX>
+struct Bwd2Smem : WsRing<Bwd2Cfg<PX>::STAGES> {
+  float part[Bwd2Cfg<PX>::R * Bwd2Cfg<PX>::IS];
+  float pyt[GS_TILE];
+  int valid[2];
+};
+
+template <int PX>
+__global__ void __launch_bounds__(256 / PX + 32) blend_bwd_ws_kernel(const float4* __restrict__ pA,
+                                                                      const float2* __restrict__ pB,
+                                                                      const float4* __restrict__ pC,
+                                                                      const int* __restrict__ tile_accum, int wp,
+                                                                      int hp, int ntx, float fx, float fy,
+                                                                      const float* __restrict__ image,
+                                                                      const float* __restrict__ grad_image,
+                                                                      float* __restrict__ grad_inst,
+                                                                      int grad_is_final, GsCrop crop,
+                                                                      uint32_t* __restrict__ row_epoch,
+                                                                      uint32_t epoch) {
+  using Cfg = Bwd2Cfg<PX>;
+  constexpr int NT = Cfg::NT, TPR = Cfg::TPR, R = Cfg::R, SQ = Cfg::SQ, QS = Cfg::QS, IS = Cfg::IS, STAGES = Cfg::STAGES;
+  using Smem = Bwd2Smem<PX>;
+  __shared__ __align__(16) Smem sm;
+  const int tile = blockIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int start = tile_accum[tile];
+  const int cnt = tile_accum[tile + 1] - start;
+  if (cnt == 0) return;
+  const int nchunks = (cnt + WS_CH - 1) / WS_CH;
+  const int tx = tile % ntx, ty = tile / ntx;
+  if (tid < GS_TILE) sm.pyt[tid] = gs_pixel_coord(ty * GS_TILE + tid, hp, fy);
+  ws_init<Smem, STAGES>(sm, tid);
+  if (tid >= NT) {
+    if (tid == NT) ws_producer<Smem, STAGES>(sm, pA, pB, pC, start, cnt, nchunks);
+    return;
+  }
+  const int shift = start & 1;
+  const int ix0 = tx * GS_TILE + (tid % TPR) * PX;
+  const int iy = ty * GS_TILE + (tid / TPR);
+  float px[PX];
+#pragma unroll
+  for (int p = 0; p < PX; ++p) px[p] = gs_pixel_coord(ix0 + p, wp, fx);
+  const float py = sm.pyt[tid / TPR];
+
+  float T[PX], Rr[PX], gr[PX], gg[PX], gb[PX];
+  {
+    const size_t off = ((size_t)iy * wp + ix0) * 3;     // PX*12 contiguous, 16-byte aligned bytes
+    const float4* im = reinterpret_cast<const float4*>(image + off);
+    float gbuf[PX * 3], ibuf[PX * 3];
+#pragma unroll
+    for (int q = 0; q < PX * 3 / 4; ++q) {
+      const float4 i4 = im[q];
+      ibuf[4 * q] = i4.x; ibuf[4 * q + 1] = i4.y; ibuf[4 * q + 2] = i4.z; ibuf[4 * q + 3] = i4.w;
+    }
+    if (!grad_is_final) {
+      const float4* gi = reinterpret_cast<const float4*>(grad_image + off);
+#pragma unroll
+      for (int q = 0; q < PX * 3 / 4; ++q) {
+        const float4 g4 = gi[q];
+        gbuf[4 * q] = g4.x; gbuf[4 * q + 1] = g4.y; gbuf[4 * q + 2] = g4.z; gbuf[4 * q + 3] = g4.w;
+      }
+    } else {
+#pragma unroll
+      for (int p = 0; p < PX; ++p)
+        gs_load_final_grad(grad_image, ibuf + 3 * p, ix0 + p, iy, crop.left, crop.top, crop.width, crop.height,
+                           gbuf[3 * p], gbuf[3 * p + 1], gbuf[3 * p + 2]);
+    }
+#pragma unroll
+    for (int p = 0; p < PX; ++p) {
+      gr[p] = gbuf[3 * p];
+      gg[p] = gbuf[3 * p + 1];
+      gb[p] = gbuf[3 * p + 2];
+      Rr[p] = gr[p] * ibuf[3 * p] + gg[p] * ibuf[3 * p + 1] + gb[p] * ibuf[3 * p + 2];
+      T[p] = 1.f;
+    }
+  }
+  // this thread's slot in the partial buffer: quarter tid / SQ, position tid % SQ
+  float2* const my_part = reinterpret_cast<float2*>(sm.part + (tid / SQ) * QS + (tid % SQ) * 6);
+  // second-phase role: instance ri of the round, quarter rq of the source threads
+  const int ri = tid >> 2, rq = tid & 3;
+  const float2* const red_src = reinterpret_cast<const float2*>(sm.part + ri * IS + rq * QS);
+
+  int consumed = cnt;
+  bool finished = false;
+  int k = 0;
+  for (; k < nchunks && !finished; ++k) {
+    const int stage = k % STAGES;
+    gs_mbar_wait(&sm.full[stage], (uint32_t)((k / STAGES) & 1));
+    const int n = min(WS_CH, cnt - k * WS_CH);
+    const float4* __restrict__ sA = sm.A[stage];
+    const float4* __restrict__ sC = sm.C[stage];
+    const float2* __restrict__ sB = sm.B[stage] + shift;
+
+    for (int sub = 0; sub < n; sub += R) {
+      const int nr = min(R, n - sub);
+      // ---- phase 1: per-thread partial sums of up to R instances
+      int j = 0;
+      for (; j < nr; ++j) {
+        if ((j & 3) == 0) {
+          bool dead = true;
+#pragma unroll
+          for (int p = 0; p < PX; ++p) dead = dead && !(T[p] > GS_T_STOP);
+          if (__all_sync(0xffffffffu, dead)) break;
+        }
+        const float4 a = sA[sub + j];
+        const float2 b = sB[sub + j];
+        const float4 c = sC[sub + j];
+        float s0 = 0.f, sx = 0.f, sxx = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
+        const float dy = py - a.y;
+        const float m1 = a.w * dy;
+        const float ev = fmaf(-b.x * dy, dy, b.y);
+#pragma unroll
+        for (int p = 0; p < PX; ++p) {
+          const float dx = px[p] - a.x;
+          const float eu = fmaf(a.z, dx, -m1);
+          float alpha = gs_ex2(fmaf(-dx, eu, ev));                     // l2o - (ca dx^2 - cb dx dy + cc dy^2)
+          alpha = (T[p] > GS_T_STOP) ? alpha : 0.f;                    // early stop (:578): no weight, no gradient
+          const float w = alpha * T[p];
+          const float gc = fmaf(gr[p], c.x, fmaf(gg[p], c.y, gb[p] * c.z));
+          Rr[p] = fmaf(-gc, w, Rr[p]);                                 // sum_c g_c (out_c - C_c^{<=i})
+          const float rc = gs_rcp(1.0000001f - alpha);                 // 1/(1 - alpha + 1e-7)  (:721)
+          const float dal = fmaf(T[p], gc, -Rr[p] * rc);               // d L / d alpha            (:710-722)
+          const float e = dal * alpha;
+          T[p] -= w;
+          const float ex = e * dx;
+          s0 += e;
+          sx += ex;
+          sxx = fmaf(ex, dx, sxx);
+          c0 = fmaf(gr[p], w, c0);
+          c1 = fmaf(gg[p], w, c1);
+          c2 = fmaf(gb[p], w, c2);
+        }
+        float2* dst = my_part + j * (IS / 2);
+        dst[0] = make_float2(s0, sx);
+        dst[1] = make_float2(sxx, c0);
+        dst[2] = make_float2(c1, c2);
+      }
+      bool dead = true;
+#pragma unroll
+      for (int p = 0; p < PX; ++p) dead = dead && !(T[p] > GS_T_STOP);
+      int all_dead;
+      int v0, v1;
+      if (NT == 64) {
+        if (lane == 0) sm.valid[warp] = j;          // j is warp-uniform (the loop only breaks on a warp vote)
+        all_dead = gs_bar_red_and(1, NT, dead);
+        v0 = sm.valid[0];
+        v1 = sm.valid[1];
+      } else {
+        __syncwarp();
+        all_dead = __all_sync(0xffffffffu, dead);
+        v0 = v1 = j;
+      }
+      // ---- phase 2: 4 threads per instance, one quarter of the source threads (4 pixel rows) each
+      {
+        float S0 = 0.f, Sx = 0.f, Sxx = 0.f, Sy = 0.f, Sxy = 0.f, Syy = 0.f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
+        const bool act = ri < nr;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        float2 b = make_float2(0.f, 0.f);
+        if (act) {
+          a = sA[sub + ri];
+          b = sB[sub + ri];
+        }
+        const int vq = (NT == 64 && rq >= 2) ? v1 : v0;   // instances the quarter's source warp really processed
+        if (act && ri < vq) {
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            float2 u0 = red_src[(r * TPR) * 3], u1 = red_src[(r * TPR) * 3 + 1], u2 = red_src[(r * TPR) * 3 + 2];
+#pragma unroll
+            for (int t = 1; t < TPR; ++t) {
+              const float2 w0 = red_src[(r * TPR + t) * 3], w1 = red_src[(r * TPR + t) * 3 + 1],
+                           w2 = red_src[(r * TPR + t) * 3 + 2];
+              u0.x += w0.x; u0.y += w0.y; u1.x += w1.x; u1.y += w1.y; u2.x += w2.x; u2.y += w2.y;
+            }
+            const float dyr = sm.pyt[4 * rq + r] - a.y;
+            S0 += u0.x;
+            Sx += u0.y;
+            Sxx += u1.x;
+            C0 += u1.y;
+            C1 += u2.x;
+            C2 += u2.y;
+            Sy = fmaf(dyr, u0.x, Sy);
+            Sxy = fmaf(dyr, u0.y, Sxy);
+            Syy = fmaf(dyr * dyr, u0.x, Syy);
+          }
+        }
+#define GS_RED4(V)                                   \
+  V += __shfl_xor_sync(0xffffffffu, V, 1);           \
+  V += __shfl_xor_sync(0xffffffffu, V, 2);
+        GS_RED4(S0) GS_RED4(Sx) GS_RED4(Sxx) GS_RED4(Sy) GS_RED4(Sxy) GS_RED4(Syy) GS_RED4(C0) GS_RED4(C1) GS_RED4(C2)
+#undef GS_RED4
+        if (act) {
+          const uint32_t slot = __float_as_uint(sC[sub + ri].w);
+          float4* out = reinterpret_cast<float4*>(grad_inst + (size_t)slot * GS_GREC);
+          // d/dx, d/dy, d/dca, d/dcb  |  d/dcc, d/dl2o, d/dr, d/dg  |  d/db
+          if (rq == 0)
+            out[0] = make_float4(GS_LN2 * (2.f * a.z * Sx - a.w * Sy), GS_LN2 * (2.f * b.x * Sy - a.w * Sx),
+                                 -GS_LN2 * Sxx, GS_LN2 * Sxy);
+          else if (rq == 1)
+            out[1] = make_float4(-GS_LN2 * Syy, GS_LN2 * S0, C0, C1);
+          else if (rq == 2)
+            out[2] = make_float4(C2, 0.f, 0.f, 0.f);
+          else if (row_epoch)
+            row_epoch[slot] = epoch;               // marks the row as written in this frame
+        }
+      }
+      if (NT == 64) gs_bar_sync(1, NT);            // the partial buffer may be overwritten now
+      else __syncwarp();
+      if (all_dead) {
+        consumed = min(cnt, k * WS_CH + sub + nr);
+        finished = true;
+        break;
+      }
+    }
+    if (tid == 0) {
+      sm.consumed_chunks = k + 1;
+      if (finished) sm.stop = 1;
+      gs_mbar_arrive(&sm.empty[stage]);
+    }
+  }
+  if (tid == 0) gs_mbar_arrive(&sm.done);
+  // the unread tail of a saturated tile has zero gradient: with an epoch array the rows are simply
+  // left stale (the consumer skips rows whose tag is not this frame's); otherwise write zeros
+  if (row_epoch) return;
+  for (int t = consumed + tid; t < cnt; t += NT) {
+    const uint32_t slot = __float_as_uint(pC[start + t].w);
+    float4* out = reinterpret_cast<float4*>(grad_inst + (size_t)slot * GS_GREC);
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    out[0] = z;
+    out[1] = z;
+    out[2] = z;
+  }
+}
+
+// =======================================================================================
 // legacy boundary helpers: per-instance tensors <-> packed record streams
 // =======================================================================================
 __global__ void __launch_bounds__(256) legacy_pack_kernel(const float* __restrict__ pos, const float* __restrict__ rgb,
@@ -522,6 +935,12 @@ inline size_t legacy_ws_layout(int m, int d, LegacyWs* ws, char* base) {
 cudaError_t gs_launch_blend_fwd(const float4* pA, const float2* pB, const float4* pC, const int* tile_accum,
                                 const GsFrameGeom& g, float* image, int* tile_neff, float* final_img,
                                 const GsCrop& crop, cudaStream_t st) {
+  static const int ver = getenv("GS_BLEND_V") ? atoi(getenv("GS_BLEND_V")) : 2;   // A/B knob: 1 = round-1 kernels
+  if (ver != 1) {
+    blend_fwd_ws_kernel<<<g.n_tiles, WSF_CONS + 32, 0, st>>>(pA, pB, pC, tile_accum, g.wp, g.hp, g.ntx, g.fx, g.fy, image,
+                                                             tile_neff, final_img, crop);
+    return cudaGetLastError();
+  }
   static const int ch = getenv("GS_FWD_CH") ? atoi(getenv("GS_FWD_CH")) : 256;   // A/B knob (staging chunk)
 #define GS_FWD_LAUNCH(CH)                                                                                       \
   blend_fwd_kernel<CH><<<g.n_tiles, FWD_THREADS, 0, st>>>(pA, pB, pC, tile_accum, g.wp, g.hp, g.ntx, g.fx, g.fy, \
@@ -537,6 +956,19 @@ cudaError_t gs_launch_blend_bwd(const float4* pA, const float2* pB, const float4
                                 const GsFrameGeom& g, const float* image, const float* grad_image, float* grad_inst,
                                 int grad_is_final, const GsCrop& crop, uint32_t* row_epoch, uint32_t epoch,
                                 cudaStream_t st) {
+  static const int ver = getenv("GS_BLEND_V") ? atoi(getenv("GS_BLEND_V")) : 2;   // A/B knob: 1 = round-1 kernels
+  static const int bpx = getenv("GS_BWD_PX") ? atoi(getenv("GS_BWD_PX")) : 4;     // A/B knob: pixels per consumer thread
+  if (ver != 1) {
+    if (bpx == 8)
+      blend_bwd_ws_kernel<8><<<g.n_tiles, 256 / 8 + 32, 0, st>>>(pA, pB, pC, tile_accum, g.wp, g.hp, g.ntx, g.fx, g.fy,
+                                                                 image, grad_image, grad_inst, grad_is_final, crop,
+                                                                 row_epoch, epoch);
+    else
+      blend_bwd_ws_kernel<4><<<g.n_tiles, 256 / 4 + 32, 0, st>>>(pA, pB, pC, tile_accum, g.wp, g.hp, g.ntx, g.fx, g.fy,
+                                                                 image, grad_image, grad_inst, grad_is_final, crop,
+                                                                 row_epoch, epoch);
+    return cudaGetLastError();
+  }
   static const int warps = getenv("GS_BWD_WARPS") ? atoi(getenv("GS_BWD_WARPS")) : 2;   // A/B knob: 1 = one warp x 8 px
   static const int ch = getenv("GS_BWD_CH") ? atoi(getenv("GS_BWD_CH")) : 64;            // A/B knob (staging chunk)
 #define GS_BWD_LAUNCH(W, CH)                                                                                         \

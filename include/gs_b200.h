@@ -216,6 +216,24 @@ int gs_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg
                  float eps, int step, gs_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Next-row widening: the training loss of reference train.py:99-107 on the device,
+ * forward and backward in two kernels, producing the image gradient in the layout
+ * gs_render_backward_final consumes.  image / grad_image: [height, width, 3] float32; target: same
+ * shape, float32 or float16 (`target_is_half`; reference `ground_truth` is float16, splatter.py:478).
+ *   L1   = mean |image - target|                                             (train.py:99)
+ *   SSIM = torchmetrics StructuralSimilarityIndexMeasure(data_range=1.0): 11x11 Gaussian window,
+ *          sigma 1.5, k1 0.01, k2 0.03, mean over the pixels whose window is inside the image and
+ *          over channels                                                      (train.py:72,101-104)
+ *   out3 (device) = { w_l1 * L1 + w_ssim * SSIM + bias,  L1,  SSIM }
+ *   grad_image (nullable) = d out3[0] / d image.
+ * train.py:107's loss (1 - w) l1 + w (1 - ssim) is w_l1 = 1 - w, w_ssim = -w, bias = w.
+ * height and width must exceed 10.  No allocation, no synchronisation. */
+size_t gs_loss_workspace_bytes(int height, int width);
+int gs_loss_l1_ssim(const float* image, const void* target, int target_is_half, int height, int width,
+                    float w_l1, float w_ssim, float bias, float* grad_image, float* out3, void* workspace,
+                    size_t workspace_bytes, gs_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
  * Multi-GPU exchange step (new - the reference is single-GPU): in-place SUM of
  * the flat gradient bucket across `world` GPUs of one NVSwitch domain through an NVLS multicast
  * mapping.  `multicast_ptr` is the multicast address of a symmetric buffer holding each rank's

@@ -10,9 +10,9 @@ next to our own ``gaussian`` module in one process).
 
 The built .so travels to the GPU box with the gpurun snapshot; /root/reference itself
 does not exist there, so nothing at test/bench time reads the sources.
-The reference's pure-python glue files (renderer.py, splatter.py, utils.py) that the
-``bench.py --impl reference`` arm drives are copied next to the .so at build time as
-build outputs (also git-ignored), never committed.
+The reference's pure-python files that the ``bench.py --impl reference`` arm and the drop-in tests
+drive UNCHANGED (renderer.py, splatter.py, utils.py, train.py, visergui.py, transforms/) are copied next
+to the .so at build time as build outputs (also git-ignored), never committed.
 """
 import os
 import shutil
@@ -67,7 +67,7 @@ def build(verbose: bool = False) -> str:
 
 
 def _copy_glue():
-    for f in ("renderer.py", "splatter.py", "utils.py"):
+    for f in ("renderer.py", "splatter.py", "utils.py", "train.py", "visergui.py"):
         s = os.path.join(REF, f)
         if os.path.exists(s):
             shutil.copyfile(s, os.path.join(OUT, f))

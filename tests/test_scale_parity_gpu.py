@@ -38,39 +38,83 @@ def _splatter(g, views, dev, **kw):
 
 
 # ------------------------------------------------------------------------------------------
-def test_p4_at_c2(gs, ref, cuda):
-    """SURVEY.md §8c "P4@C2": C2's heaviest tile (<= 500 instances) is inside the limit below which the
-    reference's draw_backward is valid (hazard 1), so its kernels are the arbiter here - fed our
-    (tile, depth, id) order so that its fp32 sort-key ties (hazard 4) cannot enter."""
+def _reference_chain(rref, g, v, cam, gi, accum, go, dev):
+    """The reference's own operators (its CUDA build through its unmodified renderer.py) on OUR sorted
+    instance order: pre-activations (splatter.py:519-524,539-540) -> global_culling -> gather (a8) ->
+    draw -> clamp + crop (splatter.py:652-653) -> backward of all of it."""
+    p = {k: t.to(dev).clone().requires_grad_(True) for k, t in g.items()}
+    nq = p["quat"] / p["quat"].norm(dim=1, keepdim=True)
+    ns = p["scale"].abs() + 1e-4
+    _pos, _cov, mask = rref.global_culling(p["pos"], nq, ns, v.rot.to(dev), v.tran.to(dev), cam.near,
+                                           cam.half_w, cam.half_h)
+    t_pos, t_cov = _pos[gi], _cov[gi]
+    t_rgb, t_opa = p["rgb"].sigmoid()[gi], p["opa"].sigmoid()[gi]
+    dummy = torch.zeros(3, device=dev)
+    rimg_p = rref.draw(t_pos, t_rgb, t_opa, t_cov, accum, cam.Hp, cam.Wp, cam.fx, cam.fy, False, False, False, True,
+                       dummy, dummy, dummy, dummy)
+    rimg = cam.crop(torch.clamp(rimg_p, 0, 1))
+    rimg.backward(go)
+    return rimg.detach(), {k: p[k].grad for k in NAMES}, mask
+
+
+def _tile_mask(cam, tiles, h, w):
+    top, left = (cam.Hp - h) // 2, (cam.Wp - w) // 2
+    mpad = torch.zeros(cam.Hp, cam.Wp, 1)
+    for t in tiles:
+        ty, tx = divmod(t, cam.ntx)
+        mpad[ty * 16:(ty + 1) * 16, tx * 16:(tx + 1) * 16] = 1.0
+    return mpad[top:top + h, left:left + w]
+
+
+@pytest.mark.parametrize("regime,opa", [("safe", (0.005, 0.05)), ("standard", (0.05, 0.9))])
+def test_p4_at_c2(gs, ref, cuda, regime, opa):
+    """SURVEY.md §8c "P4@C2": C2 (500 k Gaussians, 1080p; heaviest tile <= 500 instances, inside the limit
+    below which the reference's draw_backward does not mix chunks - hazard 1).  The reference build's own
+    kernels are fed OUR (tile, depth, id) order, so its fp32 sort-key ties (hazard 4) cannot enter.
+      safe     - opacities in [0.005, 0.05]: no pixel reaches T < 1e-4, the reference's backward is exact:
+                 image <= 1e-4 and ALL gradients <= 1e-3 are gated against it;
+      standard - the benchmark's opacities [0.05, 0.9]: pixels saturate, and the reference's partial-mask
+                 shuffle reduction (hazard 3, gaussian.cu:675-772) is no longer exact.  The image is gated
+                 against the reference; for the gradients the fp64 oracle arbitrates on sampled tiles: ours
+                 must match it to 1e-3, and any disagreement with the reference must be the reference's."""
     gref, rref = ref
     n, w, h = 500_000, 1920, 1080
-    g, v, cam = scene(n, w, h, k=0)
+    g, v, cam = scene(n, w, h, k=0, opa_range=opa)
     go = (S.make_grad_output(h, w, 0) * (h * w)).to(cuda)
     sp = _splatter(g, [v], cuda)
     img = sp(0)
     img.backward(go)
+    ours = {k: getattr(sp.gaussian_3ds, k).grad.clone() for k in NAMES}
     st = sp.frame_stats()
     assert st["max_tile_count"] <= 500, st
     idx, accum = sp._rctx.sorted_instances()
     gi = idx.long()
-
-    # the reference's own operators (its CUDA build through its renderer.py), our instance order
-    p = {k: t.to(cuda).clone().requires_grad_(True) for k, t in g.items()}
-    nq = p["quat"] / p["quat"].norm(dim=1, keepdim=True)                    # splatter.py:519-524
-    ns = p["scale"].abs() + 1e-4
-    _pos, _cov, mask = rref.global_culling(p["pos"], nq, ns, v.rot.to(cuda), v.tran.to(cuda), cam.near,
-                                           cam.half_w, cam.half_h)
+    rimg, rgrads, mask = _reference_chain(rref, g, v, cam, gi, accum, go, cuda)
     assert torch.equal(mask, sp.culling_mask)
-    t_pos, t_cov = _pos[gi], _cov[gi]                                        # a8: gather of the sorted instances
-    t_rgb, t_opa = p["rgb"].sigmoid()[gi], p["opa"].sigmoid()[gi]
-    dummy = torch.zeros(3, device=cuda)
-    rimg_p = rref.draw(t_pos, t_rgb, t_opa, t_cov, accum, cam.Hp, cam.Wp, cam.fx, cam.fy, False, False, False, True,
-                       dummy, dummy, dummy, dummy)
-    rimg = cam.crop(torch.clamp(rimg_p, 0, 1))                               # splatter.py:652-653
-    rimg.backward(go)
     assert abs_err(img, rimg) < IMG_ATOL
-    for name in NAMES:
-        assert rel_err(getattr(sp.gaussian_3ds, name).grad, p[name].grad) < GRAD_RTOL, name
+    errs = {k: rel_err(ours[k], rgrads[k]) for k in NAMES}
+    print(f"P4@C2[{regime}] ours vs reference build, full frame: {errs}")
+    if regime == "safe":
+        assert st["n_instances_eff"] == st["n_instances"]              # nothing saturated
+        for k in NAMES:
+            assert errs[k] < GRAD_RTOL, (k, errs)
+        return
+    # standard regime: arbitrate on sampled tiles with the fp64 oracle
+    neff = sp._rctx.tile_consumed().cpu().long()
+    tiles = _pick_tiles(accum.cpu().long(), neff, cam.ntx, cam.nty, 5)
+    gom = S.make_grad_output(h, w, 0) * (h * w) * _tile_mask(cam, tiles, h, w)
+    for p_ in sp.gaussian_3ds.parameters():
+        p_.grad = None
+    sp(0).backward(gom.to(cuda))
+    _, rg, _ = _reference_chain(rref, g, v, cam, gi, accum, gom.to(cuda), cuda)
+    _, U, og = _oracle_on_tiles(g, v, cam, idx.cpu(), accum.cpu().long(), tiles, gom, False)
+    for k in NAMES:
+        e_ours = rel_err(getattr(sp.gaussian_3ds, k).grad.cpu()[U], og[k])
+        e_ref = rel_err(rg[k].cpu()[U], og[k])
+        print(f"P4@C2[standard] {k}: ours vs oracle {e_ours:.2e}, reference vs oracle {e_ref:.2e}, "
+              f"ours vs reference (full frame) {errs[k]:.2e}")
+        assert e_ours < GRAD_RTOL, (k, e_ours)
+        assert errs[k] < GRAD_RTOL or e_ref > 10 * e_ours, (k, errs[k], e_ref, e_ours)
 
 
 # ------------------------------------------------------------------------------------------
@@ -133,11 +177,7 @@ def test_masked_gradient_at_scale(gs, cuda, label, n, w, h, sh_dim):
 
     # upstream gradient: O(1) values on the sampled tiles only (crop coordinates)
     top, left = (cam.Hp - h) // 2, (cam.Wp - w) // 2
-    mpad = torch.zeros(cam.Hp, cam.Wp, 1)
-    for t in tiles:
-        ty, tx = divmod(t, cam.ntx)
-        mpad[ty * 16:(ty + 1) * 16, tx * 16:(tx + 1) * 16] = 1.0
-    go = S.make_grad_output(h, w, 0) * (h * w) * mpad[top:top + h, left:left + w]
+    go = S.make_grad_output(h, w, 0) * (h * w) * _tile_mask(cam, tiles, h, w)
 
     img = sp(0)
     img.backward(go.to(cuda))
