@@ -399,6 +399,7 @@ struct RenderContext {
     d["height_padded"] = fi.height_padded;
     d["n_tiles"] = fi.n_tiles;
     d["max_tile_count"] = fi.max_tile_count;
+    d["n_instances_eff_bwd"] = fi.n_instances_eff_bwd;
     return d;
   }
 
@@ -492,6 +493,16 @@ void allreduce_push_finish(std::vector<int64_t> bucket_ptrs, int64_t staging_loc
            "gs_allreduce_push_finish_f32");
 }
 
+void allreduce_push_finish_mc(int64_t bucket_multicast, int64_t bucket_local, int64_t staging_local, int64_t n_floats,
+                              int64_t per, int rank, int world, int device) {
+  c10::cuda::CUDAGuard guard(c10::Device(c10::kCUDA, (c10::DeviceIndex)device));
+  check_rc(gs_allreduce_push_finish_mc_f32(reinterpret_cast<void*>(static_cast<uintptr_t>(bucket_multicast)),
+                                           reinterpret_cast<const float*>(static_cast<uintptr_t>(bucket_local)),
+                                           reinterpret_cast<const float*>(static_cast<uintptr_t>(staging_local)), n_floats,
+                                           per, rank, world, cur_stream()),
+           "gs_allreduce_push_finish_mc_f32");
+}
+
 }  // namespace gsb200
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
@@ -547,9 +558,13 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def("sorted_instances", &RenderContext::sorted_instances)
       .def("tile_consumed", &RenderContext::tile_consumed);
   m.def("allreduce_push_finish", &allreduce_push_finish, "second half of the pushed gradient exchange");
+  m.def("allreduce_push_finish_mc", &allreduce_push_finish_mc,
+        "second half of the pushed gradient exchange, broadcast through the NVSwitch (multimem.st)");
   m.def("allreduce_p2p", &allreduce_p2p, "peer-to-peer two-shot in-place all-reduce of a symmetric buffer");
   m.def("allreduce_multimem", &allreduce_multimem, "NVLS multimem in-place all-reduce of a symmetric buffer");
   m.def("loss_l1_ssim", &loss_l1_ssim, "fused L1 + SSIM loss, forward + image gradient (CUDA)");
   m.def("adam_step", &adam_step, "fused Adam over flat parameter / gradient buffers (CUDA)");
+  m.def("kernel_launches", []() { return (int64_t)gs_kernel_launches(); },
+        "kernels of libgs_b200 launched by this process so far");
   m.attr("abi_version") = gs_abi_version();
 }

@@ -249,6 +249,7 @@ extern "C" int gs_tile_list(const float* pos, const float* cov, int n, const flo
                                                                         tile_gaussian_list, n, max_per_tile, thresh);
   }
   GS_CUDA_TRY(cudaGetLastError());
+  gs_count_launch();
   return 0;
 }
 
@@ -262,6 +263,7 @@ extern "C" int gs_gather(const int* tile_n_point_accum, const int* tile_gaussian
   gather_kernel<<<(n_tiles + warps - 1) / warps, kBlock, 0, (cudaStream_t)stream>>>(
       tile_n_point_accum, tile_gaussian_list, n_tiles, list_stride, gathered_list, tile_ids_for_points);
   GS_CUDA_TRY(cudaGetLastError());
+  gs_count_launch();
   return 0;
 }
 

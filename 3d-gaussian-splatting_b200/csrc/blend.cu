@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(32 * WARPS) blend_bwd_kernel(const float4* __r
                                                                 const float* __restrict__ grad_image,
                                                                 float* __restrict__ grad_inst, int grad_is_final,
                                                                 GsCrop crop, uint32_t* __restrict__ row_epoch,
-                                                                uint32_t epoch) {
+                                                                uint32_t epoch, int* __restrict__ tile_neff_b) {
   constexpr int THREADS = 32 * WARPS;
   constexpr int PX = 256 / THREADS;          // 8 (1 warp) or 4 (2 warps)
   constexpr int TPR = GS_TILE / PX;          // threads per pixel row
@@ -390,6 +390,7 @@ __global__ void __launch_bounds__(32 * WARPS) blend_bwd_kernel(const float4* __r
     for (int kk = k + 1; kk < nchunks && kk < k + BWD_STAGES; ++kk)
       gs_mbar_wait(&sm.full[kk % BWD_STAGES], (uint32_t)((kk / BWD_STAGES) & 1));
   }
+  if (tile_neff_b && tid == 0) tile_neff_b[tile] = consumed;
   // the unread tail of a saturated tile has zero gradient: with an epoch array the rows are simply
   // left stale (the consumer skips rows whose tag is not this frame's); otherwise write zeros
   if (row_epoch) return;
@@ -601,7 +602,7 @@ __global__ void __launch_bounds__(256 / PX + 32) blend_bwd_ws_kernel(const float
                                                                       float* __restrict__ grad_inst,
                                                                       int grad_is_final, GsCrop crop,
                                                                       uint32_t* __restrict__ row_epoch,
-                                                                      uint32_t epoch) {
+                                                                      uint32_t epoch, int* __restrict__ tile_neff_b) {
   using Cfg = Bwd2Cfg<PX>;
   constexpr int NT = Cfg::NT, TPR = Cfg::TPR, R = Cfg::R, SQ = Cfg::SQ, QS = Cfg::QS, IS = Cfg::IS, STAGES = Cfg::STAGES;
   using Smem = Bwd2Smem<PX>;
@@ -802,7 +803,10 @@ __global__ void __launch_bounds__(256 / PX + 32) blend_bwd_ws_kernel(const float
       gs_mbar_arrive(&sm.empty[stage]);
     }
   }
-  if (tid == 0) gs_mbar_arrive(&sm.done);
+  if (tid == 0) {
+    gs_mbar_arrive(&sm.done);
+    if (tile_neff_b) tile_neff_b[tile] = consumed;
+  }
   // the unread tail of a saturated tile has zero gradient: with an epoch array the rows are simply
   // left stale (the consumer skips rows whose tag is not this frame's); otherwise write zeros
   if (row_epoch) return;
@@ -955,25 +959,26 @@ cudaError_t gs_launch_blend_fwd(const float4* pA, const float2* pB, const float4
 cudaError_t gs_launch_blend_bwd(const float4* pA, const float2* pB, const float4* pC, const int* tile_accum,
                                 const GsFrameGeom& g, const float* image, const float* grad_image, float* grad_inst,
                                 int grad_is_final, const GsCrop& crop, uint32_t* row_epoch, uint32_t epoch,
-                                cudaStream_t st) {
+                                int* tile_neff_b, cudaStream_t st) {
   static const int ver = getenv("GS_BLEND_V") ? atoi(getenv("GS_BLEND_V")) : 2;   // A/B knob: 1 = round-1 kernels
   static const int bpx = getenv("GS_BWD_PX") ? atoi(getenv("GS_BWD_PX")) : 4;     // A/B knob: pixels per consumer thread
   if (ver != 1) {
     if (bpx == 8)
       blend_bwd_ws_kernel<8><<<g.n_tiles, 256 / 8 + 32, 0, st>>>(pA, pB, pC, tile_accum, g.wp, g.hp, g.ntx, g.fx, g.fy,
                                                                  image, grad_image, grad_inst, grad_is_final, crop,
-                                                                 row_epoch, epoch);
+                                                                 row_epoch, epoch, tile_neff_b);
     else
       blend_bwd_ws_kernel<4><<<g.n_tiles, 256 / 4 + 32, 0, st>>>(pA, pB, pC, tile_accum, g.wp, g.hp, g.ntx, g.fx, g.fy,
                                                                  image, grad_image, grad_inst, grad_is_final, crop,
-                                                                 row_epoch, epoch);
+                                                                 row_epoch, epoch, tile_neff_b);
     return cudaGetLastError();
   }
   static const int warps = getenv("GS_BWD_WARPS") ? atoi(getenv("GS_BWD_WARPS")) : 2;   // A/B knob: 1 = one warp x 8 px
   static const int ch = getenv("GS_BWD_CH") ? atoi(getenv("GS_BWD_CH")) : 64;            // A/B knob (staging chunk)
 #define GS_BWD_LAUNCH(W, CH)                                                                                         \
   blend_bwd_kernel<W, CH><<<g.n_tiles, 32 * W, 0, st>>>(pA, pB, pC, tile_accum, g.wp, g.hp, g.ntx, g.fx, g.fy, image, \
-                                                        grad_image, grad_inst, grad_is_final, crop, row_epoch, epoch)
+                                                        grad_image, grad_inst, grad_is_final, crop, row_epoch, epoch, \
+                                                        tile_neff_b)
   if (warps == 1) GS_BWD_LAUNCH(1, 64);
   else if (ch == 32) GS_BWD_LAUNCH(2, 32);
   else if (ch == 128) GS_BWD_LAUNCH(2, 128);
@@ -1017,6 +1022,7 @@ extern "C" int gs_draw_fwd(const float* pos, const float* rgb, const float* opa,
       legacy_pack_sh_kernel<<<(m + 255) / 256, 256, 0, st>>>(pos, rgb, opa, cov, m, d, gs_sh_stream_width(d), ws.pA,
                                                              ws.pB, reinterpret_cast<float*>(ws.pC));
     GS_CUDA_TRY(cudaGetLastError());
+    gs_count_launch();
   }
   GsFrameGeom g{};
   g.wp = width_padded;
@@ -1033,6 +1039,7 @@ extern "C" int gs_draw_fwd(const float* pos, const float* rgb, const float* opa,
     GS_CUDA_TRY(gs_launch_blend_sh_fwd(ws.pA, ws.pB, reinterpret_cast<float*>(ws.pC), d, tile_n_point_accum, g, r,
                                        image, nullptr, nullptr, GsCrop{}, st));
   }
+  gs_count_launch();
   return 0;
 }
 
@@ -1057,6 +1064,7 @@ extern "C" int gs_draw_bwd(const float* pos, const float* rgb, const float* opa,
     legacy_pack_sh_kernel<<<(m + 255) / 256, 256, 0, st>>>(pos, rgb, opa, cov, m, d, gs_sh_stream_width(d), ws.pA,
                                                            ws.pB, reinterpret_cast<float*>(ws.pC));
   GS_CUDA_TRY(cudaGetLastError());
+  gs_count_launch();
   GsFrameGeom g{};
   g.wp = width_padded;
   g.hp = height_padded;
@@ -1067,16 +1075,17 @@ extern "C" int gs_draw_bwd(const float* pos, const float* rgb, const float* opa,
   g.fy = focal_y;
   if (d == 3) {
     GS_CUDA_TRY(gs_launch_blend_bwd(ws.pA, ws.pB, ws.pC, tile_n_point_accum, g, image, grad_image, ws.grad_inst, 0,
-                                    GsCrop{}, nullptr, 0u, st));
+                                    GsCrop{}, nullptr, 0u, nullptr, st));
     legacy_unpack_grads_kernel<<<(m + 255) / 256, 256, 0, st>>>(ws.grad_inst, opa, cov, m, grad_pos, grad_rgb,
                                                               grad_opa, grad_cov);
   } else {
     GsRayPtrs r{rays_o, lefttop, vec_dx, vec_dy};
     GS_CUDA_TRY(gs_launch_blend_sh_bwd(ws.pA, ws.pB, reinterpret_cast<float*>(ws.pC), d, tile_n_point_accum, g, r,
-                                       image, grad_image, ws.grad_inst, 0, GsCrop{}, nullptr, 0u, st));
+                                       image, grad_image, ws.grad_inst, 0, GsCrop{}, nullptr, 0u, nullptr, st));
     legacy_unpack_grads_sh_kernel<<<(m + 255) / 256, 256, 0, st>>>(ws.grad_inst, gs_sh_grad_width(d), opa, cov, m, d,
                                                                  grad_pos, grad_rgb, grad_opa, grad_cov);
   }
   GS_CUDA_TRY(cudaGetLastError());
+  gs_count_launch(2);   // blend backward + unpack
   return 0;
 }

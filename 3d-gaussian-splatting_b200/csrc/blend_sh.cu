@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(64) blend_sh_bwd_kernel(const float4* __restri
                                                            const float* __restrict__ grad_image,
                                                            float* __restrict__ grad_inst, int grad_is_final,
                                                            GsCrop crop, uint32_t* __restrict__ row_epoch,
-                                                           uint32_t epoch) {
+                                                           uint32_t epoch, int* __restrict__ tile_neff_b) {
   constexpr int CH = 32, STAGES = 2, PX = 4, SW = sh_sw(K), NV = sh_nv(K), NVP = sh_nvp(K), THREADS = 64;
   constexpr int GREC = (NV + 3) / 4 * 4;
   __shared__ __align__(16) ShBwdSmem<K> smem;
@@ -435,6 +435,7 @@ __global__ void __launch_bounds__(64) blend_sh_bwd_kernel(const float4* __restri
   if (tid == 0 && k < nchunks)
     for (int kk = k + 1; kk < nchunks && kk < k + STAGES; ++kk)
       gs_mbar_wait(&sm.full[kk % STAGES], (uint32_t)((kk / STAGES) & 1));
+  if (tile_neff_b && tid == 0) tile_neff_b[tile] = consumed;
   if (row_epoch) return;   // stale rows are skipped by the consumer (see blend.cu)
   for (int t = consumed + tid; t < cnt; t += THREADS) {
     const uint32_t slot = __float_as_uint(pS[(size_t)(start + t) * SW + 3 * K]);
@@ -464,14 +465,14 @@ cudaError_t gs_launch_blend_sh_fwd(const float4* pA, const float2* pB, const flo
 cudaError_t gs_launch_blend_sh_bwd(const float4* pA, const float2* pB, const float* pS, int d, const int* tile_accum,
                                    const GsFrameGeom& g, const GsRayPtrs& r, const float* image,
                                    const float* grad_image, float* grad_inst, int grad_is_final, const GsCrop& crop,
-                                   uint32_t* row_epoch, uint32_t epoch, cudaStream_t st) {
+                                   uint32_t* row_epoch, uint32_t epoch, int* tile_neff_b, cudaStream_t st) {
   if (d == 27)
     blend_sh_bwd_kernel<9><<<g.n_tiles, 64, 0, st>>>(pA, pB, pS, tile_accum, g.wp, g.hp, g.ntx, g.fx, g.fy, r.rays_o,
                                                      r.lefttop, r.dx, r.dy, image, grad_image, grad_inst, grad_is_final, crop, row_epoch,
-                                                     epoch);
+                                                     epoch, tile_neff_b);
   else
     blend_sh_bwd_kernel<16><<<g.n_tiles, 64, 0, st>>>(pA, pB, pS, tile_accum, g.wp, g.hp, g.ntx, g.fx, g.fy, r.rays_o,
                                                       r.lefttop, r.dx, r.dy, image, grad_image, grad_inst, grad_is_final, crop, row_epoch,
-                                                     epoch);
+                                                     epoch, tile_neff_b);
   return cudaGetLastError();
 }

@@ -96,6 +96,32 @@ __global__ void __launch_bounds__(512) push_finish_kernel(GsPeers buckets, const
   }
 }
 
+// Same second half with the broadcast done by the NVSwitch: ONE multimem.st per 16 bytes delivers the sum
+// to all W buckets (each GPU sends its slice once instead of W-1 times; receive traffic is unchanged).
+template <int W>
+__global__ void __launch_bounds__(512) push_finish_mc_kernel(float4* mc_bucket, const float4* own,
+                                                             const float4* __restrict__ staging, long long per4,
+                                                             int rank, long long begin4, long long end4) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = begin4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < end4; i += stride) {
+    const long long j = i - begin4;
+    float4 v[W];
+#pragma unroll
+    for (int p = 0; p < W; ++p) v[p] = p == rank ? own[i] : ld_sys(staging + p * per4 + j);
+    float4 acc = v[0];
+#pragma unroll
+    for (int p = 1; p < W; ++p) {
+      acc.x += v[p].x;
+      acc.y += v[p].y;
+      acc.z += v[p].z;
+      acc.w += v[p].w;
+    }
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_bucket + i), "f"(acc.x),
+                 "f"(acc.y), "f"(acc.z), "f"(acc.w)
+                 : "memory");
+  }
+}
+
 int nvls_max_grid() {
   static const int g = [] {
     const char* e = getenv("GS_NVLS_GRID");          // tuning knob (CTAs), default 4 per SM
@@ -129,6 +155,7 @@ extern "C" int gs_allreduce_p2p_f32(void* const* peer_ptrs, long long n_floats, 
   else if (world == 4) p2p_allreduce_kernel<4><<<grid, 512, 0, st>>>(peers, begin4, end4);
   else p2p_allreduce_kernel<8><<<grid, 512, 0, st>>>(peers, begin4, end4);
   GS_CUDA_TRY(cudaGetLastError());
+  gs_count_launch();
   return 0;
 }
 
@@ -156,6 +183,33 @@ extern "C" int gs_allreduce_push_finish_f32(void* const* peer_buckets, const flo
   else if (world == 4) push_finish_kernel<4><<<grid, 512, 0, st>>>(peers, peers.p[rank], sg, per4, rank, begin4, end4);
   else push_finish_kernel<8><<<grid, 512, 0, st>>>(peers, peers.p[rank], sg, per4, rank, begin4, end4);
   GS_CUDA_TRY(cudaGetLastError());
+  gs_count_launch();
+  return 0;
+}
+
+extern "C" int gs_allreduce_push_finish_mc_f32(void* bucket_multicast, const float* bucket_local,
+                                               const float* staging_local, long long n_floats, long long per, int rank,
+                                               int world, gs_stream_t stream) {
+  if (!bucket_multicast || !bucket_local || !staging_local || n_floats < 0 || (n_floats % 4) || per <= 0 || (per % 4) ||
+      rank < 0 || rank >= world || !(world == 2 || world == 4 || world == 8) || per * world < n_floats ||
+      reinterpret_cast<uintptr_t>(staging_local) % 16 || reinterpret_cast<uintptr_t>(bucket_local) % 16 ||
+      reinterpret_cast<uintptr_t>(bucket_multicast) % 16)
+    return gs_set_error_msg(GS_ERR_INVALID_ARG, "gs_allreduce_push_finish_mc_f32: bad arguments");
+  const long long n4 = n_floats / 4, per4 = per / 4;
+  const long long begin4 = per4 * rank;
+  const long long end4 = begin4 + per4 < n4 ? begin4 + per4 : n4;
+  if (end4 <= begin4) return 0;
+  int grid = (int)((end4 - begin4 + 511) / 512);
+  if (grid > nvls_max_grid()) grid = nvls_max_grid();
+  cudaStream_t st = (cudaStream_t)stream;
+  float4* mc = static_cast<float4*>(bucket_multicast);
+  const float4* own = reinterpret_cast<const float4*>(bucket_local);
+  const float4* sg = reinterpret_cast<const float4*>(staging_local);
+  if (world == 2) push_finish_mc_kernel<2><<<grid, 512, 0, st>>>(mc, own, sg, per4, rank, begin4, end4);
+  else if (world == 4) push_finish_mc_kernel<4><<<grid, 512, 0, st>>>(mc, own, sg, per4, rank, begin4, end4);
+  else push_finish_mc_kernel<8><<<grid, 512, 0, st>>>(mc, own, sg, per4, rank, begin4, end4);
+  GS_CUDA_TRY(cudaGetLastError());
+  gs_count_launch();
   return 0;
 }
 
@@ -175,5 +229,6 @@ extern "C" int gs_allreduce_multimem_f32(void* multicast_ptr, long long n_floats
   if (grid > nvls_max_grid()) grid = nvls_max_grid();
   nvls_allreduce_kernel<<<grid, 512, 0, (cudaStream_t)stream>>>(static_cast<float4*>(multicast_ptr), begin4, end4);
   GS_CUDA_TRY(cudaGetLastError());
+  gs_count_launch();
   return 0;
 }

@@ -27,6 +27,9 @@ struct GsRayPtrs {
   const float *rays_o, *lefttop, *dx, *dy;
 };
 
+// every launch of one of OUR kernels is counted (bench.py reports the count of the timed region)
+void gs_count_launch(int n = 1);
+
 // ---- blend_sh.cu -----------------------------------------------------------------------
 int gs_sh_basis_count(int d);      // 27 -> 9, 48 -> 16, else 0
 int gs_sh_stream_width(int d);     // floats per instance row of the SH stream (coefficients + slot, padded)
@@ -37,7 +40,7 @@ cudaError_t gs_launch_blend_sh_fwd(const float4* pA, const float2* pB, const flo
 cudaError_t gs_launch_blend_sh_bwd(const float4* pA, const float2* pB, const float* pS, int d, const int* tile_accum,
                                    const GsFrameGeom& g, const GsRayPtrs& r, const float* image,
                                    const float* grad_image, float* grad_inst, int grad_is_final, const GsCrop& crop,
-                                   uint32_t* row_epoch, uint32_t epoch, cudaStream_t st);
+                                   uint32_t* row_epoch, uint32_t epoch, int* tile_neff_b, cudaStream_t st);
 
 // ---- project.cu ------------------------------------------------------------------------
 cudaError_t gs_launch_fused_project(const float* pos, const float* rgb, const float* opa, const float* quat,
@@ -83,4 +86,4 @@ cudaError_t gs_launch_blend_bwd(const float4* pA, const float2* pB, const float4
                                 const GsFrameGeom& g, const float* image, const float* grad_image,
                                 float* grad_inst /*[M,GS_GREC] rows addressed by C.w slot*/, int grad_is_final,
                                 const GsCrop& crop, uint32_t* row_epoch /*nullable*/, uint32_t epoch,
-                                cudaStream_t st);
+                                int* tile_neff_b /*nullable: instances the backward consumed per tile*/, cudaStream_t st);

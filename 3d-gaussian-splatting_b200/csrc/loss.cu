@@ -244,8 +244,10 @@ extern "C" int gs_loss_l1_ssim(const float* image, const void* target, int targe
     ssim_stats_kernel<float><<<grid, 256, 0, st>>>(image, static_cast<const float*>(target), height, width, win, c1, c2,
                                                    abc, partial);
   GS_CUDA_TRY(cudaGetLastError());
+  gs_count_launch();
   loss_finalize_kernel<<<1, 256, 0, st>>>(partial, nblk, 1.0 / n_all, 1.0 / n_inner, w_l1, w_ssim, bias, out3);
   GS_CUDA_TRY(cudaGetLastError());
+  gs_count_launch();
   if (grad_image) {
     const float k_l1 = (float)((double)w_l1 / n_all), k_ssim = (float)((double)w_ssim / n_inner);
     if (target_is_half)
@@ -255,6 +257,7 @@ extern "C" int gs_loss_l1_ssim(const float* image, const void* target, int targe
       ssim_grad_kernel<float><<<grid, 256, 0, st>>>(image, static_cast<const float*>(target), height, width, win, abc,
                                                     k_l1, k_ssim, grad_image);
     GS_CUDA_TRY(cudaGetLastError());
+    gs_count_launch();
   }
   return 0;
 }

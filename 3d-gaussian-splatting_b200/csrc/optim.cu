@@ -68,5 +68,6 @@ extern "C" int gs_adam_step(float* param, const float* grad, float* exp_avg, flo
       reinterpret_cast<float4*>(param), reinterpret_cast<const float4*>(grad), reinterpret_cast<float4*>(exp_avg),
       reinterpret_cast<float4*>(exp_avg_sq), n4, segs, beta1, beta2, (float)(1.0 / std::sqrt(bc2)), eps);
   GS_CUDA_TRY(cudaGetLastError());
+  gs_count_launch();
   return 0;
 }

@@ -341,6 +341,7 @@ extern "C" int gs_project_fwd(const float* pos, const float* quat, const float* 
                                                                         half_width, half_height, res_pos, res_cov,
                                                                         mask);
   GS_CUDA_TRY(cudaGetLastError());
+  gs_count_launch();
   return 0;
 }
 
@@ -354,6 +355,7 @@ extern "C" int gs_project_bwd(const float* pos, const float* quat, const float* 
                                                                         gradout_cov, mask, gradin_pos, gradin_quat,
                                                                         gradin_scale);
   GS_CUDA_TRY(cudaGetLastError());
+  gs_count_launch();
   return 0;
 }
 
@@ -362,6 +364,7 @@ extern "C" int gs_w2c_fwd(const float* pos, const float* rot, const float* tran,
   if (n <= 0) return n == 0 ? 0 : gs_set_error_msg(GS_ERR_INVALID_ARG, "gs_w2c_fwd: n < 0");
   w2c_fwd_kernel_p<<<grid_for(n), kBlock, 0, (cudaStream_t)stream>>>(pos, rot, tran, n, res);
   GS_CUDA_TRY(cudaGetLastError());
+  gs_count_launch();
   return 0;
 }
 
@@ -369,6 +372,7 @@ extern "C" int gs_w2c_bwd(const float* grad_out, const float* rot, int n, float*
   if (n <= 0) return n == 0 ? 0 : gs_set_error_msg(GS_ERR_INVALID_ARG, "gs_w2c_bwd: n < 0");
   w2c_bwd_kernel_p<<<grid_for(n), kBlock, 0, (cudaStream_t)stream>>>(grad_out, rot, n, grad_in);
   GS_CUDA_TRY(cudaGetLastError());
+  gs_count_launch();
   return 0;
 }
 
@@ -376,6 +380,7 @@ extern "C" int gs_jacobian(const float* pos_cam, int n, float* jac, gs_stream_t 
   if (n <= 0) return n == 0 ? 0 : gs_set_error_msg(GS_ERR_INVALID_ARG, "gs_jacobian: n < 0");
   jacobian_kernel<<<grid_for(n), kBlock, 0, (cudaStream_t)stream>>>(pos_cam, n, jac);
   GS_CUDA_TRY(cudaGetLastError());
+  gs_count_launch();
   return 0;
 }
 

@@ -38,7 +38,12 @@ int gs_set_error_msg(int code, const char* what) {
   return code;
 }
 extern "C" const char* gs_last_error(void) { return g_err; }
-extern "C" int gs_abi_version(void) { return 1; }
+extern "C" int gs_abi_version(void) { return 2; }
+
+#include <atomic>
+static std::atomic<unsigned long long> g_launches{0};
+void gs_count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+extern "C" unsigned long long gs_kernel_launches(void) { return g_launches.load(std::memory_order_relaxed); }
 
 // ---- growable device buffer -------------------------------------------------------------
 struct DevBuf {
@@ -77,12 +82,12 @@ struct gs_ctx {
   DevBuf keys_in, keys_out, vals_in, vals_out, pA, pB, pC, grad_inst, row_epoch;
   uint32_t epoch = 0;                      // tag of the current backward in row_epoch[]
   // per tile / misc
-  DevBuf tile_accum, tile_neff, cub_tmp, counters, img_dev, gimg_dev, rays;
+  DevBuf tile_accum, tile_neff, tile_neff_b, cub_tmp, counters, img_dev, gimg_dev, rays;
   float* host_rays = nullptr;             // pinned: rays_o, lefttop, dx, dy (SH colour only)
   unsigned long long* host_m = nullptr;   // pinned: {M}
   cudaEvent_t ev_m = nullptr;             // marks the completion of the M read-back
   // state of the last forward
-  bool have_forward = false;
+  bool have_forward = false, have_backward = false;
   int n = 0, d = 3, scale_act = 0;
   long long m = 0;
   GsCam cam{};
@@ -130,7 +135,7 @@ extern "C" void gs_ctx_destroy(gs_ctx* c) {
   cudaDeviceSynchronize();
   DevBuf* bufs[] = {&c->rec, &c->count, &c->offsets, &c->dkey_in, &c->dkey_out, &c->perm, &c->iota, &c->offsets_g, &c->keys_in, &c->keys_out,
                     &c->vals_in, &c->vals_out, &c->pA, &c->pB, &c->pC, &c->grad_inst, &c->row_epoch, &c->tile_accum, &c->tile_neff,
-                    &c->cub_tmp, &c->counters, &c->img_dev, &c->gimg_dev, &c->rays};
+                    &c->tile_neff_b, &c->cub_tmp, &c->counters, &c->img_dev, &c->gimg_dev, &c->rays};
   for (DevBuf* b : bufs) b->release();
   if (c->host_m) cudaFreeHost(c->host_m);
   if (c->host_rays) cudaFreeHost(c->host_rays);
@@ -175,6 +180,7 @@ static int render_forward_impl(gs_ctx* c, const float* pos, const float* rgb, co
   if (int rc = gs_check_device(c->device, "gs_render_forward")) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   c->have_forward = false;
+  c->have_backward = false;
 
   GsFrameGeom g{};
   g.width = cam->width;
@@ -214,10 +220,12 @@ static int render_forward_impl(gs_ctx* c, const float* pos, const float* rgb, co
   GS_CUDA_TRY(c->offsets_g.reserve((N + 1) * 4, st));
   GS_CUDA_TRY(c->tile_accum.reserve((size_t)(g.n_tiles + 1) * 4, st));
   GS_CUDA_TRY(c->tile_neff.reserve((size_t)g.n_tiles * 4, st));
+  GS_CUDA_TRY(c->tile_neff_b.reserve((size_t)g.n_tiles * 4, st));
   GS_CUDA_TRY(c->counters.reserve(64, st));
   if (c->iota_n < N) {   // 0..N-1 values for the depth sort (kept across frames)
     GS_CUDA_TRY(c->iota.reserve(N * 4 + 4, st));
     GS_CUDA_TRY(gs_launch_iota(c->iota.as<uint32_t>(), n, st));
+    gs_count_launch();
     c->iota_n = N;
   }
 
@@ -256,6 +264,7 @@ static int render_forward_impl(gs_ctx* c, const float* pos, const float* rgb, co
   GS_CUDA_TRY(gs_launch_fused_project(pos, rgb, opa, quat, scale, n, d, scale_activation, dc, grid, cam->near_plane,
                                       half_w, half_h, c->rec.as<GsRec>(), c->count.as<uint32_t>(),
                                       c->dkey_in.as<uint32_t>(), culling_mask, c->counters.as<unsigned int>(), st));
+  if (n > 0) gs_count_launch();
   // 2. (a) exclusive scan of the tile counts in Gaussian-id order -> gradient-row bases and M;
   //    (b) stable depth sort of the N Gaussians; (c) scan of the counts in depth order (the
   //    count gather is fused into the scan's input iterator) -> instance emission offsets
@@ -312,6 +321,7 @@ static int render_forward_impl(gs_ctx* c, const float* pos, const float* rgb, co
     // 3. instances in (depth, id) order: tile-id keys + Gaussian-id values
     GS_CUDA_TRY(gs_launch_emit_keys(c->rec.as<GsRec>(), c->perm.as<uint32_t>(), c->offsets.as<uint32_t>(), n, g.ntx,
                                     c->keys_in.p, key_bytes, c->vals_in.as<uint32_t>(), st));
+    gs_count_launch();
     // 4. stable radix sort on the tile id only -> (tile, depth, id)
     gs_mark(c, 3, st);
     int end_bit = ceil_log2((unsigned)g.n_tiles);
@@ -348,6 +358,7 @@ static int render_forward_impl(gs_ctx* c, const float* pos, const float* rgb, co
                                          gs_sh_stream_width(d), c->pA.as<float4>(), c->pB.as<float2>(),
                                          c->pC.as<float>(), c->tile_accum.as<int>(), st));
   }
+  if (m > 0) gs_count_launch();   // pack
   // 6. blend (+ optional fused clamp & centre crop, splatter.py:652-653 / :267-272)
   GsCrop crop{(g.wp - g.width) / 2, (g.hp - g.height) / 2, g.width, g.height};
   gs_mark(c, 5, st);
@@ -361,6 +372,7 @@ static int render_forward_impl(gs_ctx* c, const float* pos, const float* rgb, co
                                        c->tile_accum.as<int>(), g, rays, image, c->tile_neff.as<int>(), final_img,
                                        crop, st));
   }
+  gs_count_launch();   // blend forward
   gs_mark(c, 6, st);
   c->ev_fwd_valid = c->timing && c->ev_ok;
 
@@ -427,15 +439,18 @@ static int render_backward_impl(gs_ctx* c, const float* pos, const float* rgb, c
     if (d == 3) {
       GS_CUDA_TRY(gs_launch_blend_bwd(c->pA.as<float4>(), c->pB.as<float2>(), c->pC.as<float4>(),
                                       c->tile_accum.as<int>(), c->geom, image, grad_image, c->grad_inst.as<float>(),
-                                      grad_is_final, crop, c->row_epoch.as<uint32_t>(), c->epoch, st));
+                                      grad_is_final, crop, c->row_epoch.as<uint32_t>(), c->epoch,
+                                      c->tile_neff_b.as<int>(), st));
     } else {
       const float* rp = c->rays.as<float>();
       GsRayPtrs rays{rp, rp + 3, rp + 6, rp + 9};
       GS_CUDA_TRY(gs_launch_blend_sh_bwd(c->pA.as<float4>(), c->pB.as<float2>(), c->pC.as<float>(), d,
                                          c->tile_accum.as<int>(), c->geom, rays, image, grad_image,
                                          c->grad_inst.as<float>(), grad_is_final, crop,
-                                         c->row_epoch.as<uint32_t>(), c->epoch, st));
+                                         c->row_epoch.as<uint32_t>(), c->epoch, c->tile_neff_b.as<int>(), st));
     }
+    gs_count_launch();
+    c->have_backward = true;
   }
   gs_mark(c, 8, st);
   if (c->push.world) {
@@ -455,6 +470,7 @@ static int render_backward_impl(gs_ctx* c, const float* pos, const float* rgb, c
                                           c->half_w, c->half_h, c->offsets_g.as<uint32_t>(), c->count.as<uint32_t>(),
                                           c->grad_inst.as<float>(), c->row_epoch.as<uint32_t>(), c->epoch,
                                           grad_pos, grad_rgb, grad_opa, grad_quat, grad_scale, c->push, st));
+  if (c->n > 0) gs_count_launch();
   gs_mark(c, 9, st);
   c->ev_bwd_valid = c->timing && c->ev_ok;
   return 0;
@@ -507,30 +523,34 @@ extern "C" int gs_frame_stats(gs_ctx* c, gs_frame_info* out, gs_stream_t stream)
   if (!c->have_forward) return gs_set_error_msg(GS_ERR_NO_FORWARD, "gs_frame_stats: no forward on this ctx");
   cudaStream_t st = (cudaStream_t)stream;
   int T = c->geom.n_tiles;
-  int* h = static_cast<int*>(malloc(sizeof(int) * (size_t)(2 * T + 1)));
+  int* h = static_cast<int*>(malloc(sizeof(int) * (size_t)(3 * T + 1)));
   if (!h) return gs_set_error_msg(GS_ERR_INVALID_ARG, "gs_frame_stats: out of host memory");
   unsigned int nvis = 0;
   cudaError_t e = cudaMemcpyAsync(h, c->tile_accum.p, sizeof(int) * (size_t)(T + 1), cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess)
     e = cudaMemcpyAsync(h + T + 1, c->tile_neff.p, sizeof(int) * (size_t)T, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && c->have_backward)
+    e = cudaMemcpyAsync(h + 2 * T + 1, c->tile_neff_b.p, sizeof(int) * (size_t)T, cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(&nvis, c->counters.p, 4, cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) {
     free(h);
     return gs_set_error(e, "gs_frame_stats copy");
   }
-  long long meff = 0;
+  long long meff = 0, meff_b = 0;
   int mx = 0;
   for (int t = 0; t < T; ++t) {
     int cnt = h[t + 1] - h[t];
     if (cnt > mx) mx = cnt;
     meff += h[T + 1 + t];
+    if (c->have_backward && cnt > 0) meff_b += h[2 * T + 1 + t];
   }
   free(h);
   out->n_gaussians = c->n;
   out->n_visible = (int)nvis;
   out->n_instances = c->m;
   out->n_instances_eff = meff;
+  out->n_instances_eff_bwd = c->have_backward ? meff_b : -1;
   out->width_padded = c->geom.wp;
   out->height_padded = c->geom.hp;
   out->n_tiles = T;

@@ -10,6 +10,7 @@ writes its gradients straight into a symmetric-memory bucket and one kernel of o
 """
 from __future__ import annotations
 
+import os
 from typing import Iterable, List, Sequence
 
 import torch
@@ -88,7 +89,8 @@ class SymmetricGradBucket:
                        slots and stores the sum to every bucket (gs_allreduce_push_finish_f32).
                        (W-1)/W bucket sizes per direction hidden under the backward + the same
                        again exposed.  The bucket is only complete after `allreduce()`.
-      mode "auto":     push for W = 2, multimem otherwise (p2p if there is no multicast mapping).
+      mode "auto":     push (W = 2, 4, 8; its broadcast half goes through the NVSwitch with multimem.st at
+                       W >= 4 when a multicast mapping exists), else multimem / p2p.
 
     Measured on B200 for the 134 MB bucket of 2.4 M Gaussians (profiles/r1_exchange.md), exchange
     alone: W = 2: p2p 0.214 ms, multimem 0.357, NCCL 0.292; W = 8: multimem 0.330, p2p 0.394,
@@ -135,8 +137,11 @@ class SymmetricGradBucket:
         if push:
             self.mode = "p2p"                  # the self-check below runs the plain p2p kernel
         if self.mode == "auto":
-            push = self.world == 2
-            self.mode = "p2p" if (self.world == 2 or not has_mc) else "multimem"
+            push = p2p_ok
+            self.mode = "p2p" if (p2p_ok or not has_mc) else "multimem"
+        # broadcast half of the pushed exchange through the NVSwitch (multimem.st) where it pays (W >= 4)
+        env_mc = os.environ.get("GS_DP_PUSH_MC")
+        self.push_mc = has_mc and (self.world >= 4 if env_mc is None else env_mc == "1")
         if self.mode == "multimem" and not has_mc:
             raise RuntimeError("symmetric memory has no multicast mapping (NVLS unavailable)")
         if self.mode == "p2p" and not p2p_ok:
@@ -152,9 +157,14 @@ class SymmetricGradBucket:
     def _reduce(self, buf, hdl, numel):
         hdl.barrier(channel=0)                  # every rank's bucket is written (push: and every pushed slice)
         if self.mode == "push":
-            self._gaussian.allreduce_push_finish([int(p) for p in hdl.buffer_ptrs], int(self.staging.data_ptr()),
-                                                 int(numel), int(self.per), self.rank, self.world,
-                                                 buf.device.index)
+            if self.push_mc:
+                self._gaussian.allreduce_push_finish_mc(int(hdl.multicast_ptr), int(buf.data_ptr()),
+                                                        int(self.staging.data_ptr()), int(numel), int(self.per),
+                                                        self.rank, self.world, buf.device.index)
+            else:
+                self._gaussian.allreduce_push_finish([int(p) for p in hdl.buffer_ptrs], int(self.staging.data_ptr()),
+                                                     int(numel), int(self.per), self.rank, self.world,
+                                                     buf.device.index)
         elif self.mode == "multimem":
             self._gaussian.allreduce_multimem(int(hdl.multicast_ptr), int(numel), self.rank, self.world,
                                               buf.device.index)
@@ -211,8 +221,9 @@ def make_grad_bucket(params: Sequence[torch.Tensor], average: bool = False, grou
     """The gradient exchange for `params`: `exchange` (env GS_DP_EXCHANGE overrides) is
     "nccl" (portable `GradBucket`), "multimem" / "p2p" / "push" (required `SymmetricGradBucket` mode) or
     "auto": a push-mode `SymmetricGradBucket` (installed as the backward's bucket allocator) when
-    the group is NCCL with world == 2 on CUDA and symmetric memory works - the configuration
-    validated against NCCL - else `GradBucket`."""
+    the group is NCCL with 2, 4 or 8 ranks on CUDA and symmetric memory works (each validated against
+    NCCL's sum by tests/test_exchange_gpu.py and, on every multi-GPU bench run, by bench.py's
+    `exchange_check`) - else `GradBucket`."""
     import os
     import sys
     exchange = os.environ.get("GS_DP_EXCHANGE", exchange)
@@ -220,7 +231,7 @@ def make_grad_bucket(params: Sequence[torch.Tensor], average: bool = False, grou
     params = list(params)
     usable = (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
               and len(params) > 0 and params[0].is_cuda and dist.get_backend(group) == "nccl")
-    if exchange == "auto" and usable and dist.get_world_size(group) != 2:
+    if exchange == "auto" and usable and dist.get_world_size(group) not in (2, 4, 8):
         exchange = "nccl"
     if exchange != "nccl" and usable:
         try:

@@ -41,8 +41,8 @@ def _parse(argv):
     else:
         own, rest = [], argv
     ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
-    ap.add_argument("--train-py", default=os.environ.get("GS_TRAIN_PY", os.path.join(ROOT, "oracle", "_ref", "train.py")),
-                    help="path of the reference's train.py (default: the copy oracle/build_ref.py makes)")
+    ap.add_argument("--train-py", default=os.environ.get("GS_TRAIN_PY", os.path.join(os.getcwd(), "train.py")),
+                    help="path of the reference's train.py (default: $GS_TRAIN_PY, else ./train.py)")
     ap.add_argument("--splatter", default="ours", choices=["ours", "reference"])
     ap.add_argument("--torch-adam", action="store_true", help="keep torch.optim.Adam's update (default: fused FlatAdam)")
     ap.add_argument("--torch-seed", type=int, default=1234)

@@ -62,21 +62,6 @@ METRIC = "render+backward FPS @1080p (2.4M Gaussians)"
 
 
 # ------------------------------------------------------------------------------------------
-def ncu_traffic(workload, kernel):
-    """dram read+write bytes per launch of `kernel` from the committed ncu --set full capture
-    (profiles/<round>_traffic.json; null when that workload was not captured)."""
-    best = None
-    pdir = os.path.join(ROOT, "profiles")
-    for name in sorted(os.listdir(pdir)) if os.path.isdir(pdir) else []:
-        if name.endswith("_traffic.json"):
-            try:
-                d = json.load(open(os.path.join(pdir, name)))
-                best = d.get(workload, {}).get(kernel, best)
-            except Exception:
-                pass
-    return best
-
-
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -229,64 +214,165 @@ def cpu_baseline(workload, n_tiles_sample=12, max_threads=32):
 
 
 # ------------------------------------------------------------------------------------------
+def workload_string(name, n, w, h, colour, fwd_only):
+    """Identical for both arms (the driver compares it): the scene, not its measured statistics."""
+    col = "RGB colour (D=3)" if colour == 3 else f"per-pixel SH colour (D={colour})"
+    return (f"{name}: {n} gaussians, {w}x{h}, {col}, {'forward only' if fwd_only else 'forward+backward'}, "
+            f"one view per GPU (view k = rank mod 8), seed 0 (SURVEY.md §8d generator)")
+
+
+def ncu_metrics(workload, colour, kernel):
+    """Per-launch counters of `kernel` from the committed `ncu --set full` captures
+    (profiles/*_ncu_metrics.json, written by profiles/summarize.py; latest round wins): DRAM traffic,
+    executed warp instructions, MUFU (XU pipe) and FMA pipe utilisation.  None if not captured."""
+    best = None
+    pdir = os.path.join(ROOT, "profiles")
+    for name in sorted(os.listdir(pdir)) if os.path.isdir(pdir) else []:
+        if name.endswith("_ncu_metrics.json"):
+            try:
+                d = json.load(open(os.path.join(pdir, name)))
+                best = d.get(f"{workload}/D{colour}", {}).get(kernel, best)
+            except Exception:
+                pass
+    return best
+
+
+class Scene:
+    """One replica of the benchmark scene on this rank's GPU, driven through the public Splatter API."""
+
+    def __init__(self, workload, colour, dev, exchange="auto", opa_range=(0.05, 0.9)):
+        import dp
+        import splatter
+        import synthetic as S
+        self.n, self.w, self.h, self.fwd_only = WORKLOADS[workload]
+        g = S.make_gaussians(self.n, self.w, self.h, 0, sh_dim=colour, opa_range=opa_range)
+        views = [S.make_view(self.w, self.h, k) for k in range(8)]
+        vd = [dict(width=v.width, height=v.height, focal_x=v.fx, focal_y=v.fy, rot=v.rot, tran=v.tran) for v in views]
+        self.sp = splatter.Splatter.from_tensors(g, vd, device=dev, use_sh_coeff=colour != 3)
+        self.params = list(self.sp.gaussian_3ds.parameters())
+        self.bucket = dp.make_grad_bucket(self.params, exchange=exchange)
+        self.symmetric = isinstance(self.bucket, dp.SymmetricGradBucket)
+        self.go_host = S.make_grad_output(self.h, self.w, 0).pin_memory()
+        self.go_dev = self.go_host.to(dev)
+        self.dev = dev
+
+    def step(self, view_id, exchange=True, go=None):
+        for p in self.params:
+            p.grad = None
+        if self.fwd_only:
+            with torch.no_grad():
+                return self.sp(view_id)
+        img = self.sp(view_id)
+        img.backward(self.go_dev if go is None else go)
+        if exchange:
+            self.bucket.allreduce()
+        return img
+
+
+def exchange_check(sc, view_id, world, dev):
+    """Run on every multi-GPU bench (the driver's GPU-test box has ONE GPU): the gradient bucket summed by the
+    active exchange vs NCCL's all-reduce of the same per-rank gradients (the backward is deterministic, so
+    two backwards of the same frame give identical local gradients), and bit-equality across ranks."""
+    import torch.distributed as dist
+    import renderer
+    renderer.set_flat_grad_allocator(None)                      # plain bucket, no push: local gradients
+    sc.step(view_id, exchange=False)
+    ref = torch.cat([p.grad.flatten() for p in sc.params])
+    dist.all_reduce(ref)
+    if sc.symmetric:
+        renderer.set_flat_grad_allocator(sc.bucket.allocator)
+    sc.step(view_id, exchange=True)
+    got = torch.cat([p.grad.flatten() for p in sc.params])
+    err = (got - ref).abs().max() / ref.abs().max().clamp_min(1e-30)
+    dist.all_reduce(err, op=dist.ReduceOp.MAX)
+    digest = got.view(torch.int32).to(torch.int64).sum().reshape(1)
+    alld = [torch.zeros_like(digest) for _ in range(world)]
+    dist.all_gather(alld, digest)
+    return {"mode": (sc.bucket.mode + ("+multimem.st" if getattr(sc.bucket, "push_mc", False) and sc.bucket.mode == "push" else ""))
+            if sc.symmetric else "nccl",
+            "max_rel_err_vs_nccl": float(err), "bit_equal_across_ranks": bool(all(int(d) == int(alld[0]) for d in alld)),
+            "floats": int(got.numel())}
+
+
 def run_ours(args, world, rank, local):
-    import splatter
-    import synthetic as S
+    import gaussian
     dev = torch.device("cuda", local)
     n, w, h, fwd_only = WORKLOADS[args.workload]
-    g = S.make_gaussians(n, w, h, 0, sh_dim=args.colour)
-    views = [S.make_view(w, h, k) for k in range(8)]
-    vd = [dict(width=v.width, height=v.height, focal_x=v.fx, focal_y=v.fy, rot=v.rot, tran=v.tran) for v in views]
-    sp = splatter.Splatter.from_tensors(g, vd, device=dev, use_sh_coeff=args.colour != 3)
-    params = list(sp.gaussian_3ds.parameters())
-    import dp
-    # N>1: in-place sum of the symmetric gradient bucket the backward writes into, by our own
-    # kernels over NVLink peer memory at N=2 ("push": the projection backward stores the peer's slice
-    # straight into its staging buffer, a finish kernel sums and broadcasts); one NCCL all-reduce of
-    # the same flat bucket at N>=4 (push measured faster there too but is parity-tested at 2 GPUs
-    # only, profiles/r1_exchange.md) or when symmetric memory is unavailable (no-op at N=1)
-    bucket = dp.make_grad_bucket(params, exchange=args.exchange)
-    exchange = "none" if world == 1 else (f"own kernel over symmetric memory ({bucket.mode})"
-                                          if isinstance(bucket, dp.SymmetricGradBucket) else "NCCL all-reduce")
+    sc = Scene(args.workload, args.colour, dev, exchange=args.exchange)
+    sp, params, bucket = sc.sp, sc.params, sc.bucket
+    exchange = "none" if world == 1 else (f"own kernels over symmetric memory ({bucket.mode}"
+                                          f"{', broadcast via multimem.st' if getattr(bucket, 'push_mc', False) and bucket.mode == 'push' else ''})"
+                                          if sc.symmetric else "NCCL all-reduce")
     view_id = rank % 8
-    go_host = S.make_grad_output(h, w, 0).pin_memory()
-    go_dev = go_host.to(dev)
     sp._rctx.set_timing(True)
 
-    def step_resident():
-        for p in params:
-            p.grad = None
-        if fwd_only:
-            with torch.no_grad():
-                sp(view_id)
-        else:
-            img = sp(view_id)
-            img.backward(go_dev)
-            bucket.allreduce()
+    xcheck = None
+    if world > 1 and not fwd_only:
+        xcheck = exchange_check(sc, view_id, world, dev)
 
     # clocks / throttle reasons are sampled DURING the timed region (nvidia-smi -lms 20 in a side
     # process; the sampler is started, and has delivered its first row, before the warm-up)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms = timed_loop(step_resident, args.steps, args.warmup, world, dev)
+    launches0 = None
+
+    def step_resident():
+        sc.step(view_id)
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier(world)
+    launches0 = gaussian.kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_resident()
+    e1.record()
+    barrier(world)
+    launches = gaussian.kernel_launches() - launches0
+    ms_local = e0.elapsed_time(e1) / args.steps
+    ms = max_over_ranks(ms_local, world, dev)
     clocks = sampler.stop() if rank == 0 else {}
 
     # per-stage device times of the last frame (CUDA events on the launching stream)
     stage = sp._rctx.stage_ms()
     st = sp.frame_stats()
 
+    # per-rank compute time without the exchange (separates view imbalance from the collective)
+    compute_ms = ms_local
+    if world > 1 and not fwd_only:
+        import renderer
+        renderer.set_flat_grad_allocator(None)
+        k2 = max(5, args.steps // 4)
+        for _ in range(2):
+            sc.step(view_id, exchange=False)
+        barrier(world)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(k2):
+            sc.step(view_id, exchange=False)
+        c1.record()
+        torch.cuda.synchronize()
+        compute_ms = c0.elapsed_time(c1) / k2
+        if sc.symmetric:
+            renderer.set_flat_grad_allocator(bucket.allocator)
+        barrier(world)
+
     # ---- e2e: host buffers in the timed region -------------------------------------------
     img_host = torch.empty(h, w, 3, dtype=torch.float32).pin_memory()
     copy_stream = torch.cuda.Stream(device=dev)
-    go_stage = torch.empty_like(go_dev)
+    go_stage = torch.empty_like(sc.go_dev)
+    bwd_done = [None]
 
     def step_e2e():
         for p in params:
             p.grad = None
         main = torch.cuda.current_stream(dev)
         with torch.cuda.stream(copy_stream):
-            go_stage.copy_(go_host, non_blocking=True)          # H2D: this step's upstream gradient
+            if bwd_done[0] is not None:
+                copy_stream.wait_event(bwd_done[0])              # the previous backward has read go_stage
+            go_stage.copy_(sc.go_host, non_blocking=True)        # H2D: this step's upstream gradient
             h2d_done = torch.cuda.Event()
             h2d_done.record(copy_stream)
         if fwd_only:
@@ -303,63 +389,190 @@ def run_ours(args, world, rank, local):
             main.wait_event(h2d_done)
             img.backward(go_stage)
             bucket.allreduce()
+            bwd_done[0] = torch.cuda.Event()
+            bwd_done[0].record(main)
         copy_stream.synchronize()
 
-    ms_e2e = timed_loop(step_e2e, args.steps, max(1, args.warmup // 2), world, dev)
+    ms_e2e = timed_loop(step_e2e, args.steps, max(3, args.warmup // 2), world, dev)
 
+    # per-rank record (every rank contributes; rank 0 prints)
+    per_rank = None
+    if world > 1:
+        import torch.distributed as dist
+        mine = torch.tensor([float(view_id), float(st["n_instances"]), float(st["n_instances_eff"]), compute_ms, ms_local],
+                            dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = [{"rank": r, "view": int(t[0]), "tile_instances_M": int(t[1]), "consumed_M_eff": int(t[2]),
+                     "compute_ms": round(float(t[3]), 4), "step_ms": round(float(t[4]), 4),
+                     "exchange_ms": round(float(t[4]) - float(t[3]), 4)} for r, t in enumerate(allr)]
     if rank != 0:
         return None
-    own_exchange = (not fwd_only) and isinstance(bucket, dp.SymmetricGradBucket)
     M, Meff = int(st["n_instances"]), int(st["n_instances_eff"])
+    Meff_b = int(st.get("n_instances_eff_bwd", -1))
+    if Meff_b < 0:
+        Meff_b = Meff
     T = int(st["n_tiles"])
     P = int(st["width_padded"]) * int(st["height_padded"])
     D = args.colour
     peak, peak_src = measured_peak_gbs()
     bf = 4 * (7 + D) * Meff + 12 * P + 4 * (T + 1)
-    bb = 8 * (7 + D) * Meff + 24 * P + 4 * (T + 1)
+    bb = 8 * (7 + D) * Meff_b + 24 * P + 4 * (T + 1)             # the backward's OWN consumed count
     blend_f_ms, blend_b_ms = stage[5], stage[6]
-    roof_kernel = "blend_bwd_kernel" if not fwd_only else "blend_fwd_kernel"
+    roof_kernel = "blend_bwd" if not fwd_only else "blend_fwd"
     alg_bytes, k_ms = (bb, blend_b_ms) if not fwd_only else (bf, blend_f_ms)
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms and k_ms > 0 else None
-    pairs = Meff * 256
+    pairs = (Meff_b if not fwd_only else Meff) * 256
+    ncu = ncu_metrics(args.workload, D, roof_kernel) or {}
+    sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
+    n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+    roof = {"bound": "hbm", "kernel": roof_kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": (achieved / peak) if achieved else None, "traffic": ncu.get("dram_bytes"),
+            "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full)",
+            "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+            # the roof that actually binds: instruction issue (4 warp-instructions / clk / SM) and MUFU (16 / clk / SM)
+            "binding": "issue",
+            "pairs_per_launch": pairs, "pairs_per_s": pairs / (k_ms * 1e-3) if k_ms and k_ms > 0 else None,
+            "pairs_per_clk_per_sm": pairs / (k_ms * 1e-3 * sm_hz * n_sm) if k_ms and k_ms > 0 else None,
+            "issue_frac": ncu.get("issue_active_frac"), "mufu_frac": ncu.get("xu_pipe_frac"),
+            "fma_pipe_frac": ncu.get("fma_pipe_frac"), "warp_inst_per_launch": ncu.get("warp_inst"),
+            "thread_inst_per_pair": (ncu["warp_inst"] * 32.0 / ncu["pairs"]) if ncu.get("warp_inst") and ncu.get("pairs") else None,
+            "ncu_source": ncu.get("source"),
+            "note": "blend is instruction-issue / MUFU bound, not HBM bound (SURVEY.md §8d): the HBM fraction is reported "
+                    "because the metric asks for it; issue_frac / mufu_frac come from the committed ncu capture of this "
+                    "workload (null if not captured), pairs_per_s is measured live",
+            "blend_fwd": {"ms": blend_f_ms, "algorithmic_bytes": bf,
+                          "achieved": bf / (blend_f_ms * 1e-3) / 1e9 if blend_f_ms > 0 else None},
+            "blend_bwd": {"ms": blend_b_ms, "algorithmic_bytes": bb,
+                          "achieved": bb / (blend_b_ms * 1e-3) / 1e9 if blend_b_ms > 0 else None}}
     out = {
         "metric": METRIC if args.workload == "C3" else f"render{'' if fwd_only else '+backward'} FPS ({args.workload})",
         "value": world * 1000.0 / ms, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {n} gaussians, {w}x{h}, " + ("RGB colour (D=3), " if D == 3 else f"per-pixel SH colour (D={D}), ") +
-                               f"{'forward only' if fwd_only else 'forward+backward'}, one view per GPU "
-                               f"(view k = rank mod 8), seed 0 (SURVEY.md §8d generator)",
-                   "tile_instances_M": M, "tile_instances_consumed_M_eff": Meff, "max_tile_count": st["max_tile_count"],
+        "config": {"workload": workload_string(args.workload, n, w, h, D, fwd_only),
+                   "tile_instances_M": M, "tile_instances_consumed_M_eff": Meff, "consumed_by_backward": Meff_b,
+                   "max_tile_count": st["max_tile_count"],
                    "n_visible": st["n_visible"], "l2": "inputs larger than L2 (per-frame working set "
                                                        f"{(M * 112 + n * 56) / 1e6:.0f} MB >> 126 MB)",
                    "parallelism": f"dp{world} over views, gradient bucket exchange: {exchange}"},
         "clocks": clocks,
         "e2e": {"value": world * 1000.0 / ms_e2e, "unit": "frames/s", "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": int(go_host.numel() * 4 + 48), "d2h_bytes_per_step": int(img_host.numel() * 4),
+                "h2d_bytes_per_step": int(sc.go_host.numel() * 4 + 48), "d2h_bytes_per_step": int(img_host.numel() * 4),
                 "api": "Splatter.forward(camera_id) + image.backward(grad) with pinned host grad / image buffers"},
-        "gpu_launches": int(((4 if fwd_only else 6) + int(own_exchange)) * args.steps),
-        "gpu_launches_note": "our kernels per step: fused_project, emit_keys, pack_sorted, blend_fwd"
-                             + ("" if fwd_only else ", blend_bwd, fused_project_bwd")
-                             + (", exchange kernel (push finish / p2p / multimem)" if own_exchange else "") +
-                             "; plus CUB scan (2) and onesweep radix sort (8) library kernels",
+        "gpu_launches": int(launches),
+        "gpu_launches_note": "kernels of libgs_b200 launched by rank 0 inside the timed region, counted by the library "
+                             "(gs_kernel_launches); CUB scan / onesweep sort kernels are library code and not counted",
         "stage_ms": dict(zip(["project", "depth_sort+scan+readback", "emit_keys", "tile_sort", "pack", "blend_fwd",
                               "blend_bwd", "project_bwd"], [round(x, 4) for x in stage])),
-        "roofline": {"bound": "hbm", "kernel": roof_kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": (achieved / peak) if achieved else None, "traffic": ncu_traffic(args.workload, roof_kernel) if D == 3 else None,
-                     "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full)",
-                     "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": alg_bytes,
-                     "note": "blend is FP32/MUFU-issue bound, not HBM bound (SURVEY.md §8d): "
-                             f"{pairs / 1e9:.2f} G pixel-instance pairs upper bound per launch",
-                     "blend_fwd": {"ms": blend_f_ms, "algorithmic_bytes": bf,
-                                   "achieved": bf / (blend_f_ms * 1e-3) / 1e9 if blend_f_ms > 0 else None},
-                     "blend_bwd": {"ms": blend_b_ms, "algorithmic_bytes": bb,
-                                   "achieved": bb / (blend_b_ms * 1e-3) / 1e9 if blend_b_ms > 0 else None}},
+        "stage_ms_note": "one frame (the last resident step) on rank 0, CUDA events recorded by the library",
+        "roofline": roof,
     }
+    if xcheck is not None:
+        out["exchange_check"] = xcheck
+    if per_rank is not None:
+        out["per_rank"] = per_rank
+    if world == 1 and args.workload == "C3" and D == 3 and not args.no_extra_legs:
+        out["sh"] = sh_legs(dev)
+        out["opaque_scene"] = opaque_leg(dev, peak)
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args.workload)
     return out
+
+
+def _short_leg(sc, steps=10, warmup=3):
+    for _ in range(warmup):
+        sc.step(0)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        sc.step(0)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def sh_legs(dev):
+    """BASELINE configs[2] as written ("SH degree 3") and the reference's own SH (degree 2): short 10-step
+    legs of the same C3 scene with per-pixel SH colour; D=27 also times the reference's CUDA build here."""
+    import gc
+    res = {}
+    for D in (27, 48):
+        sc = Scene("C3", D, dev)
+        sc.sp._rctx.set_timing(True)
+        ms = _short_leg(sc)
+        stage = sc.sp._rctx.stage_ms()
+        leg = {"value": 1000.0 / ms, "unit": "frames/s", "ms_per_step": ms, "steps": 10, "warmup": 3,
+               "blend_fwd_ms": round(stage[5], 4), "blend_bwd_ms": round(stage[6], 4), "pack_ms": round(stage[4], 4)}
+        del sc
+        gc.collect()
+        torch.cuda.empty_cache()
+        if D == 27:
+            try:
+                ref_ms = reference_ms("C3", 27, dev, steps=3, warmup=1)
+                if ref_ms:
+                    leg["reference_ms_per_step"] = ref_ms
+                    leg["vs_reference"] = ref_ms / ms
+            except Exception as e:                    # the reference arm is optional here
+                leg["reference_error"] = str(e)[:200]
+        res[str(D)] = leg
+    return res
+
+
+def opaque_leg(dev, peak):
+    """SURVEY.md §8d lever 3: the same C3 geometry with opacities in [0.5, 0.99] - pixels saturate after a few
+    instances, the regime where the blend IS closer to HBM-bound; reports its HBM fraction."""
+    import gc
+    sc = Scene("C3", 3, dev, opa_range=(0.5, 0.99))
+    sc.sp._rctx.set_timing(True)
+    ms = _short_leg(sc)
+    stage = sc.sp._rctx.stage_ms()
+    st = sc.sp.frame_stats()
+    T, P = int(st["n_tiles"]), int(st["width_padded"]) * int(st["height_padded"])
+    mf, mb = int(st["n_instances_eff"]), int(st.get("n_instances_eff_bwd", st["n_instances_eff"]))
+    bf = 40 * mf + 12 * P + 4 * (T + 1)
+    bb = 80 * mb + 24 * P + 4 * (T + 1)
+    out = {"opacity_range": [0.5, 0.99], "ms_per_step": ms, "tile_instances_M": int(st["n_instances"]),
+           "consumed_M_eff": mf, "consumed_by_backward": mb,
+           "blend_fwd": {"ms": stage[5], "achieved_GBps": bf / (stage[5] * 1e-3) / 1e9, "frac_of_hbm_peak": bf / (stage[5] * 1e-3) / 1e9 / peak},
+           "blend_bwd": {"ms": stage[6], "achieved_GBps": bb / (stage[6] * 1e-3) / 1e9, "frac_of_hbm_peak": bb / (stage[6] * 1e-3) / 1e9 / peak}}
+    del sc
+    gc.collect()
+    torch.cuda.empty_cache()
+    return out
+
+
+def reference_ms(workload, colour, dev, steps, warmup):
+    """ms per step of the reference's CUDA build on this GPU (None when oracle/_ref is absent)."""
+    import ref_pipeline
+    import synthetic as S
+    n, w, h, fwd_only = WORKLOADS[workload]
+    gref, rref = ref_pipeline.load_reference()
+    if gref is None:
+        return None
+    g = S.make_gaussians(n, w, h, 0, sh_dim=colour)
+    v = S.make_view(w, h, 0)
+    frame = ref_pipeline.LegacyFrame(gref, rref, w, h, v.fx, v.fy, v.rot.to(dev), v.tran.to(dev), use_sh_coeff=colour != 3)
+    p = {k: t.to(dev).clone().requires_grad_(True) for k, t in g.items()}
+    go = S.make_grad_output(h, w, 0).to(dev)
+
+    def step():
+        for t in p.values():
+            t.grad = None
+        img = frame(p["pos"], p["rgb"], p["opa"], p["quat"], p["scale"])
+        img.backward(go)
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
 
 
 def run_reference(args, world, rank, local):
@@ -407,8 +620,7 @@ def run_reference(args, world, rank, local):
             "value": fps, "unit": "frames/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {n} gaussians, {w}x{h}, {'RGB' if args.colour == 3 else 'SH-27'}, "
-                                   f"{'forward only' if fwd_only else 'forward+backward'}, view 0",
+            "config": {"workload": workload_string(args.workload, n, w, h, args.colour, fwd_only),
                        "impl": "reference CUDA build (oracle/_ref: unmodified gaussian.cu + bindings.cpp + renderer.py, "
                                "-std=c++17 flag only) driven with the call sequence of reference splatter.py:513-655",
                        "tile_instances_M": frame.aux.get("n_instances"), "max_tile_count": frame.aux.get("max_tile"),
@@ -433,9 +645,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-legs", action="store_true",
+                    help="skip the short SH (D=27, 48) and opaque-scene legs of the default N=1 C3 run")
     ap.add_argument("--exchange", default="auto", choices=["auto", "multimem", "p2p", "push", "nccl"],
                     help="N>1 gradient exchange: own push / p2p / multimem kernels on a symmetric bucket, NCCL all-reduce, "
-                         "or auto (push at N=2, NCCL otherwise)")
+                         "or auto (push at N = 2, 4, 8; NCCL otherwise)")
     ap.add_argument("--colour", type=int, default=3, choices=[3, 27, 48],
                     help="3 = RGB (default; the reference's published 2.4M point), 27 = per-pixel SH degree 2 "
                          "(the reference's use_sh_coeff), 48 = SH degree 3 extension")

@@ -33,6 +33,9 @@ typedef void* gs_stream_t; /* cudaStream_t */
 int gs_abi_version(void);
 /* Human-readable text of the last error on this host thread ("" if none). */
 const char* gs_last_error(void);
+/* Number of kernels of THIS library launched by the process so far (library kernels such as CUB's are not
+ * counted); bench.py reports the difference over its timed region as `gpu_launches`. */
+unsigned long long gs_kernel_launches(void);
 
 /* ---------------------------------------------------------------------------------------
  * Legacy per-stage entry points == the reference's `gaussian` module functions.
@@ -127,6 +130,7 @@ typedef struct gs_frame_info {
                               /*        of their tile saturated (filled by forward)      */
   int width_padded, height_padded, n_tiles;
   int max_tile_count;
+  long long n_instances_eff_bwd; /* instances the last BACKWARD consumed (sub-chunk granular); -1 if none ran */
 } gs_frame_info;
 
 /* scale_activation: 0 = abs()+1e-4 (splatter.py:521), 1 = trunc_exp (splatter.py:524). */
@@ -271,6 +275,11 @@ typedef struct gs_grad_push {
 int gs_ctx_set_grad_push(gs_ctx* ctx, const gs_grad_push* push);
 int gs_allreduce_push_finish_f32(void* const* peer_buckets, const float* staging_local, long long n_floats,
                                  long long per, int rank, int world, gs_stream_t stream);
+/* The same second half with the broadcast done by the NVSwitch: the sum of rank r's slice is written once
+ * through `bucket_multicast` (the NVLS multicast address of the symmetric bucket; `bucket_local` is this
+ * rank's own mapping of it) with multimem.st and lands in all `world` buckets. */
+int gs_allreduce_push_finish_mc_f32(void* bucket_multicast, const float* bucket_local, const float* staging_local,
+                                    long long n_floats, long long per, int rank, int world, gs_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     for s in _declared_symbols():
         assert hasattr(lib, s), f"libgs_b200.so does not export {s}"
     lib.gs_abi_version.restype = ctypes.c_int
-    assert lib.gs_abi_version() == 1
+    assert lib.gs_abi_version() == 2
     lib.gs_draw_workspace_bytes.restype = ctypes.c_size_t
     assert lib.gs_draw_workspace_bytes(0, 3) >= 0
     assert lib.gs_draw_workspace_bytes(1000, 3) >= 1000 * (16 + 16 + 8 + 48)

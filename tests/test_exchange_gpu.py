@@ -54,10 +54,7 @@ def _worker(rank, world, port, q):
         worst, same = 0.0, True
         for mode in ("p2p", "multimem", "push", "auto"):
             got, b = grads(lambda ps: dp.make_grad_bucket(ps, exchange=mode))
-            if mode == "auto" and world != 2:            # auto keeps NCCL beyond 2 ranks
-                assert type(b) is dp.GradBucket, type(b)
-            else:
-                assert isinstance(b, dp.SymmetricGradBucket) and b.mode == ("push" if mode == "auto" else mode), b.mode
+            assert isinstance(b, dp.SymmetricGradBucket) and b.mode == ("push" if mode == "auto" else mode), b.mode
             renderer.set_flat_grad_allocator(None)
             for a, r in zip(got, ref):
                 worst = max(worst, float((a - r).abs().max() / (r.abs().max() + 1e-30)))

@@ -81,7 +81,7 @@ def test_reference_train_py_runs_unchanged(gs, cuda, tmp_path, which):
     data = str(tmp_path / "data")
     n_points = make_colmap_dataset(data, cuda)
     exp = str(tmp_path / f"exp_{which}")
-    r = _run([sys.executable, LAUNCH, "--splatter", which, "--", "--data", data, "--exp", exp] + TRAIN_ARGS, str(tmp_path))
+    r = _run([sys.executable, LAUNCH, "--train-py", TRAIN_PY, "--splatter", which, "--", "--data", data, "--exp", exp] + TRAIN_ARGS, str(tmp_path))
     ckpt = _check_outputs(exp, n_points)
     # the run really optimised: PSNR on the test split rose between iteration 0 and 60
     psnrs = [float(l.split(":")[1]) for l in r.stdout.splitlines() if l.startswith("TEST SPLIT PSNR")]
@@ -111,7 +111,7 @@ def test_reference_train_py_data_parallel(gs, cuda, tmp_path):
                       ("--n_adaptive_control", "100")):
         args[args.index(name) + 1] = val
     _run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
-          "127.0.0.1", "--master-port", str(port), LAUNCH, "--", "--data", data, "--exp", exp, "--use_clone", "1",
+          "127.0.0.1", "--master-port", str(port), LAUNCH, "--train-py", TRAIN_PY, "--", "--data", data, "--exp", exp, "--use_clone", "1",
           "--grad_thresh", "0.00001"] + args, str(tmp_path), timeout=900)
     c0 = torch.load(os.path.join(exp, "ckpt.pth"), map_location="cpu", weights_only=False)
     c1 = torch.load(os.path.join(exp + "_rank1", "ckpt.pth"), map_location="cpu", weights_only=False)
