@@ -466,6 +466,45 @@ std::tuple<torch::Tensor, torch::Tensor> loss_l1_ssim(torch::Tensor image, torch
   return {out3, grad};
 }
 
+// densification: returns the five new parameter tensors + (n_deleted, n_clone, n_split)
+std::tuple<std::vector<torch::Tensor>, std::vector<int64_t>> densify(
+    torch::Tensor pos, torch::Tensor rgb, torch::Tensor opa, torch::Tensor quat, torch::Tensor scale, torch::Tensor grad,
+    int scale_activation, double opa_logit_min, double delete_thresh, double grad_thresh, bool grad_agg_max, double tau,
+    bool use_clone, bool use_split, double clone_dt, c10::optional<at::Generator> gen) {
+  GS_CHECK_F32(pos); GS_CHECK_F32(rgb); GS_CHECK_F32(opa); GS_CHECK_F32(quat); GS_CHECK_F32(scale); GS_CHECK_F32(grad);
+  const int64_t n = pos.size(0);
+  TORCH_CHECK(pos.dim() == 2 && pos.size(1) == 3 && rgb.dim() == 2 && rgb.size(0) == n && opa.numel() == n &&
+                  quat.numel() == 4 * n && scale.numel() == 3 * n && grad.numel() == 3 * n && n < (int64_t(1) << 31),
+              "densify: bad shapes");
+  c10::cuda::CUDAGuard guard(pos.device());
+  auto bopt = pos.options().dtype(at::kByte);
+  auto code = torch::empty({n + 1}, bopt);
+  auto dst = torch::empty({3, n + 1}, pos.options().dtype(at::kInt));
+  auto ws = torch::empty({(int64_t)gs_densify_workspace_bytes((int)n)}, bopt);
+  check_rc(gs_densify_plan(fp(opa), fp(scale), fp(grad), (int)n, scale_activation, (float)opa_logit_min,
+                           (float)delete_thresh, (float)grad_thresh, grad_agg_max ? 1 : 0, (float)tau, use_clone ? 1 : 0,
+                           use_split ? 1 : 0, code.data_ptr<uint8_t>(), dst.data_ptr<int>(), ws.data_ptr(),
+                           (size_t)ws.numel(), cur_stream()),
+           "gs_densify_plan");
+  int64_t nk = n, nc = 0, nsp = 0;
+  if (n > 0) {
+    auto tot = dst.index({torch::indexing::Slice(), n}).cpu();        // the one host sync: sizes of the new arrays
+    nk = tot[0].item<int>(); nc = tot[1].item<int>(); nsp = tot[2].item<int>();
+  }
+  const int64_t m = nk + nc + nsp;
+  const int64_t d = rgb.size(1);
+  auto z = torch::randn({2, nsp, 3}, gen, pos.options());              // torch's generator: identical on every DP rank
+  std::vector<torch::Tensor> out = {torch::empty({m, 3}, pos.options()), torch::empty({m, d}, pos.options()),
+                                    torch::empty({m}, pos.options()), torch::empty({m, 4}, pos.options()),
+                                    torch::empty({m, 3}, pos.options())};
+  check_rc(gs_densify_apply(fp(pos), fp(rgb), fp(opa), fp(quat), fp(scale), (int)n, (int)d, code.data_ptr<uint8_t>(),
+                            dst.data_ptr<int>(), fp(grad), (float)clone_dt, fp(z), (int)nk, (int)nc, (int)nsp,
+                            scale_activation, fpm(out[0]), fpm(out[1]), fpm(out[2]), fpm(out[3]), fpm(out[4]),
+                            cur_stream()),
+           "gs_densify_apply");
+  return {out, {n - nk, nc, nsp}};
+}
+
 // NVLS in-place all-reduce of a symmetric flat buffer (multicast address as an integer)
 void allreduce_multimem(int64_t multicast_ptr, int64_t n_floats, int rank, int world, int device) {
   c10::cuda::CUDAGuard guard(c10::Device(c10::kCUDA, (c10::DeviceIndex)device));
@@ -562,6 +601,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         "second half of the pushed gradient exchange, broadcast through the NVSwitch (multimem.st)");
   m.def("allreduce_p2p", &allreduce_p2p, "peer-to-peer two-shot in-place all-reduce of a symmetric buffer");
   m.def("allreduce_multimem", &allreduce_multimem, "NVLS multimem in-place all-reduce of a symmetric buffer");
+  m.def("densify", &densify, "prune / clone / split on the device (reference splatter.py:122-228)", py::arg("pos"),
+        py::arg("rgb"), py::arg("opa"), py::arg("quat"), py::arg("scale"), py::arg("grad"), py::arg("scale_activation"),
+        py::arg("opa_logit_min"), py::arg("delete_thresh"), py::arg("grad_thresh"), py::arg("grad_agg_max"), py::arg("tau"),
+        py::arg("use_clone"), py::arg("use_split"), py::arg("clone_dt"), py::arg("generator") = py::none());
   m.def("loss_l1_ssim", &loss_l1_ssim, "fused L1 + SSIM loss, forward + image gradient (CUDA)");
   m.def("adam_step", &adam_step, "fused Adam over flat parameter / gradient buffers (CUDA)");
   m.def("kernel_launches", []() { return (int64_t)gs_kernel_launches(); },

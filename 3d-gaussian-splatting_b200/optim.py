@@ -62,7 +62,14 @@ class FlatAdam:
             p.data = view                                   # the Parameter now aliases the flat buffer
             nxt = ordered[i + 1].grad.storage_offset() - base if i + 1 < len(ordered) else total
             ends.append(nxt)
-        self._flat = (flat, torch.zeros_like(flat), torch.zeros_like(flat), ordered, ends, base)
+        m, v = torch.zeros_like(flat), torch.zeros_like(flat)
+        resume = getattr(self, "_resume", None)          # moments restored by checkpoint.load_checkpoint
+        if resume is not None and resume[0] is not None and resume[0].numel() == flat.numel():
+            m.copy_(resume[0])
+            v.copy_(resume[1])
+            self._keep_step = True
+        self._resume = None
+        self._flat = (flat, m, v, ordered, ends, base)
 
     @torch.no_grad()
     def step(self):
@@ -80,7 +87,9 @@ class FlatAdam:
         if self._flat is None or len(self._flat[3]) != len(ordered) or any(a is not b for a, b in zip(self._flat[3], ordered)) \
                 or any(p.data.untyped_storage().data_ptr() != self._flat[0].untyped_storage().data_ptr() for p in ordered):
             self._build(ordered)
-            self.step_count = 0
+            if not getattr(self, "_keep_step", False):
+                self.step_count = 0
+            self._keep_step = False
         flat, m, v, _, ends, _ = self._flat
         base = g0.storage_offset()
         gflat = torch.empty(0, dtype=torch.float32, device=g0.device).set_(g0.untyped_storage(), base, (flat.numel(),))

@@ -69,55 +69,29 @@ class Gaussian3ds(nn.Module):
 
     @torch.no_grad()
     def adaptive_control(self, grad, taus, delete_thresh, scale_activation="abs", grad_thresh=0.0002,
-                         grad_aggregation="max", use_clone=True, use_split=True, clone_dt=0.01):
-        """Prune / clone / split (reference splatter.py:122-228): delete Gaussians with opacity
-        below sigmoid^-1(0.02) or a scale norm above `delete_thresh`; where the accumulated position
-        gradient exceeds `grad_thresh`, clone the small ones (moved against the gradient) and split
-        the large ones (scale / 1.6, two positions sampled from the Gaussian itself).  Parameters
-        are re-created, so the caller rebuilds its optimizer (train.py:173-181)."""
-        if scale_activation == "abs":
-            norm = self.scale.norm(dim=-1)
-        elif scale_activation == "exp":
-            norm = self.scale.exp().norm(dim=-1)
-        else:
+                         grad_aggregation="max", use_clone=True, use_split=True, clone_dt=0.01, generator=None):
+        """Prune / clone / split (reference splatter.py:122-228, same signature as train.py:160-171 calls it):
+        delete Gaussians with opacity below sigmoid^-1(0.02) or a scale norm above `delete_thresh`; where the
+        accumulated position gradient exceeds `grad_thresh`, clone the small ones (moved against the gradient)
+        and split the large ones (scale / 1.6, two positions sampled from the un-shrunk Gaussian itself).
+        Runs on the device (`gaussian.densify`: classify -> scans -> one kernel that writes the new arrays);
+        the split samples come from torch's CUDA generator, so data-parallel replicas that seed torch
+        identically stay identical.  Parameters are re-created: the caller rebuilds its optimizer
+        (train.py:173-181)."""
+        if scale_activation not in ("abs", "exp"):
             raise ValueError("scale_activation must be 'abs' or 'exp'")
-        keep = (self.opa > inverse_sigmoid(0.02)) & (norm < delete_thresh)
-        pos, rgb, opa, quat, scale = (t.detach()[keep].clone()
-                                      for t in (self.pos, self.rgb, self.opa, self.quat, self.scale))
-        grad = grad[keep]
-        n_deleted = int((~keep).sum())
-        agg = grad.abs().max(-1)[0] if grad_aggregation == "max" else grad.abs().mean(-1)
-        densify = agg > grad_thresh
-        new = [[pos], [rgb], [opa], [quat], [scale]]
-        n_clone = n_split = 0
-        if bool(densify.any()):
-            norm = scale.norm(dim=-1) if scale_activation == "abs" else scale.exp().norm(dim=-1)
-            split_mask = (norm > taus) & densify
-            clone_mask = (norm <= taus) & densify
-            if use_clone and bool(clone_mask.any()):
-                n_clone = int(clone_mask.sum())
-                for lst, t in zip(new, (pos[clone_mask] - grad[clone_mask] * clone_dt, rgb[clone_mask],
-                                        opa[clone_mask], quat[clone_mask], scale[clone_mask])):
-                    lst.append(t.clone())
-            if use_split and bool(split_mask.any()):
-                n_split = int(split_mask.sum())
-                # the two positions are drawn from the ORIGINAL (un-shrunk) Gaussian: the reference builds
-                # the covariance from self.scale (splatter.py:204-205) and only the stored scale is / 1.6
-                R = quat_to_rotmat(quat[split_mask])
-                s = scale[split_mask].abs() + EPS if scale_activation == "abs" else torch.exp(scale[split_mask])
-                RS = R * s.unsqueeze(-2)
-                cov = RS @ RS.transpose(-1, -2)
-                dist = torch.distributions.MultivariateNormal(pos[split_mask], cov)      # utils.py:391-402
-                p1, p2 = dist.sample(), dist.sample()
-                if scale_activation == "abs":
-                    scale[split_mask] /= 1.6
-                else:
-                    scale[split_mask] -= math.log(1.6)
-                pos[split_mask] = p1
-                for lst, t in zip(new, (p2, rgb[split_mask], opa[split_mask], quat[split_mask], scale[split_mask])):
-                    lst.append(t.clone())
-        self.pos, self.rgb, self.opa, self.quat, self.scale = (nn.Parameter(torch.cat(l).contiguous()) for l in new)
-        return dict(deleted=n_deleted, cloned=n_clone, split=n_split, total=self.pos.shape[0])
+        if grad_aggregation not in ("max", "mean"):
+            raise ValueError("grad_aggregation must be 'max' or 'mean'")
+        g = grad.detach()
+        if g.dtype != torch.float32 or not g.is_contiguous():
+            g = g.float().contiguous()
+        args = [t.detach().contiguous() for t in (self.pos, self.rgb, self.opa, self.quat, self.scale)]
+        new, (n_deleted, n_clone, n_split) = gaussian.densify(
+            *args, g, 0 if scale_activation == "abs" else 1, inverse_sigmoid(0.02), float(delete_thresh),
+            float(grad_thresh), grad_aggregation == "max", float(taus), bool(use_clone), bool(use_split),
+            float(clone_dt), generator)
+        self.pos, self.rgb, self.opa, self.quat, self.scale = (nn.Parameter(t) for t in new)
+        return dict(deleted=int(n_deleted), cloned=int(n_clone), split=int(n_split), total=self.pos.shape[0])
 
 
 class Tiles:
@@ -178,7 +152,7 @@ class Splatter(nn.Module):
         else:
             params = self._load_colmap(colmap_path, image_path, opa_init_value, scale_init_value)
         if load_ckpt is not None:                                   # reference splatter.py:417-424
-            ckpt = torch.load(load_ckpt, map_location="cpu")
+            ckpt = torch.load(load_ckpt, map_location="cpu", weights_only=False)   # nn.Parameters, train.py:284-290
             params = {k: ckpt[k].detach() for k in ("pos", "rgb", "opa", "quat", "scale")}
         if self.use_sh_coeff != (params["rgb"].shape[1] != 3):
             raise ValueError("use_sh_coeff must match the colour width (3 = RGB logits, 27 / 48 = SH)")
@@ -314,6 +288,11 @@ class Splatter(nn.Module):
         self.set_camera(camera_id, extrinsics, intrinsics)
         padded = self.render_padded()
         return self.tile_info.crop(torch.clamp(padded, 0, 1))
+
+    def save_checkpoint(self, path, optimizer=None, iteration=None, trainer_state=None):
+        """reference Trainer.save_checkpoint (train.py:283-291) + resume state; see checkpoint.py."""
+        import checkpoint
+        return checkpoint.save_checkpoint(self, path, optimizer, iteration, trainer_state)
 
     def frame_stats(self):
         s = self._rctx.stats()

@@ -219,6 +219,28 @@ int gs_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg
                  const long long* seg_end_host, const float* lr_host, int n_seg, float beta1, float beta2,
                  float eps, int step, gs_stream_t stream);
 
+/* Densification on the device (reference splatter.py:122-228 `adaptive_control`, called
+ * from train.py:156-172): prune Gaussians with opacity logit <= opa_logit_min or activated-scale norm >=
+ * delete_thresh; of the kept ones whose aggregated |grad| (max or mean over xyz) exceeds grad_thresh, CLONE the
+ * small ones (norm <= tau; the copy is moved by -grad * clone_dt) and SPLIT the large ones (scale / 1.6, or
+ * - log 1.6 for the exp activation; both halves re-positioned at pos + R (s_act * z), z ~ N(0, I) supplied by the
+ * caller so that data-parallel replicas draw identical samples).
+ *   gs_densify_plan : code[n+1] (bit0 keep, bit1 clone, bit2 split) and dst[3][n+1] = exclusive scans of the
+ *                     three flags (dst[b][n] = totals: n_keep, n_clone, n_split).  No synchronisation.
+ *   gs_densify_apply: writes the n_keep + n_clone + n_split rows of the new parameter arrays, laid out like the
+ *                     reference's torch.cat: kept (in order), clones (in order), second split samples (in order).
+ *                     normals: [2][n_split][3].  Output arrays are caller-allocated. */
+size_t gs_densify_workspace_bytes(int n);
+int gs_densify_plan(const float* opa, const float* scale, const float* grad, int n, int scale_activation,
+                    float opa_logit_min, float delete_thresh, float grad_thresh, int grad_agg_max, float tau,
+                    int use_clone, int use_split, unsigned char* code, int* dst, void* workspace,
+                    size_t workspace_bytes, gs_stream_t stream);
+int gs_densify_apply(const float* pos, const float* rgb, const float* opa, const float* quat, const float* scale,
+                     int n, int d, const unsigned char* code, const int* dst, const float* grad, float clone_dt,
+                     const float* normals, int n_keep, int n_clone, int n_split, int scale_activation,
+                     float* out_pos, float* out_rgb, float* out_opa, float* out_quat, float* out_scale,
+                     gs_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------
  * Next-row widening: the training loss of reference train.py:99-107 on the device,
  * forward and backward in two kernels, producing the image gradient in the layout

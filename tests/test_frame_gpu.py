@@ -515,3 +515,98 @@ def test_fused_flat_adam_matches_torch_adam(gs, cuda):
         assert rel_err(pa[k], pb[k]) < 2e-6, k
     # the parameters now alias one flat buffer, in bucket order
     assert pa["pos"].data.untyped_storage().data_ptr() == pa["scale"].data.untyped_storage().data_ptr()
+
+
+def test_checkpoint_schema_and_exact_resume(gs, cuda, tmp_path):
+    """§8 f-4: `save_checkpoint` writes the reference's five keys (train.py:283-291) + resume state; training
+    N steps, saving, training M more == loading into a fresh scene + optimizer and training M steps, bit for bit;
+    a reference-style file (five keys only) loads too."""
+    import checkpoint
+    import optim
+    import splatter
+    n, w, h = 3000, 128, 96
+    g, v, cam = scene(n, w, h, k=0)
+    teacher, _, _ = scene(n, w, h, seed=3, k=0)
+    vd = [dict(width=v.width, height=v.height, focal_x=v.fx, focal_y=v.fy, rot=v.rot, tran=v.tran)]
+    with torch.no_grad():
+        gt = splatter.Splatter.from_tensors(teacher, vd, device=cuda)(0)
+
+    def make(gauss):
+        sp = splatter.Splatter.from_tensors(gauss, vd, device=cuda)
+        g3 = sp.gaussian_3ds
+        opt = optim.FlatAdam([{"params": g3.opa, "lr": 0.03}, {"params": g3.rgb, "lr": 0.03}, {"params": g3.pos, "lr": 0.003},
+                              {"params": g3.scale, "lr": 0.003}, {"params": g3.quat, "lr": 0.003}], betas=(0.9, 0.99))
+        return sp, opt
+
+    def train(sp, opt, steps):
+        for _ in range(steps):
+            opt.zero_grad()
+            (sp(0) - gt).abs().mean().backward()
+            opt.step()
+
+    sp, opt = make(g)
+    train(sp, opt, 5)
+    path = str(tmp_path / "exp" / "ckpt.pth")
+    sp.save_checkpoint(path, optimizer=opt, iteration=5, trainer_state={"grad_counter": 3})
+    train(sp, opt, 4)
+    want = {k: getattr(sp.gaussian_3ds, k).detach().clone() for k in checkpoint.KEYS}
+
+    raw = torch.load(path, map_location="cpu", weights_only=False)
+    assert [k for k in raw if k != "resume"] == list(checkpoint.KEYS) and raw["pos"].shape == (n, 3)
+    assert raw["resume"]["iteration"] == 5 and raw["resume"]["trainer"]["grad_counter"] == 3
+
+    sp2, opt2 = make(g)
+    checkpoint.load_checkpoint(path, sp2, None)
+    sp2b, opt2 = make({k: getattr(sp2.gaussian_3ds, k).detach().cpu() for k in checkpoint.KEYS})
+    checkpoint.load_checkpoint(path, None, opt2)
+    train(sp2b, opt2, 4)
+    for k in checkpoint.KEYS:
+        assert torch.equal(getattr(sp2b.gaussian_3ds, k).detach(), want[k]), k
+
+    # a file as the reference writes it (train.py:284-291: the nn.Parameters, nothing else) loads as well
+    ref_style = str(tmp_path / "ref_ckpt.pth")
+    torch.save({k: getattr(sp.gaussian_3ds, k) for k in ("pos", "opa", "rgb", "quat", "scale")}, ref_style)
+    sp3 = splatter.Splatter(g, vd, device=cuda, tile_culling_prob_thresh=0.05, load_ckpt=ref_style)
+    assert torch.equal(sp3.gaussian_3ds.pos.detach(), want["pos"])
+    assert checkpoint.load_checkpoint(ref_style, sp3).get("resume") is None
+
+
+@pytest.mark.parametrize("act,agg,sh", [("abs", "max", 3), ("exp", "mean", 27)])
+def test_densification_kernel_vs_oracle(gs, cuda, act, agg, sh):
+    """§8 f-2: `Gaussian3ds.adaptive_control` (device kernels) == the torch restatement of reference
+    splatter.py:122-228 given the same normals, element for element, incl. layout and counts."""
+    import densify_oracle as DO
+    import splatter
+    n, w, h = 5000, 128, 96
+    g, v, cam = scene(n, w, h, k=0, sh_dim=sh)
+    if act == "exp":
+        g["scale"] = torch.log(g["scale"])
+    gen = torch.Generator().manual_seed(7)
+    g["opa"] = g["opa"] - 3.0 * (torch.rand(n, generator=gen) < 0.2)          # some below the prune threshold
+    g["scale"][::50] = 2.0 if act == "abs" else 1.0                              # some above delete_thresh
+    grad = torch.randn(n, 3, generator=gen) * 3e-4
+    vd = [dict(width=v.width, height=v.height, focal_x=v.fx, focal_y=v.fy, rot=v.rot, tran=v.tran)]
+    sp = splatter.Splatter.from_tensors(g, vd, device=cuda, use_sh_coeff=sh != 3, scale_activation=act)
+    norm = (g["scale"].norm(dim=-1) if act == "abs" else g["scale"].exp().norm(dim=-1))
+    tau = float(norm.median())
+    torch.cuda.manual_seed(123)
+    info = sp.gaussian_3ds.adaptive_control(grad.to(cuda), taus=tau, delete_thresh=1.5, scale_activation=act,
+                                            grad_thresh=2e-4, grad_aggregation=agg, use_clone=True, use_split=True,
+                                            clone_dt=0.01)
+    torch.cuda.manual_seed(123)
+    z = torch.randn(2, info["split"], 3, device=cuda).cpu()
+    want, oinfo = DO.adaptive_control(g["pos"], g["rgb"], g["opa"], g["quat"], g["scale"], grad, tau, 1.5, act, 2e-4, agg,
+                                      True, True, 0.01, z=z)
+    assert (info["deleted"], info["cloned"], info["split"]) == (oinfo["deleted"], oinfo["cloned"], oinfo["split"])
+    assert info["deleted"] > 0 and info["cloned"] > 0 and info["split"] > 0
+    assert info["total"] == n - info["deleted"] + info["cloned"] + info["split"]
+    for name, t in zip(("pos", "rgb", "opa", "quat", "scale"), want):
+        got = getattr(sp.gaussian_3ds, name).detach().cpu()
+        assert got.shape == t.shape, name
+        assert rel_err(got, t) < 1e-6, name
+    assert bool(torch.isfinite(sp(0)).all())                  # the new scene renders
+    # clone / split switched off (train.py passes False inside the opacity-reset interval): prune only
+    n1 = sp.gaussian_3ds.pos.shape[0]
+    info2 = sp.gaussian_3ds.adaptive_control(torch.zeros(n1, 3, device=cuda), taus=tau, delete_thresh=1.5,
+                                             scale_activation=act, use_clone=False, use_split=False)
+    assert info2["cloned"] == 0 and info2["split"] == 0 and info2["total"] == n1 - info2["deleted"]
