@@ -607,6 +607,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("use_clone"), py::arg("use_split"), py::arg("clone_dt"), py::arg("generator") = py::none());
   m.def("loss_l1_ssim", &loss_l1_ssim, "fused L1 + SSIM loss, forward + image gradient (CUDA)");
   m.def("adam_step", &adam_step, "fused Adam over flat parameter / gradient buffers (CUDA)");
+  m.def("tune", [](const std::string& name, int value) { check_rc(gs_tune(name.c_str(), value), "gs_tune"); },
+        "set an A/B tuning knob of the blend kernels (see include/gs_b200.h gs_tune)");
   m.def("kernel_launches", []() { return (int64_t)gs_kernel_launches(); },
         "kernels of libgs_b200 launched by this process so far");
   m.attr("abi_version") = gs_abi_version();

@@ -573,39 +573,77 @@ __global__ void __launch_bounds__(WSF_CONS + 32) blend_fwd_ws_kernel(const float
 // xor-shuffles combine the quarters, and each of the 4 lanes stores one 16-byte piece of the
 // instance's gradient record.  ~13 instructions per (thread, instance) instead of ~42 for the
 // recursive-halving shuffle network; fixed summation order => bit-deterministic.
-template <int PX>
+template <int PX, int STAGES_, int RQ_>
 struct Bwd2Cfg {
   static constexpr int NT = 256 / PX;                        // consumer threads (64 or 32)
   static constexpr int TPR = GS_TILE / PX;                   // threads per pixel row
-  static constexpr int R = NT / 4;                           // instances per reduction round
-  static constexpr int SQ = NT / 4;                          // source threads per quarter (= 4 pixel rows)
-  static constexpr int QS = SQ * 6 + (SQ == 16 ? 8 : 24);    // quarter stride, floats: = 8 (mod 32)
-  static constexpr int IS = 4 * QS + 2;                      // instance stride, floats: = 2 (mod 32)
-  static constexpr int STAGES = 3;
+  static constexpr int RQ = RQ_;                             // reducer threads per instance in the second phase
+  static constexpr int R = NT / RQ;                          // instances per reduction round
+  static constexpr int SQ = NT / RQ;                         // source threads per reducer ("part")
+  static constexpr int ROWS = SQ / TPR;                      // pixel rows per reducer
+  // strides (floats) of the partial buffer [instance][part][source thread][6]: part stride = 32/RQ and
+  // instance stride = 2 (mod 32) make the 8-byte loads of a half-warp (16 / RQ instances x RQ parts) hit
+  // 16 distinct bank pairs; the 8-byte stores of 16 consecutive source threads (stride 6) are conflict free
+  static constexpr int QS = (SQ * 6 + 31) / 32 * 32 + 32 / RQ;
+  static constexpr int IS = RQ * QS + 2 - (RQ * QS) % 32 + ((RQ * QS) % 32 > 2 ? 32 : 0);
+  static constexpr int STAGES = STAGES_;
 };
 
-template <int PX>
-struct Bwd2Smem : WsRing<Bwd2Cfg<PX>::STAGES> {
-  float part[Bwd2Cfg<PX>::R * Bwd2Cfg<PX>::IS];
+template <int PX, int STAGES, int RQ>
+struct Bwd2Smem : WsRing<STAGES> {
+  float part[Bwd2Cfg<PX, STAGES, RQ>::R * Bwd2Cfg<PX, STAGES, RQ>::IS];
   float pyt[GS_TILE];
   int valid[2];
 };
 
+// one instance x this thread's row of PX pixels: recompute alpha, analytic d/d alpha, six partial sums
 template <int PX>
-__global__ void __launch_bounds__(256 / PX + 32) blend_bwd_ws_kernel(const float4* __restrict__ pA,
-                                                                      const float2* __restrict__ pB,
-                                                                      const float4* __restrict__ pC,
-                                                                      const int* __restrict__ tile_accum, int wp,
-                                                                      int hp, int ntx, float fx, float fy,
-                                                                      const float* __restrict__ image,
-                                                                      const float* __restrict__ grad_image,
-                                                                      float* __restrict__ grad_inst,
-                                                                      int grad_is_final, GsCrop crop,
-                                                                      uint32_t* __restrict__ row_epoch,
-                                                                      uint32_t epoch, int* __restrict__ tile_neff_b) {
-  using Cfg = Bwd2Cfg<PX>;
-  constexpr int NT = Cfg::NT, TPR = Cfg::TPR, R = Cfg::R, SQ = Cfg::SQ, QS = Cfg::QS, IS = Cfg::IS, STAGES = Cfg::STAGES;
-  using Smem = Bwd2Smem<PX>;
+__device__ __forceinline__ void bwd_row(const float4 a, const float2 b, const float4 c, const float (&px)[PX],
+                                        const float py, float (&T)[PX], float (&Rr)[PX], const float (&gr)[PX],
+                                        const float (&gg)[PX], const float (&gb)[PX], float2* __restrict__ dst) {
+  float s0 = 0.f, sx = 0.f, sxx = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
+  const float dy = py - a.y;
+  const float m1 = a.w * dy;
+  const float ev = fmaf(-b.x * dy, dy, b.y);
+#pragma unroll
+  for (int p = 0; p < PX; ++p) {
+    const float dx = px[p] - a.x;
+    const float eu = fmaf(a.z, dx, -m1);
+    float alpha = gs_ex2(fmaf(-dx, eu, ev));                     // l2o - (ca dx^2 - cb dx dy + cc dy^2)
+    alpha = (T[p] > GS_T_STOP) ? alpha : 0.f;                    // early stop (:578): no weight, no gradient
+    const float w = alpha * T[p];
+    const float gc = fmaf(gr[p], c.x, fmaf(gg[p], c.y, gb[p] * c.z));
+    Rr[p] = fmaf(-gc, w, Rr[p]);                                 // sum_c g_c (out_c - C_c^{<=i})
+    const float rc = gs_rcp(1.0000001f - alpha);                 // 1/(1 - alpha + 1e-7)  (:721)
+    const float dal = fmaf(T[p], gc, -Rr[p] * rc);               // d L / d alpha            (:710-722)
+    const float e = dal * alpha;
+    T[p] -= w;
+    const float ex = e * dx;
+    s0 += e;
+    sx += ex;
+    sxx = fmaf(ex, dx, sxx);
+    c0 = fmaf(gr[p], w, c0);
+    c1 = fmaf(gg[p], w, c1);
+    c2 = fmaf(gb[p], w, c2);
+  }
+  dst[0] = make_float2(s0, sx);
+  dst[1] = make_float2(sxx, c0);
+  dst[2] = make_float2(c1, c2);
+}
+
+// WS: dedicated producer warp (full / empty mbarrier ring); !WS: consumer thread 0 issues the copies at the
+// chunk boundaries (no extra warp holding registers).  UNR: instances per unrolled step of the first phase.
+template <int PX, bool WS, int UNR, int STAGES, int MINB, int RQ>
+__global__ void __launch_bounds__(256 / PX + (WS ? 32 : 0), MINB)
+    blend_bwd2_kernel(const float4* __restrict__ pA, const float2* __restrict__ pB, const float4* __restrict__ pC,
+                      const int* __restrict__ tile_accum, int wp, int hp, int ntx, float fx, float fy,
+                      const float* __restrict__ image, const float* __restrict__ grad_image,
+                      float* __restrict__ grad_inst, int grad_is_final, GsCrop crop, uint32_t* __restrict__ row_epoch,
+                      uint32_t epoch, int* __restrict__ tile_neff_b) {
+  using Cfg = Bwd2Cfg<PX, STAGES, RQ>;
+  constexpr int NT = Cfg::NT, TPR = Cfg::TPR, R = Cfg::R, SQ = Cfg::SQ, QS = Cfg::QS, IS = Cfg::IS, ROWS = Cfg::ROWS;
+  static_assert(IS % 2 == 0 && QS % 2 == 0 && IS % 32 == 2 && QS % 32 == 32 / RQ, "partial buffer strides");
+  using Smem = Bwd2Smem<PX, STAGES, RQ>;
   __shared__ __align__(16) Smem sm;
   const int tile = blockIdx.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -614,13 +652,18 @@ __global__ void __launch_bounds__(256 / PX + 32) blend_bwd_ws_kernel(const float
   if (cnt == 0) return;
   const int nchunks = (cnt + WS_CH - 1) / WS_CH;
   const int tx = tile % ntx, ty = tile / ntx;
+  const int shift = start & 1;
   if (tid < GS_TILE) sm.pyt[tid] = gs_pixel_coord(ty * GS_TILE + tid, hp, fy);
   ws_init<Smem, STAGES>(sm, tid);
-  if (tid >= NT) {
-    if (tid == NT) ws_producer<Smem, STAGES>(sm, pA, pB, pC, start, cnt, nchunks);
-    return;
+  if (WS) {
+    if (tid >= NT) {
+      if (tid == NT) ws_producer<Smem, STAGES>(sm, pA, pB, pC, start, cnt, nchunks);
+      return;
+    }
+  } else if (tid == 0) {
+    for (int k = 0; k < STAGES && k < nchunks; ++k)
+      issue_chunk<Smem, WS_CH>(sm, k, pA, pB, pC, start + k * WS_CH, min(WS_CH, cnt - k * WS_CH), shift);
   }
-  const int shift = start & 1;
   const int ix0 = tx * GS_TILE + (tid % TPR) * PX;
   const int iy = ty * GS_TILE + (tid / TPR);
   float px[PX];
@@ -663,7 +706,7 @@ __global__ void __launch_bounds__(256 / PX + 32) blend_bwd_ws_kernel(const float
   // this thread's slot in the partial buffer: quarter tid / SQ, position tid % SQ
   float2* const my_part = reinterpret_cast<float2*>(sm.part + (tid / SQ) * QS + (tid % SQ) * 6);
   // second-phase role: instance ri of the round, quarter rq of the source threads
-  const int ri = tid >> 2, rq = tid & 3;
+  const int ri = tid / RQ, rq = tid % RQ;
   const float2* const red_src = reinterpret_cast<const float2*>(sm.part + ri * IS + rq * QS);
 
   int consumed = cnt;
@@ -681,46 +724,25 @@ __global__ void __launch_bounds__(256 / PX + 32) blend_bwd_ws_kernel(const float
       const int nr = min(R, n - sub);
       // ---- phase 1: per-thread partial sums of up to R instances
       int j = 0;
-      for (; j < nr; ++j) {
-        if ((j & 3) == 0) {
+      bool wdead = false;
+      for (; j + UNR <= nr; j += UNR) {
+        if (UNR >= 4 || (j & 3) == 0) {
           bool dead = true;
 #pragma unroll
           for (int p = 0; p < PX; ++p) dead = dead && !(T[p] > GS_T_STOP);
-          if (__all_sync(0xffffffffu, dead)) break;
+          if (__all_sync(0xffffffffu, dead)) {
+            wdead = true;
+            break;
+          }
         }
-        const float4 a = sA[sub + j];
-        const float2 b = sB[sub + j];
-        const float4 c = sC[sub + j];
-        float s0 = 0.f, sx = 0.f, sxx = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
-        const float dy = py - a.y;
-        const float m1 = a.w * dy;
-        const float ev = fmaf(-b.x * dy, dy, b.y);
 #pragma unroll
-        for (int p = 0; p < PX; ++p) {
-          const float dx = px[p] - a.x;
-          const float eu = fmaf(a.z, dx, -m1);
-          float alpha = gs_ex2(fmaf(-dx, eu, ev));                     // l2o - (ca dx^2 - cb dx dy + cc dy^2)
-          alpha = (T[p] > GS_T_STOP) ? alpha : 0.f;                    // early stop (:578): no weight, no gradient
-          const float w = alpha * T[p];
-          const float gc = fmaf(gr[p], c.x, fmaf(gg[p], c.y, gb[p] * c.z));
-          Rr[p] = fmaf(-gc, w, Rr[p]);                                 // sum_c g_c (out_c - C_c^{<=i})
-          const float rc = gs_rcp(1.0000001f - alpha);                 // 1/(1 - alpha + 1e-7)  (:721)
-          const float dal = fmaf(T[p], gc, -Rr[p] * rc);               // d L / d alpha            (:710-722)
-          const float e = dal * alpha;
-          T[p] -= w;
-          const float ex = e * dx;
-          s0 += e;
-          sx += ex;
-          sxx = fmaf(ex, dx, sxx);
-          c0 = fmaf(gr[p], w, c0);
-          c1 = fmaf(gg[p], w, c1);
-          c2 = fmaf(gb[p], w, c2);
-        }
-        float2* dst = my_part + j * (IS / 2);
-        dst[0] = make_float2(s0, sx);
-        dst[1] = make_float2(sxx, c0);
-        dst[2] = make_float2(c1, c2);
+        for (int u = 0; u < UNR; ++u)
+          bwd_row<PX>(sA[sub + j + u], sB[sub + j + u], sC[sub + j + u], px, py, T, Rr, gr, gg, gb,
+                      my_part + (j + u) * (IS / 2));
       }
+      if (UNR > 1 && !wdead)
+        for (; j < nr; ++j)
+          bwd_row<PX>(sA[sub + j], sB[sub + j], sC[sub + j], px, py, T, Rr, gr, gg, gb, my_part + j * (IS / 2));
       bool dead = true;
 #pragma unroll
       for (int p = 0; p < PX; ++p) dead = dead && !(T[p] > GS_T_STOP);
@@ -746,10 +768,10 @@ __global__ void __launch_bounds__(256 / PX + 32) blend_bwd_ws_kernel(const float
           a = sA[sub + ri];
           b = sB[sub + ri];
         }
-        const int vq = (NT == 64 && rq >= 2) ? v1 : v0;   // instances the quarter's source warp really processed
+        const int vq = (NT == 64 && rq * SQ >= 32) ? v1 : v0;   // instances the part's source warp really processed
         if (act && ri < vq) {
 #pragma unroll
-          for (int r = 0; r < 4; ++r) {
+          for (int r = 0; r < ROWS; ++r) {
             float2 u0 = red_src[(r * TPR) * 3], u1 = red_src[(r * TPR) * 3 + 1], u2 = red_src[(r * TPR) * 3 + 2];
 #pragma unroll
             for (int t = 1; t < TPR; ++t) {
@@ -757,7 +779,7 @@ __global__ void __launch_bounds__(256 / PX + 32) blend_bwd_ws_kernel(const float
                            w2 = red_src[(r * TPR + t) * 3 + 2];
               u0.x += w0.x; u0.y += w0.y; u1.x += w1.x; u1.y += w1.y; u2.x += w2.x; u2.y += w2.y;
             }
-            const float dyr = sm.pyt[4 * rq + r] - a.y;
+            const float dyr = sm.pyt[ROWS * rq + r] - a.y;
             S0 += u0.x;
             Sx += u0.y;
             Sxx += u1.x;
@@ -771,7 +793,8 @@ __global__ void __launch_bounds__(256 / PX + 32) blend_bwd_ws_kernel(const float
         }
 #define GS_RED4(V)                                   \
   V += __shfl_xor_sync(0xffffffffu, V, 1);           \
-  V += __shfl_xor_sync(0xffffffffu, V, 2);
+  V += __shfl_xor_sync(0xffffffffu, V, 2);           \
+  if (RQ == 8) V += __shfl_xor_sync(0xffffffffu, V, 4);
         GS_RED4(S0) GS_RED4(Sx) GS_RED4(Sxx) GS_RED4(Sy) GS_RED4(Sxy) GS_RED4(Syy) GS_RED4(C0) GS_RED4(C1) GS_RED4(C2)
 #undef GS_RED4
         if (act) {
@@ -785,7 +808,7 @@ __global__ void __launch_bounds__(256 / PX + 32) blend_bwd_ws_kernel(const float
             out[1] = make_float4(-GS_LN2 * Syy, GS_LN2 * S0, C0, C1);
           else if (rq == 2)
             out[2] = make_float4(C2, 0.f, 0.f, 0.f);
-          else if (row_epoch)
+          else if (rq == 3 && row_epoch)
             row_epoch[slot] = epoch;               // marks the row as written in this frame
         }
       }
@@ -798,13 +821,25 @@ __global__ void __launch_bounds__(256 / PX + 32) blend_bwd_ws_kernel(const float
       }
     }
     if (tid == 0) {
-      sm.consumed_chunks = k + 1;
-      if (finished) sm.stop = 1;
-      gs_mbar_arrive(&sm.empty[stage]);
+      if (WS) {
+        sm.consumed_chunks = k + 1;
+        if (finished) sm.stop = 1;
+        gs_mbar_arrive(&sm.empty[stage]);
+      } else if (!finished && k + STAGES < nchunks) {
+        const int kn = k + STAGES;               // every consumer is past the barrier: the stage is free
+        issue_chunk<Smem, WS_CH>(sm, stage, pA, pB, pC, start + kn * WS_CH, min(WS_CH, cnt - kn * WS_CH), shift);
+      }
     }
   }
   if (tid == 0) {
-    gs_mbar_arrive(&sm.done);
+    if (WS) {
+      gs_mbar_arrive(&sm.done);
+    } else if (finished) {
+      // drain copies that were issued but never consumed before the CTA may retire (k was incremented past the
+      // chunk that finished): chunks k .. k + STAGES - 2 are in flight
+      for (int kk = k; kk < nchunks && kk < k + STAGES - 1; ++kk)
+        gs_mbar_wait(&sm.full[kk % STAGES], (uint32_t)((kk / STAGES) & 1));
+    }
     if (tile_neff_b) tile_neff_b[tile] = consumed;
   }
   // the unread tail of a saturated tile has zero gradient: with an epoch array the rows are simply
@@ -939,13 +974,13 @@ inline size_t legacy_ws_layout(int m, int d, LegacyWs* ws, char* base) {
 cudaError_t gs_launch_blend_fwd(const float4* pA, const float2* pB, const float4* pC, const int* tile_accum,
                                 const GsFrameGeom& g, float* image, int* tile_neff, float* final_img,
                                 const GsCrop& crop, cudaStream_t st) {
-  static const int ver = getenv("GS_BLEND_V") ? atoi(getenv("GS_BLEND_V")) : 2;   // A/B knob: 1 = round-1 kernels
-  if (ver != 1) {
+  const GsTuning& tn = gs_tuning();
+  if (tn.fwd_kernel != 0) {
     blend_fwd_ws_kernel<<<g.n_tiles, WSF_CONS + 32, 0, st>>>(pA, pB, pC, tile_accum, g.wp, g.hp, g.ntx, g.fx, g.fy, image,
                                                              tile_neff, final_img, crop);
     return cudaGetLastError();
   }
-  static const int ch = getenv("GS_FWD_CH") ? atoi(getenv("GS_FWD_CH")) : 256;   // A/B knob (staging chunk)
+  const int ch = tn.fwd_ch;   // A/B knob (staging chunk)
 #define GS_FWD_LAUNCH(CH)                                                                                       \
   blend_fwd_kernel<CH><<<g.n_tiles, FWD_THREADS, 0, st>>>(pA, pB, pC, tile_accum, g.wp, g.hp, g.ntx, g.fx, g.fy, \
                                                           image, tile_neff, final_img, crop)
@@ -960,21 +995,36 @@ cudaError_t gs_launch_blend_bwd(const float4* pA, const float2* pB, const float4
                                 const GsFrameGeom& g, const float* image, const float* grad_image, float* grad_inst,
                                 int grad_is_final, const GsCrop& crop, uint32_t* row_epoch, uint32_t epoch,
                                 int* tile_neff_b, cudaStream_t st) {
-  static const int ver = getenv("GS_BLEND_V") ? atoi(getenv("GS_BLEND_V")) : 2;   // A/B knob: 1 = round-1 kernels
-  static const int bpx = getenv("GS_BWD_PX") ? atoi(getenv("GS_BWD_PX")) : 4;     // A/B knob: pixels per consumer thread
-  if (ver != 1) {
-    if (bpx == 8)
-      blend_bwd_ws_kernel<8><<<g.n_tiles, 256 / 8 + 32, 0, st>>>(pA, pB, pC, tile_accum, g.wp, g.hp, g.ntx, g.fx, g.fy,
-                                                                 image, grad_image, grad_inst, grad_is_final, crop,
-                                                                 row_epoch, epoch, tile_neff_b);
-    else
-      blend_bwd_ws_kernel<4><<<g.n_tiles, 256 / 4 + 32, 0, st>>>(pA, pB, pC, tile_accum, g.wp, g.hp, g.ntx, g.fx, g.fy,
-                                                                 image, grad_image, grad_inst, grad_is_final, crop,
-                                                                 row_epoch, epoch, tile_neff_b);
+  const GsTuning& tn = gs_tuning();
+  if (tn.bwd_kernel != 0) {
+#define GS_BWD2(PX, WS, UNR, ST, MINB, RQ)                                                                          \
+  blend_bwd2_kernel<PX, WS, UNR, ST, MINB, RQ><<<g.n_tiles, 256 / PX + (WS ? 32 : 0), 0, st>>>(                      \
+      pA, pB, pC, tile_accum, g.wp, g.hp, g.ntx, g.fx, g.fy, image, grad_image, grad_inst, grad_is_final, crop,    \
+      row_epoch, epoch, tile_neff_b)
+    // key: px | producer warp | unroll | stages | reducers per instance | min blocks (2 digits)
+    const int key = ((((tn.bwd_px * 10 + tn.bwd_ws) * 10 + tn.bwd_unroll) * 10 + tn.bwd_stages) * 10 + tn.bwd_rq) * 100 +
+                    tn.bwd_minb;
+    switch (key) {
+      case 4113401: GS_BWD2(4, true, 1, 3, 1, 4); break;      // round-2 first version
+      case 4113408: GS_BWD2(4, true, 1, 3, 8, 4); break;
+      case 4143408: GS_BWD2(4, true, 4, 3, 8, 4); break;
+      case 4112808: GS_BWD2(4, true, 1, 2, 8, 8); break;
+      case 4112810: GS_BWD2(4, true, 1, 2, 10, 8); break;
+      case 4142810: GS_BWD2(4, true, 4, 2, 10, 8); break;
+      case 4012401: GS_BWD2(4, false, 1, 2, 1, 4); break;
+      case 4012407: GS_BWD2(4, false, 1, 2, 7, 4); break;
+      case 4012810: GS_BWD2(4, false, 1, 2, 10, 8); break;
+      case 4012812: GS_BWD2(4, false, 1, 2, 12, 8); break;
+      case 4042810: GS_BWD2(4, false, 4, 2, 10, 8); break;
+      case 4022810: GS_BWD2(4, false, 2, 2, 10, 8); break;
+      case 8012410: GS_BWD2(8, false, 1, 2, 10, 4); break;
+      default: return cudaErrorInvalidValue;
+    }
+#undef GS_BWD2
     return cudaGetLastError();
   }
-  static const int warps = getenv("GS_BWD_WARPS") ? atoi(getenv("GS_BWD_WARPS")) : 2;   // A/B knob: 1 = one warp x 8 px
-  static const int ch = getenv("GS_BWD_CH") ? atoi(getenv("GS_BWD_CH")) : 64;            // A/B knob (staging chunk)
+  const int warps = tn.bwd_px == 8 ? 1 : 2;   // round-1 kernel: 1 warp x 8 px or 2 warps x 4 px
+  const int ch = 64;
 #define GS_BWD_LAUNCH(W, CH)                                                                                         \
   blend_bwd_kernel<W, CH><<<g.n_tiles, 32 * W, 0, st>>>(pA, pB, pC, tile_accum, g.wp, g.hp, g.ntx, g.fx, g.fy, image, \
                                                         grad_image, grad_inst, grad_is_final, crop, row_epoch, epoch, \

@@ -27,6 +27,21 @@ struct GsRayPtrs {
   const float *rays_o, *lefttop, *dx, *dy;
 };
 
+// Run-time tuning knobs (A/B experiments and profiles/; the defaults are the shipped configuration).
+// Set with gs_tune("name", value) or the environment variable GS_TUNE_<NAME> (read once).
+struct GsTuning {
+  int fwd_kernel;   // 0 = consumer thread 0 issues the copies, 1 = dedicated producer warp
+  int fwd_ch;       // staging chunk of kernel 0: 64 / 128 / 256
+  int bwd_kernel;   // 0 = shuffle-network reduction (round 1), 1 = two-phase shared-memory reduction
+  int bwd_px;       // pixels per consumer thread: 4 or 8
+  int bwd_ws;       // dedicated producer warp
+  int bwd_unroll;   // instances per unrolled step: 1, 2, 4
+  int bwd_stages;   // staging ring depth: 2 or 3
+  int bwd_minb;     // __launch_bounds__ min blocks (register cap); 1 = none
+  int bwd_rq;       // reducer threads per instance in the second phase: 4 (16 instances per round) or 8 (8)
+};
+GsTuning& gs_tuning();
+
 // every launch of one of OUR kernels is counted (bench.py reports the count of the timed region)
 void gs_count_launch(int n = 1);
 

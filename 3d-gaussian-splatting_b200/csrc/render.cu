@@ -40,6 +40,32 @@ int gs_set_error_msg(int code, const char* what) {
 extern "C" const char* gs_last_error(void) { return g_err; }
 extern "C" int gs_abi_version(void) { return 2; }
 
+static int tune_env(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+GsTuning& gs_tuning() {
+  static GsTuning t = {tune_env("GS_TUNE_FWD_KERNEL", 1),  tune_env("GS_TUNE_FWD_CH", 256),   tune_env("GS_TUNE_BWD_KERNEL", 1),
+                       tune_env("GS_TUNE_BWD_PX", 4),      tune_env("GS_TUNE_BWD_WS", 1),     tune_env("GS_TUNE_BWD_UNROLL", 1),
+                       tune_env("GS_TUNE_BWD_STAGES", 3),  tune_env("GS_TUNE_BWD_MINB", 1),   tune_env("GS_TUNE_BWD_RQ", 4)};
+  return t;
+}
+extern "C" int gs_tune(const char* name, int value) {
+  if (!name) return gs_set_error_msg(GS_ERR_INVALID_ARG, "gs_tune: null name");
+  GsTuning& t = gs_tuning();
+  struct { const char* k; int* v; } tab[] = {{"fwd_kernel", &t.fwd_kernel}, {"fwd_ch", &t.fwd_ch},
+                                             {"bwd_kernel", &t.bwd_kernel}, {"bwd_px", &t.bwd_px},
+                                             {"bwd_ws", &t.bwd_ws},         {"bwd_unroll", &t.bwd_unroll},
+                                             {"bwd_stages", &t.bwd_stages}, {"bwd_minb", &t.bwd_minb},
+                                             {"bwd_rq", &t.bwd_rq}};
+  for (auto& e : tab)
+    if (!strcmp(e.k, name)) {
+      *e.v = value;
+      return 0;
+    }
+  return gs_set_error_msg(GS_ERR_INVALID_ARG, "gs_tune: unknown knob");
+}
+
 #include <atomic>
 static std::atomic<unsigned long long> g_launches{0};
 void gs_count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }

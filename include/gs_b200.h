@@ -33,6 +33,11 @@ typedef void* gs_stream_t; /* cudaStream_t */
 int gs_abi_version(void);
 /* Human-readable text of the last error on this host thread ("" if none). */
 const char* gs_last_error(void);
+/* A/B tuning knobs of the blend kernels (profiles/ experiments; defaults = the shipped configuration):
+ * "fwd_kernel", "fwd_ch", "bwd_kernel", "bwd_px", "bwd_ws", "bwd_unroll", "bwd_stages", "bwd_minb"
+ * (see csrc/internal.h GsTuning).  An unsupported combination makes the next backward fail with
+ * cudaErrorInvalidValue.  Process-wide, not thread-safe. */
+int gs_tune(const char* name, int value);
 /* Number of kernels of THIS library launched by the process so far (library kernels such as CUB's are not
  * counted); bench.py reports the difference over its timed region as `gpu_launches`. */
 unsigned long long gs_kernel_launches(void);

@@ -44,7 +44,9 @@ def test_ssim_known_answers_and_half_target(gs, cuda):
     # constant images: every window has zero variance -> ssim = (2ab + c1) / (a^2 + b^2 + c1)
     a, b = 0.3, 0.7
     s = float(loss.ssim(torch.full((h, w, 3), a, device=cuda), torch.full((h, w, 3), b, device=cuda)))
-    assert abs(s - (2 * a * b + 1e-4) / (a * a + b * b + 1e-4)) < 1e-6
+    # (fp32: E[x^2] - mu^2 cancels to ~1e-8 instead of 0 and c2 = 9e-4 amplifies that to ~5e-5, exactly as an
+    #  fp32 evaluation of the torchmetrics formula does)
+    assert abs(s - (2 * a * b + 1e-4) / (a * a + b * b + 1e-4)) < 2e-4
     img, gt = _pair(h, w, 7)
     assert abs(float(loss.ssim(gt.to(cuda), gt.to(cuda))) - 1.0) < 1e-6          # identical images
     s_xy = float(loss.ssim(img.to(cuda), gt.to(cuda)))
