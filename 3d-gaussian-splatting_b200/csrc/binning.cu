@@ -99,8 +99,9 @@ __global__ void gather_kernel(const int* __restrict__ accum, const int* __restri
 // Gaussian are contiguous, and nothing in the pipeline needs a scattered store (scattered
 // 4-byte stores cost 0.5 ms at C3 when tried: partial-sector read-modify-write in L2).
 template <typename KeyT>
-__global__ void __launch_bounds__(kBlock) emit_keys_kernel(const GsRec* __restrict__ rec, const uint32_t* __restrict__ perm,
-                                                            const uint32_t* __restrict__ offsets_sorted, int n,
+__global__ void __launch_bounds__(kBlock) emit_keys_kernel(GsRec* __restrict__ rec, const uint32_t* __restrict__ perm,
+                                                            const uint32_t* __restrict__ offsets_sorted,
+                                                            const uint32_t* __restrict__ offsets_g, int n,
                                                             int ntx, KeyT* __restrict__ keys,
                                                             uint32_t* __restrict__ vals) {
   int i = blockIdx.x * kBlock + threadIdx.x;
@@ -109,6 +110,9 @@ __global__ void __launch_bounds__(kBlock) emit_keys_kernel(const GsRec* __restri
   if (o1 == o0) return;
   uint32_t g = perm[i];
   float4 c = rec[g].c;
+  // complete the record for the gather path of the blend kernels: first gradient row of this Gaussian
+  // (same 32-byte sector as `c`, which this thread has just pulled into L2)
+  if (offsets_g) rec[g].d.x = offsets_g[g];
   uint32_t rxy = __float_as_uint(c.z), rwh = __float_as_uint(c.w);
   uint32_t tx0 = rxy & 0xffffu, ty0 = rxy >> 16, w = rwh & 0xffffu, h = rwh >> 16;
   uint32_t r = o0;
@@ -191,6 +195,24 @@ __global__ void __launch_bounds__(kBlock) pack_sorted_sh_kernel(const KeyT* __re
   for (int q = sub; q < d; q += 8) row[q] = src[q];
 }
 
+// Tile ranges of the sorted instance list (tile_n_point_accum semantics: accum[t] = first sorted index of
+// tile t, accum[T] = M) for the gather path, where no pack pass walks the keys.
+template <typename KeyT>
+__global__ void __launch_bounds__(kBlock) tile_ranges_kernel(const KeyT* __restrict__ keys, long long m, int n_tiles,
+                                                              int* __restrict__ tile_accum) {
+  long long i = (long long)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= m) return;
+  const uint32_t tile = keys[i];
+  if (i == 0) {
+    for (uint32_t t = 0; t <= tile; ++t) tile_accum[t] = 0;
+  } else {
+    const uint32_t prev = keys[i - 1];
+    for (uint32_t t = prev + 1; t <= tile; ++t) tile_accum[t] = (int)i;
+  }
+  if (i == m - 1)
+    for (uint32_t t = tile + 1; t <= (uint32_t)n_tiles; ++t) tile_accum[t] = (int)m;
+}
+
 __global__ void __launch_bounds__(kBlock) iota_kernel(uint32_t* out, int n) {
   int i = blockIdx.x * kBlock + threadIdx.x;
   if (i < n) out[i] = (uint32_t)i;
@@ -267,15 +289,27 @@ extern "C" int gs_gather(const int* tile_n_point_accum, const int* tile_gaussian
   return 0;
 }
 
-cudaError_t gs_launch_emit_keys(const GsRec* rec, const uint32_t* perm, const uint32_t* offsets_sorted, int n, int ntx,
-                                void* keys, int key_bytes, uint32_t* vals, cudaStream_t st) {
+cudaError_t gs_launch_emit_keys(GsRec* rec, const uint32_t* perm, const uint32_t* offsets_sorted,
+                                const uint32_t* offsets_g, int n, int ntx, void* keys, int key_bytes, uint32_t* vals,
+                                cudaStream_t st) {
   if (n == 0) return cudaSuccess;
   if (key_bytes == 2)
-    emit_keys_kernel<uint16_t><<<(n + kBlock - 1) / kBlock, kBlock, 0, st>>>(rec, perm, offsets_sorted, n, ntx,
+    emit_keys_kernel<uint16_t><<<(n + kBlock - 1) / kBlock, kBlock, 0, st>>>(rec, perm, offsets_sorted, offsets_g, n, ntx,
                                                                              static_cast<uint16_t*>(keys), vals);
   else
-    emit_keys_kernel<uint32_t><<<(n + kBlock - 1) / kBlock, kBlock, 0, st>>>(rec, perm, offsets_sorted, n, ntx,
+    emit_keys_kernel<uint32_t><<<(n + kBlock - 1) / kBlock, kBlock, 0, st>>>(rec, perm, offsets_sorted, offsets_g, n, ntx,
                                                                              static_cast<uint32_t*>(keys), vals);
+  return cudaGetLastError();
+}
+
+cudaError_t gs_launch_tile_ranges(const void* keys, int key_bytes, long long m, int n_tiles, int* tile_accum,
+                                  cudaStream_t st) {
+  if (m == 0) return cudaMemsetAsync(tile_accum, 0, sizeof(int) * (size_t)(n_tiles + 1), st);
+  const unsigned grid = (unsigned)((m + kBlock - 1) / kBlock);
+  if (key_bytes == 2)
+    tile_ranges_kernel<uint16_t><<<grid, kBlock, 0, st>>>(static_cast<const uint16_t*>(keys), m, n_tiles, tile_accum);
+  else
+    tile_ranges_kernel<uint32_t><<<grid, kBlock, 0, st>>>(static_cast<const uint32_t*>(keys), m, n_tiles, tile_accum);
   return cudaGetLastError();
 }
 

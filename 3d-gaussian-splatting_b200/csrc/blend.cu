@@ -15,6 +15,7 @@
 //     recursive-halving shuffle network (14 SHFL instead of 45), combined across the two warps
 //     through shared memory and written as ONE record per instance (no atomics, deterministic).
 #include <cstdlib>
+#include <type_traits>
 
 #include "internal.h"
 
@@ -48,25 +49,88 @@ __device__ __forceinline__ void issue_chunk(SM& sm, int stage, const float4* __r
   gs_bulk_g2s(sm.B[stage], pB + (base - shift), bytes_b, &sm.full[stage]);
 }
 
+// ---- two ways a tile's sorted range reaches shared memory -------------------------------------------
+// packed : three contiguous record streams written by the pack pass (and by the legacy draw API);
+//          one thread issues three 1-D bulk copies per chunk.
+// gather : NO pack pass - every thread of the CTA issues, for "its" instances of the next chunk, one 1-D bulk
+//          copy (UBLKCP, the TMA engine) of the Gaussian's record straight from GsRec rec[N] through the sorted id
+//          list, with its share of the bytes posted on the stage's mbarrier (arrive.expect_tx; barrier count =
+//          CTA threads).  The per-instance record in shared memory is {a, b, c, d} (gs_common.cuh GsRec).
+template <bool GATHER>
+struct StageView;
+template <>
+struct StageView<false> {
+  const float4* A;
+  const float4* C;
+  const float2* B;
+  __device__ __forceinline__ float4 a(int j) const { return A[j]; }
+  __device__ __forceinline__ float2 b(int j) const { return B[j]; }
+  __device__ __forceinline__ float4 c(int j) const { return C[j]; }                   // r, g, b, (slot)
+  __device__ __forceinline__ uint32_t slot(int j, int, int) const { return __float_as_uint(C[j].w); }
+};
+template <>
+struct StageView<true> {
+  const float4* R;                                                                     // [CH][RECW]
+  int recw;
+  __device__ __forceinline__ float4 a(int j) const { return R[j * recw]; }
+  __device__ __forceinline__ float2 b(int j) const {
+    const float4 t = R[j * recw + 1];
+    return make_float2(t.x, t.y);
+  }
+  __device__ __forceinline__ float4 c(int j) const {
+    const float4 t = R[j * recw + 1];
+    return make_float4(t.z, t.w, R[j * recw + 2].x, 0.f);
+  }
+  // gradient row of this (Gaussian, tile) instance: first row of the Gaussian + rank of the tile in its rectangle
+  __device__ __forceinline__ uint32_t slot(int j, int tx, int ty) const {
+    const float4 cc = R[j * recw + 2];
+    const uint32_t rxy = __float_as_uint(cc.z), rwh = __float_as_uint(cc.w);
+    const uint32_t off = __float_as_uint(R[j * recw + 3].x);
+    return off + ((uint32_t)ty - (rxy >> 16)) * (rwh & 0xffffu) + ((uint32_t)tx - (rxy & 0xffffu));
+  }
+};
+
+template <int CH, int STAGES, int RECW>
+struct GatherRing {
+  float4 rec[STAGES][CH * RECW];
+  uint64_t full[STAGES];
+};
+
+template <typename SM, int NT, int RECW>
+__device__ __forceinline__ void gather_issue(SM& sm, int stage, const GsRec* __restrict__ grec,
+                                             const uint32_t* __restrict__ ids, int base, int n, int tid) {
+  uint32_t bytes = 0;
+  for (int i = tid; i < n; i += NT) {
+    const uint32_t id = ids[base + i];
+    gs_bulk_g2s(&sm.rec[stage][i * RECW], grec + id, RECW * 16u, &sm.full[stage]);
+    bytes += RECW * 16u;
+  }
+  gs_mbar_expect_tx(&sm.full[stage], bytes);          // arrive + this thread's share of the bytes (may be 0)
+}
+
 // Per (thread, instance): 3 broadcast LDS + 4 row-shared FP32 ops (dy, cb*dy, cc*dy, l2o-cc*dy^2)
 // + 4 pixels x (dx, u, exponent, MUFU.EX2, setp, mul, sel, 3 FFMA colour, T update) = 12.75
 // issue slots per (pixel, instance) instead of 17-18 with one pixel per thread.
-template <int FWD_CH>
-__global__ void __launch_bounds__(FWD_THREADS) blend_fwd_kernel(const float4* __restrict__ pA,
+template <int FWD_CH, int PX, bool GATHER>
+__global__ void __launch_bounds__(256 / PX) blend_fwd_kernel(const float4* __restrict__ pA,
                                                                  const float2* __restrict__ pB,
                                                                  const float4* __restrict__ pC,
+                                                                 const GsRec* __restrict__ grec,
+                                                                 const uint32_t* __restrict__ ids,
                                                                  const int* __restrict__ tile_accum, int wp, int hp,
                                                                  int ntx, float fx, float fy,
                                                                  float* __restrict__ image,
                                                                  int* __restrict__ tile_neff,
                                                                  float* __restrict__ final_img, GsCrop crop) {
-  __shared__ __align__(16) FwdSmem<FWD_CH> sm;
+  using Smem = typename std::conditional<GATHER, GatherRing<FWD_CH, FWD_STAGES, 3>, FwdSmem<FWD_CH>>::type;
+  __shared__ __align__(16) Smem sm;
   const int tile = blockIdx.x;
   const int tid = threadIdx.x;
   const int tx = tile % ntx, ty = tile / ntx;
-  // thread -> pixels (ix0 .. ix0+3, iy); warp 0 = tile rows 0-7, warp 1 = rows 8-15
-  const int ix0 = tx * GS_TILE + (tid & 3) * FWD_PX;
-  const int iy = ty * GS_TILE + (tid >> 2);
+  // thread -> a row of PX adjacent pixels (ix0 .. ix0+PX-1, iy); PX = 4: 2 warps per tile, 8: one warp
+  constexpr int FWD_PX = PX, TPR = GS_TILE / PX, NTHREADS = 256 / PX;
+  const int ix0 = tx * GS_TILE + (tid % TPR) * FWD_PX;
+  const int iy = ty * GS_TILE + (tid / TPR);
   float px[FWD_PX];
 #pragma unroll
   for (int p = 0; p < FWD_PX; ++p) px[p] = gs_pixel_coord(ix0 + p, wp, fx);
@@ -78,13 +142,16 @@ __global__ void __launch_bounds__(FWD_THREADS) blend_fwd_kernel(const float4* __
   const int nchunks = (cnt + FWD_CH - 1) / FWD_CH;
 
   if (tid == 0) {
-    for (int s = 0; s < FWD_STAGES; ++s) gs_mbar_init(&sm.full[s], 1);
+    for (int s = 0; s < FWD_STAGES; ++s) gs_mbar_init(&sm.full[s], GATHER ? NTHREADS : 1);
     gs_fence_barrier_init();
   }
   __syncthreads();
-  if (tid == 0) {
+  if constexpr (GATHER) {
     for (int k = 0; k < FWD_STAGES && k < nchunks; ++k)
-      issue_chunk<FwdSmem<FWD_CH>, FWD_CH>(sm, k, pA, pB, pC, start + k * FWD_CH, min(FWD_CH, cnt - k * FWD_CH), shift);
+      gather_issue<Smem, NTHREADS, 3>(sm, k, grec, ids, start + k * FWD_CH, min(FWD_CH, cnt - k * FWD_CH), tid);
+  } else if (tid == 0) {
+    for (int k = 0; k < FWD_STAGES && k < nchunks; ++k)
+      issue_chunk<Smem, FWD_CH>(sm, k, pA, pB, pC, start + k * FWD_CH, min(FWD_CH, cnt - k * FWD_CH), shift);
   }
 
   float T[FWD_PX], cr[FWD_PX], cg[FWD_PX], cb[FWD_PX];
@@ -99,15 +166,21 @@ __global__ void __launch_bounds__(FWD_THREADS) blend_fwd_kernel(const float4* __
     const int stage = k % FWD_STAGES;
     gs_mbar_wait(&sm.full[stage], (uint32_t)((k / FWD_STAGES) & 1));
     const int n = min(FWD_CH, cnt - k * FWD_CH);
-    const float4* __restrict__ sA = sm.A[stage];
-    const float4* __restrict__ sC = sm.C[stage];
-    const float2* __restrict__ sB = sm.B[stage] + shift;
+    StageView<GATHER> sv;
+    if constexpr (GATHER) {
+      sv.R = sm.rec[stage];
+      sv.recw = 3;
+    } else {
+      sv.A = sm.A[stage];
+      sv.C = sm.C[stage];
+      sv.B = sm.B[stage] + shift;
+    }
 
 #define GS_FWD_BODY(J)                                                                      \
   {                                                                                         \
-    const float4 a = sA[J];                                                                 \
-    const float2 b = sB[J];                                                                 \
-    const float4 c = sC[J];                                                                 \
+    const float4 a = sv.a(J);                                                               \
+    const float2 b = sv.b(J);                                                               \
+    const float4 c = sv.c(J);                                                               \
     const float dy = py - a.y;                                                              \
     const float m1 = a.w * dy;                                                              \
     const float ev = fmaf(-b.x * dy, dy, b.y);                                              \
@@ -127,7 +200,9 @@ __global__ void __launch_bounds__(FWD_THREADS) blend_fwd_kernel(const float4* __
     for (; j + 4 <= n; j += 4) {
 #pragma unroll
       for (int u = 0; u < 4; ++u) GS_FWD_BODY(j + u)
-      const bool dead = !(T[0] > GS_T_STOP) && !(T[1] > GS_T_STOP) && !(T[2] > GS_T_STOP) && !(T[3] > GS_T_STOP);
+      bool dead = true;
+#pragma unroll
+      for (int p = 0; p < FWD_PX; ++p) dead = dead && !(T[p] > GS_T_STOP);
       if (__all_sync(0xffffffffu, dead)) {
         warp_dead = true;
         break;
@@ -137,15 +212,21 @@ __global__ void __launch_bounds__(FWD_THREADS) blend_fwd_kernel(const float4* __
       for (; j < n; ++j) GS_FWD_BODY(j)
 #undef GS_FWD_BODY
 
-    const bool dead = !(T[0] > GS_T_STOP) && !(T[1] > GS_T_STOP) && !(T[2] > GS_T_STOP) && !(T[3] > GS_T_STOP);
-    const int all_dead = __syncthreads_and(dead);
+    bool dead = true;
+#pragma unroll
+    for (int p = 0; p < FWD_PX; ++p) dead = dead && !(T[p] > GS_T_STOP);
+    const int all_dead = NTHREADS == 32 ? __all_sync(0xffffffffu, dead) : __syncthreads_and(dead);
+    if (NTHREADS == 32) __syncwarp();
     if (all_dead) {
       consumed = min(cnt, (k + 1) * FWD_CH);
       break;
     }
-    if (tid == 0 && k + FWD_STAGES < nchunks) {
-      const int kn = k + FWD_STAGES;
-      issue_chunk<FwdSmem<FWD_CH>, FWD_CH>(sm, stage, pA, pB, pC, start + kn * FWD_CH, min(FWD_CH, cnt - kn * FWD_CH), shift);
+    if (k + FWD_STAGES < nchunks) {
+      const int kn = k + FWD_STAGES;            // every thread is past the barrier above: the stage is free
+      if constexpr (GATHER)
+        gather_issue<Smem, NTHREADS, 3>(sm, stage, grec, ids, start + kn * FWD_CH, min(FWD_CH, cnt - kn * FWD_CH), tid);
+      else if (tid == 0)
+        issue_chunk<Smem, FWD_CH>(sm, stage, pA, pB, pC, start + kn * FWD_CH, min(FWD_CH, cnt - kn * FWD_CH), shift);
     }
   }
   // drain copies that were issued but never consumed (early exit) before the CTA retires
@@ -153,11 +234,19 @@ __global__ void __launch_bounds__(FWD_THREADS) blend_fwd_kernel(const float4* __
     for (int kk = k + 1; kk < nchunks && kk < k + FWD_STAGES; ++kk)
       gs_mbar_wait(&sm.full[kk % FWD_STAGES], (uint32_t)((kk / FWD_STAGES) & 1));
   }
-  // 4 pixels x 3 channels = 48 contiguous, 16-byte aligned bytes
-  float4* o = reinterpret_cast<float4*>(image + ((size_t)iy * wp + ix0) * 3);
-  o[0] = make_float4(cr[0], cg[0], cb[0], cr[1]);
-  o[1] = make_float4(cg[1], cb[1], cr[2], cg[2]);
-  o[2] = make_float4(cb[2], cr[3], cg[3], cb[3]);
+  // PX pixels x 3 channels = PX * 12 contiguous, 16-byte aligned bytes
+  {
+    float ob[FWD_PX * 3];
+#pragma unroll
+    for (int p = 0; p < FWD_PX; ++p) {
+      ob[3 * p] = cr[p];
+      ob[3 * p + 1] = cg[p];
+      ob[3 * p + 2] = cb[p];
+    }
+    float4* o = reinterpret_cast<float4*>(image + ((size_t)iy * wp + ix0) * 3);
+#pragma unroll
+    for (int q = 0; q < FWD_PX * 3 / 4; ++q) o[q] = make_float4(ob[4 * q], ob[4 * q + 1], ob[4 * q + 2], ob[4 * q + 3]);
+  }
   if (final_img) {
 #pragma unroll
     for (int p = 0; p < FWD_PX; ++p)
@@ -589,8 +678,8 @@ struct Bwd2Cfg {
   static constexpr int STAGES = STAGES_;
 };
 
-template <int PX, int STAGES, int RQ>
-struct Bwd2Smem : WsRing<STAGES> {
+template <int PX, int STAGES, int RQ, bool GATHER>
+struct Bwd2Smem : std::conditional<GATHER, GatherRing<WS_CH, STAGES, 4>, WsRing<STAGES>>::type {
   float part[Bwd2Cfg<PX, STAGES, RQ>::R * Bwd2Cfg<PX, STAGES, RQ>::IS];
   float pyt[GS_TILE];
   int valid[2];
@@ -633,9 +722,10 @@ __device__ __forceinline__ void bwd_row(const float4 a, const float2 b, const fl
 
 // WS: dedicated producer warp (full / empty mbarrier ring); !WS: consumer thread 0 issues the copies at the
 // chunk boundaries (no extra warp holding registers).  UNR: instances per unrolled step of the first phase.
-template <int PX, bool WS, int UNR, int STAGES, int MINB, int RQ>
+template <int PX, bool WS, int UNR, int STAGES, int MINB, int RQ, bool GATHER>
 __global__ void __launch_bounds__(256 / PX + (WS ? 32 : 0), MINB)
     blend_bwd2_kernel(const float4* __restrict__ pA, const float2* __restrict__ pB, const float4* __restrict__ pC,
+                      const GsRec* __restrict__ grec, const uint32_t* __restrict__ ids,
                       const int* __restrict__ tile_accum, int wp, int hp, int ntx, float fx, float fy,
                       const float* __restrict__ image, const float* __restrict__ grad_image,
                       float* __restrict__ grad_inst, int grad_is_final, GsCrop crop, uint32_t* __restrict__ row_epoch,
@@ -643,7 +733,8 @@ __global__ void __launch_bounds__(256 / PX + (WS ? 32 : 0), MINB)
   using Cfg = Bwd2Cfg<PX, STAGES, RQ>;
   constexpr int NT = Cfg::NT, TPR = Cfg::TPR, R = Cfg::R, SQ = Cfg::SQ, QS = Cfg::QS, IS = Cfg::IS, ROWS = Cfg::ROWS;
   static_assert(IS % 2 == 0 && QS % 2 == 0 && IS % 32 == 2 && QS % 32 == 32 / RQ, "partial buffer strides");
-  using Smem = Bwd2Smem<PX, STAGES, RQ>;
+  static_assert(!(WS && GATHER), "the gather path issues its copies from all consumer threads");
+  using Smem = Bwd2Smem<PX, STAGES, RQ, GATHER>;
   __shared__ __align__(16) Smem sm;
   const int tile = blockIdx.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -654,15 +745,25 @@ __global__ void __launch_bounds__(256 / PX + (WS ? 32 : 0), MINB)
   const int tx = tile % ntx, ty = tile / ntx;
   const int shift = start & 1;
   if (tid < GS_TILE) sm.pyt[tid] = gs_pixel_coord(ty * GS_TILE + tid, hp, fy);
-  ws_init<Smem, STAGES>(sm, tid);
-  if (WS) {
-    if (tid >= NT) {
-      if (tid == NT) ws_producer<Smem, STAGES>(sm, pA, pB, pC, start, cnt, nchunks);
-      return;
+  if constexpr (GATHER) {
+    if (tid == 0) {
+      for (int s = 0; s < STAGES; ++s) gs_mbar_init(&sm.full[s], NT);
+      gs_fence_barrier_init();
     }
-  } else if (tid == 0) {
+    __syncthreads();
     for (int k = 0; k < STAGES && k < nchunks; ++k)
-      issue_chunk<Smem, WS_CH>(sm, k, pA, pB, pC, start + k * WS_CH, min(WS_CH, cnt - k * WS_CH), shift);
+      gather_issue<Smem, NT, 4>(sm, k, grec, ids, start + k * WS_CH, min(WS_CH, cnt - k * WS_CH), tid);
+  } else {
+    ws_init<Smem, STAGES>(sm, tid);
+    if (WS) {
+      if (tid >= NT) {
+        if (tid == NT) ws_producer<Smem, STAGES>(sm, pA, pB, pC, start, cnt, nchunks);
+        return;
+      }
+    } else if (tid == 0) {
+      for (int k = 0; k < STAGES && k < nchunks; ++k)
+        issue_chunk<Smem, WS_CH>(sm, k, pA, pB, pC, start + k * WS_CH, min(WS_CH, cnt - k * WS_CH), shift);
+    }
   }
   const int ix0 = tx * GS_TILE + (tid % TPR) * PX;
   const int iy = ty * GS_TILE + (tid / TPR);
@@ -716,9 +817,15 @@ __global__ void __launch_bounds__(256 / PX + (WS ? 32 : 0), MINB)
     const int stage = k % STAGES;
     gs_mbar_wait(&sm.full[stage], (uint32_t)((k / STAGES) & 1));
     const int n = min(WS_CH, cnt - k * WS_CH);
-    const float4* __restrict__ sA = sm.A[stage];
-    const float4* __restrict__ sC = sm.C[stage];
-    const float2* __restrict__ sB = sm.B[stage] + shift;
+    StageView<GATHER> sv;
+    if constexpr (GATHER) {
+      sv.R = sm.rec[stage];
+      sv.recw = 4;
+    } else {
+      sv.A = sm.A[stage];
+      sv.C = sm.C[stage];
+      sv.B = sm.B[stage] + shift;
+    }
 
     for (int sub = 0; sub < n; sub += R) {
       const int nr = min(R, n - sub);
@@ -737,12 +844,12 @@ __global__ void __launch_bounds__(256 / PX + (WS ? 32 : 0), MINB)
         }
 #pragma unroll
         for (int u = 0; u < UNR; ++u)
-          bwd_row<PX>(sA[sub + j + u], sB[sub + j + u], sC[sub + j + u], px, py, T, Rr, gr, gg, gb,
+          bwd_row<PX>(sv.a(sub + j + u), sv.b(sub + j + u), sv.c(sub + j + u), px, py, T, Rr, gr, gg, gb,
                       my_part + (j + u) * (IS / 2));
       }
       if (UNR > 1 && !wdead)
         for (; j < nr; ++j)
-          bwd_row<PX>(sA[sub + j], sB[sub + j], sC[sub + j], px, py, T, Rr, gr, gg, gb, my_part + j * (IS / 2));
+          bwd_row<PX>(sv.a(sub + j), sv.b(sub + j), sv.c(sub + j), px, py, T, Rr, gr, gg, gb, my_part + j * (IS / 2));
       bool dead = true;
 #pragma unroll
       for (int p = 0; p < PX; ++p) dead = dead && !(T[p] > GS_T_STOP);
@@ -765,8 +872,8 @@ __global__ void __launch_bounds__(256 / PX + (WS ? 32 : 0), MINB)
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
         float2 b = make_float2(0.f, 0.f);
         if (act) {
-          a = sA[sub + ri];
-          b = sB[sub + ri];
+          a = sv.a(sub + ri);
+          b = sv.b(sub + ri);
         }
         const int vq = (NT == 64 && rq * SQ >= 32) ? v1 : v0;   // instances the part's source warp really processed
         if (act && ri < vq) {
@@ -798,7 +905,7 @@ __global__ void __launch_bounds__(256 / PX + (WS ? 32 : 0), MINB)
         GS_RED4(S0) GS_RED4(Sx) GS_RED4(Sxx) GS_RED4(Sy) GS_RED4(Sxy) GS_RED4(Syy) GS_RED4(C0) GS_RED4(C1) GS_RED4(C2)
 #undef GS_RED4
         if (act) {
-          const uint32_t slot = __float_as_uint(sC[sub + ri].w);
+          const uint32_t slot = sv.slot(sub + ri, tx, ty);
           float4* out = reinterpret_cast<float4*>(grad_inst + (size_t)slot * GS_GREC);
           // d/dx, d/dy, d/dca, d/dcb  |  d/dcc, d/dl2o, d/dr, d/dg  |  d/db
           if (rq == 0)
@@ -820,7 +927,12 @@ __global__ void __launch_bounds__(256 / PX + (WS ? 32 : 0), MINB)
         break;
       }
     }
-    if (tid == 0) {
+    if constexpr (GATHER) {
+      if (!finished && k + STAGES < nchunks) {   // every consumer is past the barrier: the stage is free
+        const int kn = k + STAGES;
+        gather_issue<Smem, NT, 4>(sm, stage, grec, ids, start + kn * WS_CH, min(WS_CH, cnt - kn * WS_CH), tid);
+      }
+    } else if (tid == 0) {
       if (WS) {
         sm.consumed_chunks = k + 1;
         if (finished) sm.stop = 1;
@@ -832,7 +944,7 @@ __global__ void __launch_bounds__(256 / PX + (WS ? 32 : 0), MINB)
     }
   }
   if (tid == 0) {
-    if (WS) {
+    if constexpr (!GATHER && WS) {
       gs_mbar_arrive(&sm.done);
     } else if (finished) {
       // drain copies that were issued but never consumed before the CTA may retire (k was incremented past the
@@ -844,7 +956,7 @@ __global__ void __launch_bounds__(256 / PX + (WS ? 32 : 0), MINB)
   }
   // the unread tail of a saturated tile has zero gradient: with an epoch array the rows are simply
   // left stale (the consumer skips rows whose tag is not this frame's); otherwise write zeros
-  if (row_epoch) return;
+  if (row_epoch || GATHER) return;              // (the gather path always runs with an epoch array)
   for (int t = consumed + tid; t < cnt; t += NT) {
     const uint32_t slot = __float_as_uint(pC[start + t].w);
     float4* out = reinterpret_cast<float4*>(grad_inst + (size_t)slot * GS_GREC);
@@ -971,53 +1083,84 @@ inline size_t legacy_ws_layout(int m, int d, LegacyWs* ws, char* base) {
 
 }  // namespace
 
-cudaError_t gs_launch_blend_fwd(const float4* pA, const float2* pB, const float4* pC, const int* tile_accum,
-                                const GsFrameGeom& g, float* image, int* tile_neff, float* final_img,
-                                const GsCrop& crop, cudaStream_t st) {
+cudaError_t gs_launch_blend_fwd(const float4* pA, const float2* pB, const float4* pC, const GsRec* grec,
+                                const uint32_t* ids, const int* tile_accum, const GsFrameGeom& g, float* image,
+                                int* tile_neff, float* final_img, const GsCrop& crop, cudaStream_t st) {
   const GsTuning& tn = gs_tuning();
-  if (tn.fwd_kernel != 0) {
+  const bool gather = grec != nullptr;
+  if (!gather && tn.fwd_kernel != 0) {
     blend_fwd_ws_kernel<<<g.n_tiles, WSF_CONS + 32, 0, st>>>(pA, pB, pC, tile_accum, g.wp, g.hp, g.ntx, g.fx, g.fy, image,
                                                              tile_neff, final_img, crop);
     return cudaGetLastError();
   }
-  const int ch = tn.fwd_ch;   // A/B knob (staging chunk)
-#define GS_FWD_LAUNCH(CH)                                                                                       \
-  blend_fwd_kernel<CH><<<g.n_tiles, FWD_THREADS, 0, st>>>(pA, pB, pC, tile_accum, g.wp, g.hp, g.ntx, g.fx, g.fy, \
-                                                          image, tile_neff, final_img, crop)
-  if (ch == 64) GS_FWD_LAUNCH(64);
-  else if (ch == 256) GS_FWD_LAUNCH(256);
-  else GS_FWD_LAUNCH(128);
+  const int ch = tn.fwd_ch;   // staging chunk
+#define GS_FWD_LAUNCH(CH, PX, GA)                                                                                   \
+  blend_fwd_kernel<CH, PX, GA><<<g.n_tiles, 256 / PX, 0, st>>>(pA, pB, pC, grec, ids, tile_accum, g.wp, g.hp, g.ntx, \
+                                                               g.fx, g.fy, image, tile_neff, final_img, crop)
+#define GS_FWD_CH(PX, GA)                     \
+  if (ch == 64) GS_FWD_LAUNCH(64, PX, GA);    \
+  else if (ch == 256) GS_FWD_LAUNCH(256, PX, GA); \
+  else GS_FWD_LAUNCH(128, PX, GA)
+  if (gather) {
+    if (tn.fwd_px == 8) { GS_FWD_CH(8, true); } else { GS_FWD_CH(4, true); }
+  } else {
+    if (tn.fwd_px == 8) { GS_FWD_CH(8, false); } else { GS_FWD_CH(4, false); }
+  }
+#undef GS_FWD_CH
 #undef GS_FWD_LAUNCH
   return cudaGetLastError();
 }
 
-cudaError_t gs_launch_blend_bwd(const float4* pA, const float2* pB, const float4* pC, const int* tile_accum,
-                                const GsFrameGeom& g, const float* image, const float* grad_image, float* grad_inst,
-                                int grad_is_final, const GsCrop& crop, uint32_t* row_epoch, uint32_t epoch,
-                                int* tile_neff_b, cudaStream_t st) {
+cudaError_t gs_launch_blend_bwd(const float4* pA, const float2* pB, const float4* pC, const GsRec* grec,
+                                const uint32_t* ids, const int* tile_accum, const GsFrameGeom& g, const float* image,
+                                const float* grad_image, float* grad_inst, int grad_is_final, const GsCrop& crop,
+                                uint32_t* row_epoch, uint32_t epoch, int* tile_neff_b, cudaStream_t st) {
   const GsTuning& tn = gs_tuning();
-  if (tn.bwd_kernel != 0) {
-#define GS_BWD2(PX, WS, UNR, ST, MINB, RQ)                                                                          \
-  blend_bwd2_kernel<PX, WS, UNR, ST, MINB, RQ><<<g.n_tiles, 256 / PX + (WS ? 32 : 0), 0, st>>>(                      \
-      pA, pB, pC, tile_accum, g.wp, g.hp, g.ntx, g.fx, g.fy, image, grad_image, grad_inst, grad_is_final, crop,    \
-      row_epoch, epoch, tile_neff_b)
+  const bool gather = grec != nullptr;
+  if (gather && !row_epoch) return cudaErrorInvalidValue;
+  if (tn.bwd_kernel != 0 || gather) {
+#define GS_BWD2(PX, WS, UNR, ST, MINB, RQ, GA)                                                                      \
+  blend_bwd2_kernel<PX, WS, UNR, ST, MINB, RQ, GA><<<g.n_tiles, 256 / PX + (WS ? 32 : 0), 0, st>>>(                  \
+      pA, pB, pC, grec, ids, tile_accum, g.wp, g.hp, g.ntx, g.fx, g.fy, image, grad_image, grad_inst, grad_is_final, \
+      crop, row_epoch, epoch, tile_neff_b)
     // key: px | producer warp | unroll | stages | reducers per instance | min blocks (2 digits)
     const int key = ((((tn.bwd_px * 10 + tn.bwd_ws) * 10 + tn.bwd_unroll) * 10 + tn.bwd_stages) * 10 + tn.bwd_rq) * 100 +
                     tn.bwd_minb;
+    if (gather) {
+      switch (key) {
+        case 8012410: GS_BWD2(8, false, 1, 2, 10, 4, true); break;
+        case 8022416: GS_BWD2(8, false, 2, 2, 16, 4, true); break;
+        case 8022410: GS_BWD2(8, false, 2, 2, 10, 4, true); break;
+        case 8042410: GS_BWD2(8, false, 4, 2, 10, 4, true); break;
+        case 8023416: GS_BWD2(8, false, 2, 3, 16, 4, true); break;
+        case 8012416: GS_BWD2(8, false, 1, 2, 16, 4, true); break;
+        case 8012420: GS_BWD2(8, false, 1, 2, 20, 4, true); break;
+        case 8012820: GS_BWD2(8, false, 1, 2, 20, 8, true); break;
+        case 8013416: GS_BWD2(8, false, 1, 3, 16, 4, true); break;
+        case 4012401: GS_BWD2(4, false, 1, 2, 1, 4, true); break;
+        case 4042401: GS_BWD2(4, false, 4, 2, 1, 4, true); break;
+        default: return cudaErrorInvalidValue;
+      }
+      return cudaGetLastError();
+    }
     switch (key) {
-      case 4113401: GS_BWD2(4, true, 1, 3, 1, 4); break;      // round-2 first version
-      case 4113408: GS_BWD2(4, true, 1, 3, 8, 4); break;
-      case 4143408: GS_BWD2(4, true, 4, 3, 8, 4); break;
-      case 4112808: GS_BWD2(4, true, 1, 2, 8, 8); break;
-      case 4112810: GS_BWD2(4, true, 1, 2, 10, 8); break;
-      case 4142810: GS_BWD2(4, true, 4, 2, 10, 8); break;
-      case 4012401: GS_BWD2(4, false, 1, 2, 1, 4); break;
-      case 4012407: GS_BWD2(4, false, 1, 2, 7, 4); break;
-      case 4012810: GS_BWD2(4, false, 1, 2, 10, 8); break;
-      case 4012812: GS_BWD2(4, false, 1, 2, 12, 8); break;
-      case 4042810: GS_BWD2(4, false, 4, 2, 10, 8); break;
-      case 4022810: GS_BWD2(4, false, 2, 2, 10, 8); break;
-      case 8012410: GS_BWD2(8, false, 1, 2, 10, 4); break;
+      case 4113401: GS_BWD2(4, true, 1, 3, 1, 4, false); break;      // round-2 first version
+      case 4143408: GS_BWD2(4, true, 4, 3, 8, 4, false); break;
+      case 4012401: GS_BWD2(4, false, 1, 2, 1, 4, false); break;
+      case 4042401: GS_BWD2(4, false, 4, 2, 1, 4, false); break;
+      case 4042810: GS_BWD2(4, false, 4, 2, 10, 8, false); break;
+      case 8012410: GS_BWD2(8, false, 1, 2, 10, 4, false); break;
+      case 8012416: GS_BWD2(8, false, 1, 2, 16, 4, false); break;
+      case 8012420: GS_BWD2(8, false, 1, 2, 20, 4, false); break;
+      case 8013416: GS_BWD2(8, false, 1, 3, 16, 4, false); break;
+      case 8022416: GS_BWD2(8, false, 2, 2, 16, 4, false); break;
+      case 8022410: GS_BWD2(8, false, 2, 2, 10, 4, false); break;
+      case 8042410: GS_BWD2(8, false, 4, 2, 10, 4, false); break;
+      case 8012816: GS_BWD2(8, false, 1, 2, 16, 8, false); break;
+      case 8012820: GS_BWD2(8, false, 1, 2, 20, 8, false); break;
+      case 8112410: GS_BWD2(8, true, 1, 2, 10, 4, false); break;
+      case 8012424: GS_BWD2(8, false, 1, 2, 24, 4, false); break;
+      case 8012824: GS_BWD2(8, false, 1, 2, 24, 8, false); break;
       default: return cudaErrorInvalidValue;
     }
 #undef GS_BWD2
@@ -1083,7 +1226,8 @@ extern "C" int gs_draw_fwd(const float* pos, const float* rgb, const float* opa,
   g.fx = focal_x;
   g.fy = focal_y;
   if (d == 3) {
-    GS_CUDA_TRY(gs_launch_blend_fwd(ws.pA, ws.pB, ws.pC, tile_n_point_accum, g, image, nullptr, nullptr, GsCrop{}, st));
+    GS_CUDA_TRY(gs_launch_blend_fwd(ws.pA, ws.pB, ws.pC, nullptr, nullptr, tile_n_point_accum, g, image, nullptr, nullptr,
+                                    GsCrop{}, st));
   } else {
     GsRayPtrs r{rays_o, lefttop, vec_dx, vec_dy};
     GS_CUDA_TRY(gs_launch_blend_sh_fwd(ws.pA, ws.pB, reinterpret_cast<float*>(ws.pC), d, tile_n_point_accum, g, r,
@@ -1124,7 +1268,8 @@ extern "C" int gs_draw_bwd(const float* pos, const float* rgb, const float* opa,
   g.fx = focal_x;
   g.fy = focal_y;
   if (d == 3) {
-    GS_CUDA_TRY(gs_launch_blend_bwd(ws.pA, ws.pB, ws.pC, tile_n_point_accum, g, image, grad_image, ws.grad_inst, 0,
+    GS_CUDA_TRY(gs_launch_blend_bwd(ws.pA, ws.pB, ws.pC, nullptr, nullptr, tile_n_point_accum, g, image, grad_image,
+                                    ws.grad_inst, 0,
                                     GsCrop{}, nullptr, 0u, nullptr, st));
     legacy_unpack_grads_kernel<<<(m + 255) / 256, 256, 0, st>>>(ws.grad_inst, opa, cov, m, grad_pos, grad_rgb,
                                                               grad_opa, grad_cov);

@@ -39,6 +39,8 @@ struct GsTuning {
   int bwd_stages;   // staging ring depth: 2 or 3
   int bwd_minb;     // __launch_bounds__ min blocks (register cap); 1 = none
   int bwd_rq;       // reducer threads per instance in the second phase: 4 (16 instances per round) or 8 (8)
+  int fwd_px;       // pixels per thread of forward kernel 0: 4 (2 warps per tile) or 8 (1 warp)
+  int gather;       // RGB frame path: 1 = no pack pass, blend kernels gather records from rec[N]; 0 = packed streams
 };
 GsTuning& gs_tuning();
 
@@ -80,8 +82,12 @@ cudaError_t gs_launch_fused_project_bwd(const float* pos, const float* rgb, cons
                                         float* g_quat, float* g_scale, const GsGradPush& push, cudaStream_t st);
 
 // ---- binning.cu ------------------------------------------------------------------------
-cudaError_t gs_launch_emit_keys(const GsRec* rec, const uint32_t* perm, const uint32_t* offsets_sorted, int n, int ntx,
-                                void* keys, int key_bytes, uint32_t* vals, cudaStream_t st);
+// offsets_g != nullptr: also completes rec[g].d.x (first gradient row) for the gather path
+cudaError_t gs_launch_emit_keys(GsRec* rec, const uint32_t* perm, const uint32_t* offsets_sorted,
+                                const uint32_t* offsets_g, int n, int ntx, void* keys, int key_bytes, uint32_t* vals,
+                                cudaStream_t st);
+cudaError_t gs_launch_tile_ranges(const void* keys, int key_bytes, long long m, int n_tiles, int* tile_accum,
+                                  cudaStream_t st);
 
 cudaError_t gs_launch_pack_sorted(const void* keys, int key_bytes, const uint32_t* vals, long long m, int n_tiles,
                                   int ntx, const GsRec* rec, const uint32_t* offsets_g, float4* pA, float2* pB, float4* pC,
@@ -93,12 +99,15 @@ cudaError_t gs_launch_pack_sorted_sh(const void* keys, int key_bytes, const uint
 cudaError_t gs_launch_iota(uint32_t* out, int n, cudaStream_t st);
 
 // ---- blend.cu --------------------------------------------------------------------------
-cudaError_t gs_launch_blend_fwd(const float4* pA, const float2* pB, const float4* pC, const int* tile_accum,
-                                const GsFrameGeom& g, float* image, int* tile_neff, float* final_img, const GsCrop& crop,
-                                cudaStream_t st);
+// grec / ids != nullptr: gather path (records pulled straight from rec[N] through the sorted id list; the packed
+// stream pointers are ignored); else the packed streams written by the pack pass / the legacy draw API.
+cudaError_t gs_launch_blend_fwd(const float4* pA, const float2* pB, const float4* pC, const GsRec* grec,
+                                const uint32_t* ids, const int* tile_accum, const GsFrameGeom& g, float* image,
+                                int* tile_neff, float* final_img, const GsCrop& crop, cudaStream_t st);
 
-cudaError_t gs_launch_blend_bwd(const float4* pA, const float2* pB, const float4* pC, const int* tile_accum,
-                                const GsFrameGeom& g, const float* image, const float* grad_image,
-                                float* grad_inst /*[M,GS_GREC] rows addressed by C.w slot*/, int grad_is_final,
-                                const GsCrop& crop, uint32_t* row_epoch /*nullable*/, uint32_t epoch,
-                                int* tile_neff_b /*nullable: instances the backward consumed per tile*/, cudaStream_t st);
+cudaError_t gs_launch_blend_bwd(const float4* pA, const float2* pB, const float4* pC, const GsRec* grec,
+                                const uint32_t* ids, const int* tile_accum, const GsFrameGeom& g, const float* image,
+                                const float* grad_image, float* grad_inst /*[M,GS_GREC] rows addressed by slot*/,
+                                int grad_is_final, const GsCrop& crop, uint32_t* row_epoch /*nullable (packed only)*/,
+                                uint32_t epoch, int* tile_neff_b /*nullable: instances the backward consumed per tile*/,
+                                cudaStream_t st);

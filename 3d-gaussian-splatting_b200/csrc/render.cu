@@ -45,9 +45,11 @@ static int tune_env(const char* name, int dflt) {
   return e ? atoi(e) : dflt;
 }
 GsTuning& gs_tuning() {
-  static GsTuning t = {tune_env("GS_TUNE_FWD_KERNEL", 1),  tune_env("GS_TUNE_FWD_CH", 256),   tune_env("GS_TUNE_BWD_KERNEL", 1),
-                       tune_env("GS_TUNE_BWD_PX", 4),      tune_env("GS_TUNE_BWD_WS", 1),     tune_env("GS_TUNE_BWD_UNROLL", 1),
-                       tune_env("GS_TUNE_BWD_STAGES", 3),  tune_env("GS_TUNE_BWD_MINB", 1),   tune_env("GS_TUNE_BWD_RQ", 4)};
+  // shipped configuration = the best of the sweeps in profiles/r2_sweeps.md
+  static GsTuning t = {tune_env("GS_TUNE_FWD_KERNEL", 0),  tune_env("GS_TUNE_FWD_CH", 256),   tune_env("GS_TUNE_BWD_KERNEL", 1),
+                       tune_env("GS_TUNE_BWD_PX", 8),      tune_env("GS_TUNE_BWD_WS", 0),     tune_env("GS_TUNE_BWD_UNROLL", 2),
+                       tune_env("GS_TUNE_BWD_STAGES", 2),  tune_env("GS_TUNE_BWD_MINB", 16),  tune_env("GS_TUNE_BWD_RQ", 4),
+                       tune_env("GS_TUNE_FWD_PX", 4),      tune_env("GS_TUNE_GATHER", 1)};
   return t;
 }
 extern "C" int gs_tune(const char* name, int value) {
@@ -57,7 +59,8 @@ extern "C" int gs_tune(const char* name, int value) {
                                              {"bwd_kernel", &t.bwd_kernel}, {"bwd_px", &t.bwd_px},
                                              {"bwd_ws", &t.bwd_ws},         {"bwd_unroll", &t.bwd_unroll},
                                              {"bwd_stages", &t.bwd_stages}, {"bwd_minb", &t.bwd_minb},
-                                             {"bwd_rq", &t.bwd_rq}};
+                                             {"bwd_rq", &t.bwd_rq},         {"fwd_px", &t.fwd_px},
+                                             {"gather", &t.gather}};
   for (auto& e : tab)
     if (!strcmp(e.k, name)) {
       *e.v = value;
@@ -113,7 +116,7 @@ struct gs_ctx {
   unsigned long long* host_m = nullptr;   // pinned: {M}
   cudaEvent_t ev_m = nullptr;             // marks the completion of the M read-back
   // state of the last forward
-  bool have_forward = false, have_backward = false;
+  bool have_forward = false, have_backward = false, gather = false;
   int n = 0, d = 3, scale_act = 0;
   long long m = 0;
   GsCam cam{};
@@ -331,22 +334,26 @@ static int render_forward_impl(gs_ctx* c, const float* pos, const float* rgb, co
   long long m = (long long)*c->host_m;
   size_t M = (size_t)m;
 
+  const bool gather = d == 3 && gs_tuning().gather != 0;
   gs_mark(c, 2, st);
   // tile-id sort key width (GS_TILE_KEY_BYTES=4 forces the wide path, for tests)
   static const int forced_key = getenv("GS_TILE_KEY_BYTES") ? atoi(getenv("GS_TILE_KEY_BYTES")) : 0;
   const int key_bytes = (g.n_tiles <= 65536 && forced_key != 4) ? 2 : 4;
-  GS_CUDA_TRY(c->pA.reserve(M * 16 + 16, st));
   const size_t crow = d == 3 ? 16 : (size_t)gs_sh_stream_width(d) * 4;   // colour / SH stream row bytes
-  GS_CUDA_TRY(c->pC.reserve(M * crow + 16, st));
-  GS_CUDA_TRY(c->pB.reserve((M + 2) * 8, st));
+  if (!gather) {
+    GS_CUDA_TRY(c->pA.reserve(M * 16 + 16, st));
+    GS_CUDA_TRY(c->pC.reserve(M * crow + 16, st));
+    GS_CUDA_TRY(c->pB.reserve((M + 2) * 8, st));
+  }
   if (m > 0) {
     GS_CUDA_TRY(c->keys_in.reserve(M * 4 + 16, st));
     GS_CUDA_TRY(c->keys_out.reserve(M * 4 + 16, st));
     GS_CUDA_TRY(c->vals_in.reserve(M * 4, st));
     GS_CUDA_TRY(c->vals_out.reserve(M * 4, st));
     // 3. instances in (depth, id) order: tile-id keys + Gaussian-id values
-    GS_CUDA_TRY(gs_launch_emit_keys(c->rec.as<GsRec>(), c->perm.as<uint32_t>(), c->offsets.as<uint32_t>(), n, g.ntx,
-                                    c->keys_in.p, key_bytes, c->vals_in.as<uint32_t>(), st));
+    GS_CUDA_TRY(gs_launch_emit_keys(c->rec.as<GsRec>(), c->perm.as<uint32_t>(), c->offsets.as<uint32_t>(),
+                                    gather ? c->offsets_g.as<uint32_t>() : nullptr, n, g.ntx, c->keys_in.p, key_bytes,
+                                    c->vals_in.as<uint32_t>(), st));
     gs_count_launch();
     // 4. stable radix sort on the tile id only -> (tile, depth, id)
     gs_mark(c, 3, st);
@@ -374,7 +381,11 @@ static int render_forward_impl(gs_ctx* c, const float* pos, const float* rgb, co
   // 5. tile ranges + packed sorted record streams
   if (m == 0) gs_mark(c, 3, st);
   gs_mark(c, 4, st);
-  if (d == 3) {
+  if (gather) {
+    // no pack pass: only the tile ranges are derived from the sorted keys; the blend kernels pull the records
+    // of their tile straight from rec[N] through the sorted id list
+    GS_CUDA_TRY(gs_launch_tile_ranges(c->keys_out.p, key_bytes, m, g.n_tiles, c->tile_accum.as<int>(), st));
+  } else if (d == 3) {
     GS_CUDA_TRY(gs_launch_pack_sorted(c->keys_out.p, key_bytes, c->vals_out.as<uint32_t>(), m, g.n_tiles, g.ntx,
                                       c->rec.as<GsRec>(), c->offsets_g.as<uint32_t>(), c->pA.as<float4>(),
                                       c->pB.as<float2>(), c->pC.as<float4>(), c->tile_accum.as<int>(), st));
@@ -384,12 +395,13 @@ static int render_forward_impl(gs_ctx* c, const float* pos, const float* rgb, co
                                          gs_sh_stream_width(d), c->pA.as<float4>(), c->pB.as<float2>(),
                                          c->pC.as<float>(), c->tile_accum.as<int>(), st));
   }
-  if (m > 0) gs_count_launch();   // pack
+  if (m > 0) gs_count_launch();   // pack, or the tile-range pass of the gather path
   // 6. blend (+ optional fused clamp & centre crop, splatter.py:652-653 / :267-272)
   GsCrop crop{(g.wp - g.width) / 2, (g.hp - g.height) / 2, g.width, g.height};
   gs_mark(c, 5, st);
   if (d == 3) {
     GS_CUDA_TRY(gs_launch_blend_fwd(c->pA.as<float4>(), c->pB.as<float2>(), c->pC.as<float4>(),
+                                    gather ? c->rec.as<GsRec>() : nullptr, c->vals_out.as<uint32_t>(),
                                     c->tile_accum.as<int>(), g, image, c->tile_neff.as<int>(), final_img, crop, st));
   } else {
     const float* rp = c->rays.as<float>();
@@ -403,6 +415,7 @@ static int render_forward_impl(gs_ctx* c, const float* pos, const float* rgb, co
   c->ev_fwd_valid = c->timing && c->ev_ok;
 
   c->have_forward = true;
+  c->gather = gather;
   c->n = n;
   c->d = d;
   c->scale_act = scale_activation;
@@ -464,6 +477,7 @@ static int render_backward_impl(gs_ctx* c, const float* pos, const float* rgb, c
   if (c->m > 0) {
     if (d == 3) {
       GS_CUDA_TRY(gs_launch_blend_bwd(c->pA.as<float4>(), c->pB.as<float2>(), c->pC.as<float4>(),
+                                      c->gather ? c->rec.as<GsRec>() : nullptr, c->vals_out.as<uint32_t>(),
                                       c->tile_accum.as<int>(), c->geom, image, grad_image, c->grad_inst.as<float>(),
                                       grad_is_final, crop, c->row_epoch.as<uint32_t>(), c->epoch,
                                       c->tile_neff_b.as<int>(), st));

@@ -19,8 +19,8 @@ import torch
 import torch.nn.functional as F
 
 
-def gaussian_window(kernel_size=11, sigma=1.5, dtype=torch.float64):
-    dist = torch.arange((1 - kernel_size) / 2, (1 + kernel_size) / 2, 1, dtype=dtype)
+def gaussian_window(kernel_size=11, sigma=1.5, dtype=torch.float64, device=None):
+    dist = torch.arange((1 - kernel_size) / 2, (1 + kernel_size) / 2, 1, dtype=dtype, device=device)
     g = torch.exp(-((dist / sigma) ** 2) / 2)
     return g / g.sum()
 
@@ -31,7 +31,7 @@ def ssim(pred_hwc, target_hwc, data_range=1.0, k1=0.01, k2=0.03):
     x = pred_hwc.permute(2, 0, 1).unsqueeze(0)
     y = target_hwc.to(dt).permute(2, 0, 1).unsqueeze(0)
     c1, c2 = (k1 * data_range) ** 2, (k2 * data_range) ** 2
-    w1 = gaussian_window(dtype=dt)
+    w1 = gaussian_window(dtype=dt, device=x.device)
     ch = x.shape[1]
     kernel = (w1.unsqueeze(1) @ w1.unsqueeze(0)).expand(ch, 1, 11, 11).contiguous()
     pad = 5

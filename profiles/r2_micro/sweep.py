@@ -22,31 +22,30 @@ sp._rctx.set_timing(True)
 go = S.make_grad_output(h, w, 0).to(dev)
 params = list(sp.gaussian_3ds.parameters())
 
-BASE = dict(fwd_kernel=1, fwd_ch=256, bwd_kernel=1, bwd_px=4, bwd_ws=1, bwd_unroll=1, bwd_stages=3, bwd_minb=1, bwd_rq=4)
+BASE = dict(fwd_kernel=0, fwd_ch=256, fwd_px=4, bwd_kernel=1, bwd_px=8, bwd_ws=0, bwd_unroll=2, bwd_stages=2, bwd_minb=16, bwd_rq=4,
+            gather=0)
 VARIANTS = [
-    ("r1 kernels (thread-0 issue, shuffle reduction)", dict(fwd_kernel=0, bwd_kernel=0)),
-    ("r1 fwd ch128", dict(fwd_kernel=0, fwd_ch=128, bwd_kernel=0)),
-    ("r1 fwd ch64", dict(fwd_kernel=0, fwd_ch=64, bwd_kernel=0)),
-    ("ws fwd + bwd2 ws rq4 (first r2 version)", dict()),
-    ("bwd2 ws rq4 minb8", dict(bwd_minb=8)),
-    ("bwd2 ws rq4 unroll4 minb8", dict(bwd_unroll=4, bwd_minb=8)),
-    ("bwd2 ws rq8 st2 minb8", dict(bwd_rq=8, bwd_stages=2, bwd_minb=8)),
-    ("bwd2 ws rq8 st2 minb10", dict(bwd_rq=8, bwd_stages=2, bwd_minb=10)),
-    ("bwd2 ws rq8 st2 unroll4 minb10", dict(bwd_rq=8, bwd_stages=2, bwd_unroll=4, bwd_minb=10)),
-    ("bwd2 t0-issue rq4 st2", dict(bwd_ws=0, bwd_stages=2)),
-    ("bwd2 t0-issue rq4 st2 minb7", dict(bwd_ws=0, bwd_stages=2, bwd_minb=7)),
-    ("bwd2 t0-issue rq8 st2 minb10", dict(bwd_ws=0, bwd_rq=8, bwd_stages=2, bwd_minb=10)),
-    ("bwd2 t0-issue rq8 st2 minb12", dict(bwd_ws=0, bwd_rq=8, bwd_stages=2, bwd_minb=12)),
-    ("bwd2 t0-issue rq8 st2 unroll2 minb10", dict(bwd_ws=0, bwd_rq=8, bwd_stages=2, bwd_unroll=2, bwd_minb=10)),
-    ("bwd2 t0-issue rq8 st2 unroll4 minb10", dict(bwd_ws=0, bwd_rq=8, bwd_stages=2, bwd_unroll=4, bwd_minb=10)),
-    ("bwd2 t0-issue px8 rq4 st2 minb10", dict(bwd_ws=0, bwd_px=8, bwd_stages=2, bwd_minb=10)),
+    ("r1 kernels (packed, thread-0 issue, shuffle reduction)", dict(bwd_kernel=0, bwd_px=4)),
+    ("packed: bwd2 px8 t0 rq4 st2 unroll2 minb16", dict()),
+    ("packed: bwd2 px8 unroll2 minb10", dict(bwd_minb=10)),
+    ("packed: bwd2 px8 unroll4 minb10", dict(bwd_unroll=4, bwd_minb=10)),
+    ("packed: bwd2 px4 unroll4", dict(bwd_px=4, bwd_unroll=4, bwd_minb=1)),
+    ("gather: fwd ch256 + bwd2 px8 unroll2 minb16", dict(gather=1)),
+    ("gather: fwd ch128", dict(gather=1, fwd_ch=128)),
+    ("gather: fwd ch64", dict(gather=1, fwd_ch=64)),
+    ("gather: fwd px8 ch128", dict(gather=1, fwd_ch=128, fwd_px=8)),
+    ("gather: bwd2 px8 unroll2 minb10", dict(gather=1, bwd_minb=10)),
+    ("gather: bwd2 px8 unroll4 minb10", dict(gather=1, bwd_unroll=4, bwd_minb=10)),
+    ("gather: bwd2 px8 unroll2 st3 minb16", dict(gather=1, bwd_stages=3)),
+    ("gather: bwd2 px8 unroll1 minb16", dict(gather=1, bwd_unroll=1)),
+    ("gather: bwd2 px4 unroll4", dict(gather=1, bwd_px=4, bwd_unroll=4, bwd_minb=1)),
 ]
 
 
 def run(cfg, frames=8):
     for k, val in {**BASE, **cfg}.items():
         gaussian.tune(k, val)
-    f = b = tot = 0.0
+    f = b = tot = pk = 0.0
     for it in range(3 + frames):
         for p in params:
             p.grad = None
@@ -60,15 +59,16 @@ def run(cfg, frames=8):
             st = sp._rctx.stage_ms()
             f += st[5] / frames
             b += st[6] / frames
+            pk += st[4] / frames
             tot += e0.elapsed_time(e1) / frames
-    return f, b, tot, img.detach().clone(), [p.grad.clone() for p in params]
+    return f, b, tot, img.detach().clone(), [p.grad.clone() for p in params], pk
 
 
 ref = None
 rows = []
 for name, cfg in VARIANTS:
     try:
-        f, b, tot, img, grads = run(cfg)
+        f, b, tot, img, grads, pk = run(cfg)
     except Exception as e:
         print(f"{name:48s} FAILED: {str(e)[:120]}", flush=True)
         continue
@@ -79,5 +79,5 @@ for name, cfg in VARIANTS:
         err = max(float((img - ref[0]).abs().max()),
                   max(float((a - r).abs().max() / (r.abs().max() + 1e-30)) for a, r in zip(grads, ref[1])))
     rows.append(dict(name=name, cfg=cfg, blend_fwd_ms=round(f, 4), blend_bwd_ms=round(b, 4), frame_ms=round(tot, 4), max_dev_vs_first=err))
-    print(f"{name:48s} fwd {f:.4f}  bwd {b:.4f}  frame {tot:.4f}  dev {err:.1e}", flush=True)
+    print(f"{name:56s} pack/ranges {pk:.4f}  fwd {f:.4f}  bwd {b:.4f}  frame {tot:.4f}  dev {err:.1e}", flush=True)
 json.dump(rows, open(os.path.join(ROOT, "gpurun_out", f"sweep_{wl}.json"), "w"), indent=1)
