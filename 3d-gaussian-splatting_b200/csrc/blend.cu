@@ -1230,7 +1230,8 @@ extern "C" int gs_draw_fwd(const float* pos, const float* rgb, const float* opa,
                                     GsCrop{}, st));
   } else {
     GsRayPtrs r{rays_o, lefttop, vec_dx, vec_dy};
-    GS_CUDA_TRY(gs_launch_blend_sh_fwd(ws.pA, ws.pB, reinterpret_cast<float*>(ws.pC), d, tile_n_point_accum, g, r,
+    GS_CUDA_TRY(gs_launch_blend_sh_fwd(ws.pA, ws.pB, reinterpret_cast<float*>(ws.pC), nullptr, nullptr, nullptr, d,
+                                       tile_n_point_accum, g, r,
                                        image, nullptr, nullptr, GsCrop{}, st));
   }
   gs_count_launch();
@@ -1275,7 +1276,8 @@ extern "C" int gs_draw_bwd(const float* pos, const float* rgb, const float* opa,
                                                               grad_opa, grad_cov);
   } else {
     GsRayPtrs r{rays_o, lefttop, vec_dx, vec_dy};
-    GS_CUDA_TRY(gs_launch_blend_sh_bwd(ws.pA, ws.pB, reinterpret_cast<float*>(ws.pC), d, tile_n_point_accum, g, r,
+    GS_CUDA_TRY(gs_launch_blend_sh_bwd(ws.pA, ws.pB, reinterpret_cast<float*>(ws.pC), nullptr, nullptr, nullptr, d,
+                                       tile_n_point_accum, g, r,
                                        image, grad_image, ws.grad_inst, 0, GsCrop{}, nullptr, 0u, nullptr, st));
     legacy_unpack_grads_sh_kernel<<<(m + 255) / 256, 256, 0, st>>>(ws.grad_inst, gs_sh_grad_width(d), opa, cov, m, d,
                                                                  grad_pos, grad_rgb, grad_opa, grad_cov);

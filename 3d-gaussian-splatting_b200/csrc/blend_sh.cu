@@ -6,6 +6,8 @@
 // (degree 3, D = 48; svox2's C3 constants, defined but unused in the reference :395-403) is the
 // extension BASELINE.json's configs[2] asks for.  Same staging / early-exit / reduction design
 // as blend.cu; the third stream carries the 3K coefficients + the gradient slot per instance.
+#include <type_traits>
+
 #include "internal.h"
 
 namespace {
@@ -82,14 +84,89 @@ __device__ __forceinline__ void issue_sh(SM& sm, int stage, const float4* __rest
   gs_bulk_g2s(sm.B[stage], pB + (base - shift), bytes_b, &sm.full[stage]);
 }
 
+// Gather staging (no pack pass): per instance the Gaussian's 64-byte record (centre, conic, log2 opacity, tile
+// rectangle, first gradient row) comes straight from GsRec rec[N] with ONE 1-D bulk copy (TMA engine), and its 3K
+// raw coefficients straight from the parameter tensor rgb[N, 3K]: one more bulk copy when the row is 16-byte
+// aligned (K = 16: 192 B), else 3K 4-byte cp.async (K = 9: rows of 108 B are only 4-byte aligned).  Every thread
+// of the CTA issues the copies of "its" instances of the chunk and arrives on the stage's mbarrier (count = CTA
+// threads): bulk bytes via expect_tx, cp.async completion via cp.async.mbarrier.arrive.noinc.
+template <int K, int CH, int STAGES>
+struct ShGatherStage {
+  float4 R[STAGES][CH * 4];
+  float S[STAGES][CH * sh_sw(K)];
+  uint64_t full[STAGES];
+};
+
+template <int K, int NT, typename SM>
+__device__ __forceinline__ void issue_sh_gather(SM& sm, int stage, const GsRec* __restrict__ grec,
+                                                const float* __restrict__ rgb, const uint32_t* __restrict__ ids,
+                                                int base, int n, int tid) {
+  constexpr int SW = sh_sw(K), D = 3 * K;
+  const uint32_t bar = gs_smem_u32(&sm.full[stage]);
+  uint32_t bytes = 0;
+  for (int i = tid; i < n; i += NT) {
+    const uint32_t id = ids[base + i];
+    gs_bulk_g2s(&sm.R[stage][i * 4], grec + id, 64u, &sm.full[stage]);
+    bytes += 64u;
+    const float* src = rgb + (size_t)id * D;
+    float* dst = &sm.S[stage][i * SW];
+    if ((D * 4) % 16 == 0) {
+      gs_bulk_g2s(dst, src, (uint32_t)(D * 4), &sm.full[stage]);
+      bytes += (uint32_t)(D * 4);
+    } else {
+#pragma unroll
+      for (int q = 0; q < D; ++q)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(gs_smem_u32(dst + q)), "l"(src + q) : "memory");
+    }
+  }
+  if ((D * 4) % 16 == 0) {
+    gs_mbar_expect_tx(&sm.full[stage], bytes);                      // arrive + bytes
+  } else {
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");   // the arrival
+  }
+}
+
+// view of one stage: packed streams (pack pass / legacy draw API) or gathered records
+template <int K, bool GATHER>
+struct ShView;
+template <int K>
+struct ShView<K, false> {
+  const float4* A;
+  const float2* B;
+  const float* S;
+  __device__ __forceinline__ float4 a(int j) const { return A[j]; }
+  __device__ __forceinline__ float2 b(int j) const { return B[j]; }
+  __device__ __forceinline__ const float* coef(int j) const { return S + j * sh_sw(K); }
+  __device__ __forceinline__ uint32_t slot(int j, int, int) const { return __float_as_uint(S[j * sh_sw(K) + 3 * K]); }
+};
+template <int K>
+struct ShView<K, true> {
+  const float4* R;
+  const float* S;
+  __device__ __forceinline__ float4 a(int j) const { return R[4 * j]; }
+  __device__ __forceinline__ float2 b(int j) const {
+    const float4 t = R[4 * j + 1];
+    return make_float2(t.x, t.y);
+  }
+  __device__ __forceinline__ const float* coef(int j) const { return S + j * sh_sw(K); }
+  __device__ __forceinline__ uint32_t slot(int j, int tx, int ty) const {
+    const float4 cc = R[4 * j + 2];
+    const uint32_t rxy = __float_as_uint(cc.z), rwh = __float_as_uint(cc.w);
+    return __float_as_uint(R[4 * j + 3].x) + ((uint32_t)ty - (rxy >> 16)) * (rwh & 0xffffu) + ((uint32_t)tx - (rxy & 0xffffu));
+  }
+};
+
 __device__ __forceinline__ float sh_sigmoid(float x) { return gs_rcp(1.f + gs_ex2(-x * GS_LOG2E)); }
 
 // ---------------------------------------------------------------------------------------
 // forward: 64 threads per tile, a row of 4 pixels per thread
 // ---------------------------------------------------------------------------------------
-template <int K>
+template <int K, bool GATHER>
 __global__ void __launch_bounds__(64) blend_sh_fwd_kernel(const float4* __restrict__ pA, const float2* __restrict__ pB,
                                                            const float* __restrict__ pS,
+                                                           const GsRec* __restrict__ grec, const float* __restrict__ rgb,
+                                                           const uint32_t* __restrict__ ids,
                                                            const int* __restrict__ tile_accum, int wp, int hp, int ntx,
                                                            float fx, float fy, const float* __restrict__ rays_o,
                                                            const float* __restrict__ lefttop,
@@ -97,8 +174,8 @@ __global__ void __launch_bounds__(64) blend_sh_fwd_kernel(const float4* __restri
                                                            const float* __restrict__ vdy, float* __restrict__ image,
                                                            int* __restrict__ tile_neff,
                                                            float* __restrict__ final_img, GsCrop crop) {
-  constexpr int CH = 64, STAGES = 2, PX = 4, SW = sh_sw(K);
-  using SM = ShStage<K, CH, STAGES>;
+  constexpr int CH = 64, STAGES = 2, PX = 4, SW = sh_sw(K), NT = 64;
+  using SM = typename std::conditional<GATHER, ShGatherStage<K, CH, STAGES>, ShStage<K, CH, STAGES>>::type;
   __shared__ __align__(16) SM sm;
   const int tile = blockIdx.x, tid = threadIdx.x;
   const int tx = tile % ntx, ty = tile / ntx;
@@ -116,13 +193,17 @@ __global__ void __launch_bounds__(64) blend_sh_fwd_kernel(const float4* __restri
   const int shift = start & 1;
   const int nchunks = (cnt + CH - 1) / CH;
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) gs_mbar_init(&sm.full[s], 1);
+    for (int s = 0; s < STAGES; ++s) gs_mbar_init(&sm.full[s], GATHER ? NT : 1);
     gs_fence_barrier_init();
   }
   __syncthreads();
-  if (tid == 0)
+  if constexpr (GATHER) {
+    for (int k = 0; k < STAGES && k < nchunks; ++k)
+      issue_sh_gather<K, NT>(sm, k, grec, rgb, ids, start + k * CH, min(CH, cnt - k * CH), tid);
+  } else if (tid == 0) {
     for (int k = 0; k < STAGES && k < nchunks; ++k)
       issue_sh<K>(sm, k, pA, pB, pS, start + k * CH, min(CH, cnt - k * CH), shift);
+  }
 
   float T[PX], cr[PX], cg[PX], cb[PX];
 #pragma unroll
@@ -135,19 +216,24 @@ __global__ void __launch_bounds__(64) blend_sh_fwd_kernel(const float4* __restri
     const int stage = k % STAGES;
     gs_mbar_wait(&sm.full[stage], (uint32_t)((k / STAGES) & 1));
     const int n = min(CH, cnt - k * CH);
-    const float4* __restrict__ sA = sm.A[stage];
-    const float2* __restrict__ sB = sm.B[stage] + shift;
-    const float* __restrict__ sS = sm.S[stage];
+    ShView<K, GATHER> sv;
+    if constexpr (GATHER) {
+      sv.R = sm.R[stage];
+    } else {
+      sv.A = sm.A[stage];
+      sv.B = sm.B[stage] + shift;
+    }
+    sv.S = sm.S[stage];
     for (int j = 0; j < n; ++j) {
       if ((j & 3) == 0) {
         const bool dead = !(T[0] > GS_T_STOP) && !(T[1] > GS_T_STOP) && !(T[2] > GS_T_STOP) && !(T[3] > GS_T_STOP);
         if (__all_sync(0xffffffffu, dead)) break;
       }
-      const float4 a = sA[j];
-      const float2 b = sB[j];
+      const float4 a = sv.a(j);
+      const float2 b = sv.b(j);
       float cf[3 * K];
       {
-        const float4* c4 = reinterpret_cast<const float4*>(sS + j * SW);
+        const float4* c4 = reinterpret_cast<const float4*>(sv.coef(j));
 #pragma unroll
         for (int q = 0; q < (3 * K + 3) / 4; ++q) {
           const float4 t4 = c4[q];
@@ -187,9 +273,12 @@ __global__ void __launch_bounds__(64) blend_sh_fwd_kernel(const float4* __restri
       consumed = min(cnt, (k + 1) * CH);
       break;
     }
-    if (tid == 0 && k + STAGES < nchunks) {
+    if (k + STAGES < nchunks) {
       const int kn = k + STAGES;
-      issue_sh<K>(sm, stage, pA, pB, pS, start + kn * CH, min(CH, cnt - kn * CH), shift);
+      if constexpr (GATHER)
+        issue_sh_gather<K, NT>(sm, stage, grec, rgb, ids, start + kn * CH, min(CH, cnt - kn * CH), tid);
+      else if (tid == 0)
+        issue_sh<K>(sm, stage, pA, pB, pS, start + kn * CH, min(CH, cnt - kn * CH), shift);
     }
   }
   if (tid == 0 && k < nchunks)
@@ -243,15 +332,17 @@ __device__ __forceinline__ float reduce8(float* v, int lane) {
 // backward: 64 threads per tile, a row of 4 pixels per thread
 // grad row (GS_SH_GREC(K) floats): d/d{x, y, ca, cb, cc, l2o}, d/d coef[0..3K)
 // ---------------------------------------------------------------------------------------
-template <int K>
+template <int K, bool GATHER>
 struct ShBwdSmem {
-  ShStage<K, 32, 2> st;
+  typename std::conditional<GATHER, ShGatherStage<K, 32, 2>, ShStage<K, 32, 2>>::type st;
   float partial[2][32 * sh_nvp(K)];
 };
 
-template <int K>
+template <int K, bool GATHER>
 __global__ void __launch_bounds__(64) blend_sh_bwd_kernel(const float4* __restrict__ pA, const float2* __restrict__ pB,
                                                            const float* __restrict__ pS,
+                                                           const GsRec* __restrict__ grec, const float* __restrict__ rgb,
+                                                           const uint32_t* __restrict__ ids,
                                                            const int* __restrict__ tile_accum, int wp, int hp, int ntx,
                                                            float fx, float fy, const float* __restrict__ rays_o,
                                                            const float* __restrict__ lefttop,
@@ -264,7 +355,7 @@ __global__ void __launch_bounds__(64) blend_sh_bwd_kernel(const float4* __restri
                                                            uint32_t epoch, int* __restrict__ tile_neff_b) {
   constexpr int CH = 32, STAGES = 2, PX = 4, SW = sh_sw(K), NV = sh_nv(K), NVP = sh_nvp(K), THREADS = 64;
   constexpr int GREC = (NV + 3) / 4 * 4;
-  __shared__ __align__(16) ShBwdSmem<K> smem;
+  __shared__ __align__(16) ShBwdSmem<K, GATHER> smem;
   auto& sm = smem.st;
   const int tile = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tx = tile % ntx, ty = tile / ntx;
@@ -308,22 +399,31 @@ __global__ void __launch_bounds__(64) blend_sh_bwd_kernel(const float4* __restri
     for (int p = 0; p < PX; ++p) T[p] = 1.f;
   }
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) gs_mbar_init(&sm.full[s], 1);
+    for (int s = 0; s < STAGES; ++s) gs_mbar_init(&sm.full[s], GATHER ? THREADS : 1);
     gs_fence_barrier_init();
   }
   __syncthreads();
-  if (tid == 0)
+  if constexpr (GATHER) {
+    for (int k = 0; k < STAGES && k < nchunks; ++k)
+      issue_sh_gather<K, THREADS>(sm, k, grec, rgb, ids, start + k * CH, min(CH, cnt - k * CH), tid);
+  } else if (tid == 0) {
     for (int k = 0; k < STAGES && k < nchunks; ++k)
       issue_sh<K>(sm, k, pA, pB, pS, start + k * CH, min(CH, cnt - k * CH), shift);
+  }
 
   int consumed = cnt, k = 0;
   for (; k < nchunks; ++k) {
     const int stage = k % STAGES;
     gs_mbar_wait(&sm.full[stage], (uint32_t)((k / STAGES) & 1));
     const int n = min(CH, cnt - k * CH);
-    const float4* __restrict__ sA = sm.A[stage];
-    const float2* __restrict__ sB = sm.B[stage] + shift;
-    const float* __restrict__ sS = sm.S[stage];
+    ShView<K, GATHER> sv;
+    if constexpr (GATHER) {
+      sv.R = sm.R[stage];
+    } else {
+      sv.A = sm.A[stage];
+      sv.B = sm.B[stage] + shift;
+    }
+    sv.S = sm.S[stage];
     float* __restrict__ part = smem.partial[warp];
     int j = 0;
     for (; j < n; ++j) {
@@ -331,11 +431,11 @@ __global__ void __launch_bounds__(64) blend_sh_bwd_kernel(const float4* __restri
         const bool dead = !(T[0] > GS_T_STOP) && !(T[1] > GS_T_STOP) && !(T[2] > GS_T_STOP) && !(T[3] > GS_T_STOP);
         if (__all_sync(0xffffffffu, dead)) break;
       }
-      const float4 a = sA[j];
-      const float2 b = sB[j];
+      const float4 a = sv.a(j);
+      const float2 b = sv.b(j);
       float cf[3 * K];
       {
-        const float4* c4 = reinterpret_cast<const float4*>(sS + j * SW);
+        const float4* c4 = reinterpret_cast<const float4*>(sv.coef(j));
 #pragma unroll
         for (int q = 0; q < (3 * K + 3) / 4; ++q) {
           const float4 t4 = c4[q];
@@ -406,9 +506,9 @@ __global__ void __launch_bounds__(64) blend_sh_bwd_kernel(const float4* __restri
     for (int t = tid; t < n; t += THREADS) {
       const float* p0 = smem.partial[0] + t * NVP;
       const float* p1 = smem.partial[1] + t * NVP;
-      const float4 a = sA[t];
-      const float2 b = sB[t];
-      const uint32_t slot = __float_as_uint(sS[t * SW + 3 * K]);
+      const float4 a = sv.a(t);
+      const float2 b = sv.b(t);
+      const uint32_t slot = sv.slot(t, tx, ty);
       float* out = grad_inst + (size_t)slot * GREC;
       float s[6];
 #pragma unroll
@@ -427,16 +527,19 @@ __global__ void __launch_bounds__(64) blend_sh_bwd_kernel(const float4* __restri
       consumed = min(cnt, (k + 1) * CH);
       break;
     }
-    if (tid == 0 && k + STAGES < nchunks) {
+    if (k + STAGES < nchunks) {
       const int kn = k + STAGES;
-      issue_sh<K>(sm, stage, pA, pB, pS, start + kn * CH, min(CH, cnt - kn * CH), shift);
+      if constexpr (GATHER)
+        issue_sh_gather<K, THREADS>(sm, stage, grec, rgb, ids, start + kn * CH, min(CH, cnt - kn * CH), tid);
+      else if (tid == 0)
+        issue_sh<K>(sm, stage, pA, pB, pS, start + kn * CH, min(CH, cnt - kn * CH), shift);
     }
   }
   if (tid == 0 && k < nchunks)
     for (int kk = k + 1; kk < nchunks && kk < k + STAGES; ++kk)
       gs_mbar_wait(&sm.full[kk % STAGES], (uint32_t)((kk / STAGES) & 1));
   if (tile_neff_b && tid == 0) tile_neff_b[tile] = consumed;
-  if (row_epoch) return;   // stale rows are skipped by the consumer (see blend.cu)
+  if (row_epoch || GATHER) return;   // stale rows are skipped by the consumer (see blend.cu)
   for (int t = consumed + tid; t < cnt; t += THREADS) {
     const uint32_t slot = __float_as_uint(pS[(size_t)(start + t) * SW + 3 * K]);
     float* out = grad_inst + (size_t)slot * GREC;
@@ -450,29 +553,38 @@ int gs_sh_basis_count(int d) { return d == 27 ? 9 : (d == 48 ? 16 : 0); }
 int gs_sh_stream_width(int d) { return d == 27 ? sh_sw(9) : sh_sw(16); }
 int gs_sh_grad_width(int d) { return d == 27 ? (sh_nv(9) + 3) / 4 * 4 : (sh_nv(16) + 3) / 4 * 4; }
 
-cudaError_t gs_launch_blend_sh_fwd(const float4* pA, const float2* pB, const float* pS, int d, const int* tile_accum,
+cudaError_t gs_launch_blend_sh_fwd(const float4* pA, const float2* pB, const float* pS, const GsRec* grec,
+                                   const float* rgb, const uint32_t* ids, int d, const int* tile_accum,
                                    const GsFrameGeom& g, const GsRayPtrs& r, float* image, int* tile_neff,
                                    float* final_img, const GsCrop& crop, cudaStream_t st) {
-  if (d == 27)
-    blend_sh_fwd_kernel<9><<<g.n_tiles, 64, 0, st>>>(pA, pB, pS, tile_accum, g.wp, g.hp, g.ntx, g.fx, g.fy, r.rays_o,
-                                                     r.lefttop, r.dx, r.dy, image, tile_neff, final_img, crop);
-  else
-    blend_sh_fwd_kernel<16><<<g.n_tiles, 64, 0, st>>>(pA, pB, pS, tile_accum, g.wp, g.hp, g.ntx, g.fx, g.fy, r.rays_o,
-                                                      r.lefttop, r.dx, r.dy, image, tile_neff, final_img, crop);
+#define GS_SHF(K, GA)                                                                                               \
+  blend_sh_fwd_kernel<K, GA><<<g.n_tiles, 64, 0, st>>>(pA, pB, pS, grec, rgb, ids, tile_accum, g.wp, g.hp, g.ntx,   \
+                                                       g.fx, g.fy, r.rays_o, r.lefttop, r.dx, r.dy, image, tile_neff, \
+                                                       final_img, crop)
+  if (grec) {
+    if (d == 27) GS_SHF(9, true); else GS_SHF(16, true);
+  } else {
+    if (d == 27) GS_SHF(9, false); else GS_SHF(16, false);
+  }
+#undef GS_SHF
   return cudaGetLastError();
 }
 
-cudaError_t gs_launch_blend_sh_bwd(const float4* pA, const float2* pB, const float* pS, int d, const int* tile_accum,
+cudaError_t gs_launch_blend_sh_bwd(const float4* pA, const float2* pB, const float* pS, const GsRec* grec,
+                                   const float* rgb, const uint32_t* ids, int d, const int* tile_accum,
                                    const GsFrameGeom& g, const GsRayPtrs& r, const float* image,
                                    const float* grad_image, float* grad_inst, int grad_is_final, const GsCrop& crop,
                                    uint32_t* row_epoch, uint32_t epoch, int* tile_neff_b, cudaStream_t st) {
-  if (d == 27)
-    blend_sh_bwd_kernel<9><<<g.n_tiles, 64, 0, st>>>(pA, pB, pS, tile_accum, g.wp, g.hp, g.ntx, g.fx, g.fy, r.rays_o,
-                                                     r.lefttop, r.dx, r.dy, image, grad_image, grad_inst, grad_is_final, crop, row_epoch,
-                                                     epoch, tile_neff_b);
-  else
-    blend_sh_bwd_kernel<16><<<g.n_tiles, 64, 0, st>>>(pA, pB, pS, tile_accum, g.wp, g.hp, g.ntx, g.fx, g.fy, r.rays_o,
-                                                      r.lefttop, r.dx, r.dy, image, grad_image, grad_inst, grad_is_final, crop, row_epoch,
-                                                     epoch, tile_neff_b);
+  if (grec && !row_epoch) return cudaErrorInvalidValue;
+#define GS_SHB(K, GA)                                                                                               \
+  blend_sh_bwd_kernel<K, GA><<<g.n_tiles, 64, 0, st>>>(pA, pB, pS, grec, rgb, ids, tile_accum, g.wp, g.hp, g.ntx,   \
+                                                       g.fx, g.fy, r.rays_o, r.lefttop, r.dx, r.dy, image, grad_image, \
+                                                       grad_inst, grad_is_final, crop, row_epoch, epoch, tile_neff_b)
+  if (grec) {
+    if (d == 27) GS_SHB(9, true); else GS_SHB(16, true);
+  } else {
+    if (d == 27) GS_SHB(9, false); else GS_SHB(16, false);
+  }
+#undef GS_SHB
   return cudaGetLastError();
 }

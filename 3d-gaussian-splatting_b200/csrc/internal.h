@@ -51,10 +51,13 @@ void gs_count_launch(int n = 1);
 int gs_sh_basis_count(int d);      // 27 -> 9, 48 -> 16, else 0
 int gs_sh_stream_width(int d);     // floats per instance row of the SH stream (coefficients + slot, padded)
 int gs_sh_grad_width(int d);       // floats per instance gradient row (6 geometry + d coefficients, padded)
-cudaError_t gs_launch_blend_sh_fwd(const float4* pA, const float2* pB, const float* pS, int d, const int* tile_accum,
+// grec != nullptr: gather path (records from rec[N], raw coefficients from the parameter tensor rgb[N, d])
+cudaError_t gs_launch_blend_sh_fwd(const float4* pA, const float2* pB, const float* pS, const GsRec* grec,
+                                   const float* rgb, const uint32_t* ids, int d, const int* tile_accum,
                                    const GsFrameGeom& g, const GsRayPtrs& r, float* image, int* tile_neff,
                                    float* final_img, const GsCrop& crop, cudaStream_t st);
-cudaError_t gs_launch_blend_sh_bwd(const float4* pA, const float2* pB, const float* pS, int d, const int* tile_accum,
+cudaError_t gs_launch_blend_sh_bwd(const float4* pA, const float2* pB, const float* pS, const GsRec* grec,
+                                   const float* rgb, const uint32_t* ids, int d, const int* tile_accum,
                                    const GsFrameGeom& g, const GsRayPtrs& r, const float* image,
                                    const float* grad_image, float* grad_inst, int grad_is_final, const GsCrop& crop,
                                    uint32_t* row_epoch, uint32_t epoch, int* tile_neff_b, cudaStream_t st);

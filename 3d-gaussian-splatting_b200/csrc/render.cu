@@ -334,7 +334,7 @@ static int render_forward_impl(gs_ctx* c, const float* pos, const float* rgb, co
   long long m = (long long)*c->host_m;
   size_t M = (size_t)m;
 
-  const bool gather = d == 3 && gs_tuning().gather != 0;
+  const bool gather = gs_tuning().gather != 0;   // RGB and SH: no pack pass
   gs_mark(c, 2, st);
   // tile-id sort key width (GS_TILE_KEY_BYTES=4 forces the wide path, for tests)
   static const int forced_key = getenv("GS_TILE_KEY_BYTES") ? atoi(getenv("GS_TILE_KEY_BYTES")) : 0;
@@ -406,7 +406,8 @@ static int render_forward_impl(gs_ctx* c, const float* pos, const float* rgb, co
   } else {
     const float* rp = c->rays.as<float>();
     GsRayPtrs rays{rp, rp + 3, rp + 6, rp + 9};
-    GS_CUDA_TRY(gs_launch_blend_sh_fwd(c->pA.as<float4>(), c->pB.as<float2>(), c->pC.as<float>(), d,
+    GS_CUDA_TRY(gs_launch_blend_sh_fwd(c->pA.as<float4>(), c->pB.as<float2>(), c->pC.as<float>(),
+                                       gather ? c->rec.as<GsRec>() : nullptr, rgb, c->vals_out.as<uint32_t>(), d,
                                        c->tile_accum.as<int>(), g, rays, image, c->tile_neff.as<int>(), final_img,
                                        crop, st));
   }
@@ -484,7 +485,8 @@ static int render_backward_impl(gs_ctx* c, const float* pos, const float* rgb, c
     } else {
       const float* rp = c->rays.as<float>();
       GsRayPtrs rays{rp, rp + 3, rp + 6, rp + 9};
-      GS_CUDA_TRY(gs_launch_blend_sh_bwd(c->pA.as<float4>(), c->pB.as<float2>(), c->pC.as<float>(), d,
+      GS_CUDA_TRY(gs_launch_blend_sh_bwd(c->pA.as<float4>(), c->pB.as<float2>(), c->pC.as<float>(),
+                                         c->gather ? c->rec.as<GsRec>() : nullptr, rgb, c->vals_out.as<uint32_t>(), d,
                                          c->tile_accum.as<int>(), c->geom, rays, image, grad_image,
                                          c->grad_inst.as<float>(), grad_is_final, crop,
                                          c->row_epoch.as<uint32_t>(), c->epoch, c->tile_neff_b.as<int>(), st));

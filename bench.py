@@ -362,16 +362,20 @@ def run_ours(args, world, rank, local):
     # ---- e2e: host buffers in the timed region -------------------------------------------
     img_host = torch.empty(h, w, 3, dtype=torch.float32).pin_memory()
     copy_stream = torch.cuda.Stream(device=dev)
-    go_stage = torch.empty_like(sc.go_dev)
-    bwd_done = [None]
+    go_stages = [torch.empty_like(sc.go_dev) for _ in range(2)]   # double buffered: the H2D of step i+1 overlaps
+    bwd_done = [None, None]                                        # the backward of step i, which still reads buffer i
+    e2e_it = [0]
 
     def step_e2e():
         for p in params:
             p.grad = None
         main = torch.cuda.current_stream(dev)
+        slot = e2e_it[0] & 1
+        e2e_it[0] += 1
+        go_stage = go_stages[slot]
         with torch.cuda.stream(copy_stream):
-            if bwd_done[0] is not None:
-                copy_stream.wait_event(bwd_done[0])              # the previous backward has read go_stage
+            if bwd_done[slot] is not None:
+                copy_stream.wait_event(bwd_done[slot])           # the backward two steps ago has read this buffer
             go_stage.copy_(sc.go_host, non_blocking=True)        # H2D: this step's upstream gradient
             h2d_done = torch.cuda.Event()
             h2d_done.record(copy_stream)
@@ -389,8 +393,8 @@ def run_ours(args, world, rank, local):
             main.wait_event(h2d_done)
             img.backward(go_stage)
             bucket.allreduce()
-            bwd_done[0] = torch.cuda.Event()
-            bwd_done[0].record(main)
+            bwd_done[slot] = torch.cuda.Event()
+            bwd_done[slot].record(main)
         copy_stream.synchronize()
 
     ms_e2e = timed_loop(step_e2e, args.steps, max(3, args.warmup // 2), world, dev)
