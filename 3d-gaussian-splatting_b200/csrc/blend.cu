@@ -52,10 +52,10 @@ __device__ __forceinline__ void issue_chunk(SM& sm, int stage, const float4* __r
 // ---- two ways a tile's sorted range reaches shared memory -------------------------------------------
 // packed : three contiguous record streams written by the pack pass (and by the legacy draw API);
 //          one thread issues three 1-D bulk copies per chunk.
-// gather : NO pack pass - every thread of the CTA issues, for "its" instances of the next chunk, one 1-D bulk
-//          copy (UBLKCP, the TMA engine) of the Gaussian's record straight from GsRec rec[N] through the sorted id
-//          list, with its share of the bytes posted on the stage's mbarrier (arrive.expect_tx; barrier count =
-//          CTA threads).  The per-instance record in shared memory is {a, b, c, d} (gs_common.cuh GsRec).
+// gather : NO pack pass - every thread of the CTA issues, for "its" instances of the next chunk, the 16-byte
+//          cp.async pieces of the Gaussian's record straight from GsRec rec[N] through the sorted id list and
+//          arrives on the stage's mbarrier when they have landed (cp.async.mbarrier.arrive; barrier count = CTA
+//          threads).  The per-instance record in shared memory is {a, b, c, d} (gs_common.cuh GsRec).
 template <bool GATHER>
 struct StageView;
 template <>
@@ -96,16 +96,43 @@ struct GatherRing {
   uint64_t full[STAGES];
 };
 
-template <typename SM, int NT, int RECW>
-__device__ __forceinline__ void gather_issue(SM& sm, int stage, const GsRec* __restrict__ grec,
-                                             const uint32_t* __restrict__ ids, int base, int n, int tid) {
-  uint32_t bytes = 0;
-  for (int i = tid; i < n; i += NT) {
-    const uint32_t id = ids[base + i];
-    gs_bulk_g2s(&sm.rec[stage][i * RECW], grec + id, RECW * 16u, &sm.full[stage]);
-    bytes += RECW * 16u;
+// ids of "this thread's" instances of one chunk, loaded one chunk boundary ahead of their use so that the
+// dependent record copies never wait for the id load
+template <int NT, int CH>
+struct GatherIds {
+  uint32_t id[(CH + NT - 1) / NT];
+  __device__ __forceinline__ void load(const uint32_t* __restrict__ ids, int base, int n, int tid) {
+#pragma unroll
+    for (int u = 0; u < (CH + NT - 1) / NT; ++u) {
+      const int i = tid + u * NT;
+      id[u] = i < n ? __ldg(ids + base + i) : 0u;
+    }
   }
-  gs_mbar_expect_tx(&sm.full[stage], bytes);          // arrive + this thread's share of the bytes (may be 0)
+};
+
+// RECW = 3: {a, b, c} (forward); RECW = 4: {a, b, c, (first gradient row of the Gaussian, -, -, -)} (backward: the
+// 4th piece comes from offsets_g[id], a 4-byte cp.async - patching it into rec[] from another kernel cost more)
+template <typename SM, int NT, int CH, int RECW>
+__device__ __forceinline__ void gather_issue(SM& sm, int stage, const GsRec* __restrict__ grec,
+                                             const uint32_t* __restrict__ goff, const GatherIds<NT, CH>& g, int n,
+                                             int tid) {
+  // 16-byte cp.async (LDGSTS) pieces: one warp-wide instruction moves a piece of 32 instances.  (Measured: one
+  // 1-D bulk copy per instance, i.e. ~6 M tiny TMA requests per frame, made both blend kernels ~15 % slower.)
+#pragma unroll
+  for (int u = 0; u < (CH + NT - 1) / NT; ++u) {
+    const int i = tid + u * NT;
+    if (i < n) {
+      const float4* src = reinterpret_cast<const float4*>(grec + g.id[u]);
+      const uint32_t dst = gs_smem_u32(&sm.rec[stage][i * RECW]);
+#pragma unroll
+      for (int q = 0; q < 3; ++q)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * q), "l"(src + q) : "memory");
+      if (RECW == 4)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 48u), "l"(goff + g.id[u]) : "memory");
+    }
+  }
+  // this thread's arrival on the stage barrier (count = CTA threads) fires when its copies have landed
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(gs_smem_u32(&sm.full[stage])) : "memory");
 }
 
 // Per (thread, instance): 3 broadcast LDS + 4 row-shared FP32 ops (dy, cb*dy, cc*dy, l2o-cc*dy^2)
@@ -146,9 +173,13 @@ __global__ void __launch_bounds__(256 / PX) blend_fwd_kernel(const float4* __res
     gs_fence_barrier_init();
   }
   __syncthreads();
+  GatherIds<NTHREADS, FWD_CH> gid;
   if constexpr (GATHER) {
-    for (int k = 0; k < FWD_STAGES && k < nchunks; ++k)
-      gather_issue<Smem, NTHREADS, 3>(sm, k, grec, ids, start + k * FWD_CH, min(FWD_CH, cnt - k * FWD_CH), tid);
+    for (int k = 0; k < FWD_STAGES && k < nchunks; ++k) {
+      gid.load(ids, start + k * FWD_CH, min(FWD_CH, cnt - k * FWD_CH), tid);
+      gather_issue<Smem, NTHREADS, FWD_CH, 3>(sm, k, grec, nullptr, gid, min(FWD_CH, cnt - k * FWD_CH), tid);
+    }
+    if (FWD_STAGES < nchunks) gid.load(ids, start + FWD_STAGES * FWD_CH, min(FWD_CH, cnt - FWD_STAGES * FWD_CH), tid);
   } else if (tid == 0) {
     for (int k = 0; k < FWD_STAGES && k < nchunks; ++k)
       issue_chunk<Smem, FWD_CH>(sm, k, pA, pB, pC, start + k * FWD_CH, min(FWD_CH, cnt - k * FWD_CH), shift);
@@ -223,9 +254,10 @@ __global__ void __launch_bounds__(256 / PX) blend_fwd_kernel(const float4* __res
     }
     if (k + FWD_STAGES < nchunks) {
       const int kn = k + FWD_STAGES;            // every thread is past the barrier above: the stage is free
-      if constexpr (GATHER)
-        gather_issue<Smem, NTHREADS, 3>(sm, stage, grec, ids, start + kn * FWD_CH, min(FWD_CH, cnt - kn * FWD_CH), tid);
-      else if (tid == 0)
+      if constexpr (GATHER) {
+        gather_issue<Smem, NTHREADS, FWD_CH, 3>(sm, stage, grec, nullptr, gid, min(FWD_CH, cnt - kn * FWD_CH), tid);
+        if (kn + 1 < nchunks) gid.load(ids, start + (kn + 1) * FWD_CH, min(FWD_CH, cnt - (kn + 1) * FWD_CH), tid);
+      } else if (tid == 0)
         issue_chunk<Smem, FWD_CH>(sm, stage, pA, pB, pC, start + kn * FWD_CH, min(FWD_CH, cnt - kn * FWD_CH), shift);
     }
   }
@@ -726,7 +758,7 @@ template <int PX, bool WS, int UNR, int STAGES, int MINB, int RQ, bool GATHER>
 __global__ void __launch_bounds__(256 / PX + (WS ? 32 : 0), MINB)
     blend_bwd2_kernel(const float4* __restrict__ pA, const float2* __restrict__ pB, const float4* __restrict__ pC,
                       const GsRec* __restrict__ grec, const uint32_t* __restrict__ ids,
-                      const int* __restrict__ tile_accum, int wp, int hp, int ntx, float fx, float fy,
+                      const uint32_t* __restrict__ goff, const int* __restrict__ tile_accum, int wp, int hp, int ntx, float fx, float fy,
                       const float* __restrict__ image, const float* __restrict__ grad_image,
                       float* __restrict__ grad_inst, int grad_is_final, GsCrop crop, uint32_t* __restrict__ row_epoch,
                       uint32_t epoch, int* __restrict__ tile_neff_b) {
@@ -751,8 +783,6 @@ __global__ void __launch_bounds__(256 / PX + (WS ? 32 : 0), MINB)
       gs_fence_barrier_init();
     }
     __syncthreads();
-    for (int k = 0; k < STAGES && k < nchunks; ++k)
-      gather_issue<Smem, NT, 4>(sm, k, grec, ids, start + k * WS_CH, min(WS_CH, cnt - k * WS_CH), tid);
   } else {
     ws_init<Smem, STAGES>(sm, tid);
     if (WS) {
@@ -764,6 +794,14 @@ __global__ void __launch_bounds__(256 / PX + (WS ? 32 : 0), MINB)
       for (int k = 0; k < STAGES && k < nchunks; ++k)
         issue_chunk<Smem, WS_CH>(sm, k, pA, pB, pC, start + k * WS_CH, min(WS_CH, cnt - k * WS_CH), shift);
     }
+  }
+  GatherIds<NT, WS_CH> gid;
+  if constexpr (GATHER) {
+    for (int k = 0; k < STAGES && k < nchunks; ++k) {
+      gid.load(ids, start + k * WS_CH, min(WS_CH, cnt - k * WS_CH), tid);
+      gather_issue<Smem, NT, WS_CH, 4>(sm, k, grec, goff, gid, min(WS_CH, cnt - k * WS_CH), tid);
+    }
+    if (STAGES < nchunks) gid.load(ids, start + STAGES * WS_CH, min(WS_CH, cnt - STAGES * WS_CH), tid);
   }
   const int ix0 = tx * GS_TILE + (tid % TPR) * PX;
   const int iy = ty * GS_TILE + (tid / TPR);
@@ -930,7 +968,8 @@ __global__ void __launch_bounds__(256 / PX + (WS ? 32 : 0), MINB)
     if constexpr (GATHER) {
       if (!finished && k + STAGES < nchunks) {   // every consumer is past the barrier: the stage is free
         const int kn = k + STAGES;
-        gather_issue<Smem, NT, 4>(sm, stage, grec, ids, start + kn * WS_CH, min(WS_CH, cnt - kn * WS_CH), tid);
+        gather_issue<Smem, NT, WS_CH, 4>(sm, stage, grec, goff, gid, min(WS_CH, cnt - kn * WS_CH), tid);
+        if (kn + 1 < nchunks) gid.load(ids, start + (kn + 1) * WS_CH, min(WS_CH, cnt - (kn + 1) * WS_CH), tid);
       }
     } else if (tid == 0) {
       if (WS) {
@@ -1112,7 +1151,8 @@ cudaError_t gs_launch_blend_fwd(const float4* pA, const float2* pB, const float4
 }
 
 cudaError_t gs_launch_blend_bwd(const float4* pA, const float2* pB, const float4* pC, const GsRec* grec,
-                                const uint32_t* ids, const int* tile_accum, const GsFrameGeom& g, const float* image,
+                                const uint32_t* ids, const uint32_t* goff, const int* tile_accum, const GsFrameGeom& g,
+                                const float* image,
                                 const float* grad_image, float* grad_inst, int grad_is_final, const GsCrop& crop,
                                 uint32_t* row_epoch, uint32_t epoch, int* tile_neff_b, cudaStream_t st) {
   const GsTuning& tn = gs_tuning();
@@ -1121,7 +1161,8 @@ cudaError_t gs_launch_blend_bwd(const float4* pA, const float2* pB, const float4
   if (tn.bwd_kernel != 0 || gather) {
 #define GS_BWD2(PX, WS, UNR, ST, MINB, RQ, GA)                                                                      \
   blend_bwd2_kernel<PX, WS, UNR, ST, MINB, RQ, GA><<<g.n_tiles, 256 / PX + (WS ? 32 : 0), 0, st>>>(                  \
-      pA, pB, pC, grec, ids, tile_accum, g.wp, g.hp, g.ntx, g.fx, g.fy, image, grad_image, grad_inst, grad_is_final, \
+      pA, pB, pC, grec, ids, goff, tile_accum, g.wp, g.hp, g.ntx, g.fx, g.fy, image, grad_image, grad_inst,          \
+      grad_is_final,                                                                                                 \
       crop, row_epoch, epoch, tile_neff_b)
     // key: px | producer warp | unroll | stages | reducers per instance | min blocks (2 digits)
     const int key = ((((tn.bwd_px * 10 + tn.bwd_ws) * 10 + tn.bwd_unroll) * 10 + tn.bwd_stages) * 10 + tn.bwd_rq) * 100 +
@@ -1230,7 +1271,7 @@ extern "C" int gs_draw_fwd(const float* pos, const float* rgb, const float* opa,
                                     GsCrop{}, st));
   } else {
     GsRayPtrs r{rays_o, lefttop, vec_dx, vec_dy};
-    GS_CUDA_TRY(gs_launch_blend_sh_fwd(ws.pA, ws.pB, reinterpret_cast<float*>(ws.pC), nullptr, nullptr, nullptr, d,
+    GS_CUDA_TRY(gs_launch_blend_sh_fwd(ws.pA, ws.pB, reinterpret_cast<float*>(ws.pC), nullptr, nullptr, nullptr, nullptr, d,
                                        tile_n_point_accum, g, r,
                                        image, nullptr, nullptr, GsCrop{}, st));
   }
@@ -1269,14 +1310,15 @@ extern "C" int gs_draw_bwd(const float* pos, const float* rgb, const float* opa,
   g.fx = focal_x;
   g.fy = focal_y;
   if (d == 3) {
-    GS_CUDA_TRY(gs_launch_blend_bwd(ws.pA, ws.pB, ws.pC, nullptr, nullptr, tile_n_point_accum, g, image, grad_image,
+    GS_CUDA_TRY(gs_launch_blend_bwd(ws.pA, ws.pB, ws.pC, nullptr, nullptr, nullptr, tile_n_point_accum, g, image,
+                                    grad_image,
                                     ws.grad_inst, 0,
                                     GsCrop{}, nullptr, 0u, nullptr, st));
     legacy_unpack_grads_kernel<<<(m + 255) / 256, 256, 0, st>>>(ws.grad_inst, opa, cov, m, grad_pos, grad_rgb,
                                                               grad_opa, grad_cov);
   } else {
     GsRayPtrs r{rays_o, lefttop, vec_dx, vec_dy};
-    GS_CUDA_TRY(gs_launch_blend_sh_bwd(ws.pA, ws.pB, reinterpret_cast<float*>(ws.pC), nullptr, nullptr, nullptr, d,
+    GS_CUDA_TRY(gs_launch_blend_sh_bwd(ws.pA, ws.pB, reinterpret_cast<float*>(ws.pC), nullptr, nullptr, nullptr, nullptr, d,
                                        tile_n_point_accum, g, r,
                                        image, grad_image, ws.grad_inst, 0, GsCrop{}, nullptr, 0u, nullptr, st));
     legacy_unpack_grads_sh_kernel<<<(m + 255) / 256, 256, 0, st>>>(ws.grad_inst, gs_sh_grad_width(d), opa, cov, m, d,

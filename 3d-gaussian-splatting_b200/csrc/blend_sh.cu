@@ -85,11 +85,10 @@ __device__ __forceinline__ void issue_sh(SM& sm, int stage, const float4* __rest
 }
 
 // Gather staging (no pack pass): per instance the Gaussian's 64-byte record (centre, conic, log2 opacity, tile
-// rectangle, first gradient row) comes straight from GsRec rec[N] with ONE 1-D bulk copy (TMA engine), and its 3K
-// raw coefficients straight from the parameter tensor rgb[N, 3K]: one more bulk copy when the row is 16-byte
-// aligned (K = 16: 192 B), else 3K 4-byte cp.async (K = 9: rows of 108 B are only 4-byte aligned).  Every thread
-// of the CTA issues the copies of "its" instances of the chunk and arrives on the stage's mbarrier (count = CTA
-// threads): bulk bytes via expect_tx, cp.async completion via cp.async.mbarrier.arrive.noinc.
+// rectangle, first gradient row) comes straight from GsRec rec[N] and its 3K raw coefficients straight from the
+// parameter tensor rgb[N, 3K], as cp.async pieces (16 B; 4 B for the 108-byte rows of K = 9, which are only
+// 4-byte aligned).  Every thread of the CTA issues the copies of "its" instances of the chunk and arrives on the
+// stage's mbarrier (count = CTA threads) when they have landed (cp.async.mbarrier.arrive.noinc).
 template <int K, int CH, int STAGES>
 struct ShGatherStage {
   float4 R[STAGES][CH * 4];
@@ -100,31 +99,30 @@ struct ShGatherStage {
 template <int K, int NT, typename SM>
 __device__ __forceinline__ void issue_sh_gather(SM& sm, int stage, const GsRec* __restrict__ grec,
                                                 const float* __restrict__ rgb, const uint32_t* __restrict__ ids,
-                                                int base, int n, int tid) {
+                                                const uint32_t* __restrict__ goff, int base, int n, int tid) {
   constexpr int SW = sh_sw(K), D = 3 * K;
-  const uint32_t bar = gs_smem_u32(&sm.full[stage]);
-  uint32_t bytes = 0;
   for (int i = tid; i < n; i += NT) {
     const uint32_t id = ids[base + i];
-    gs_bulk_g2s(&sm.R[stage][i * 4], grec + id, 64u, &sm.full[stage]);
-    bytes += 64u;
+    const float4* src4 = reinterpret_cast<const float4*>(grec + id);
+    const uint32_t dr = gs_smem_u32(&sm.R[stage][i * 4]);
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dr + 16u * q), "l"(src4 + q) : "memory");
+    // first gradient row of the Gaussian (offsets_g[id]) into the record's 4th piece
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dr + 48u), "l"(goff + id) : "memory");
     const float* src = rgb + (size_t)id * D;
-    float* dst = &sm.S[stage][i * SW];
-    if ((D * 4) % 16 == 0) {
-      gs_bulk_g2s(dst, src, (uint32_t)(D * 4), &sm.full[stage]);
-      bytes += (uint32_t)(D * 4);
-    } else {
+    const uint32_t ds = gs_smem_u32(&sm.S[stage][i * SW]);
+    if ((D * 4) % 16 == 0) {        // K = 16: rows of 192 B are 16-byte aligned
+#pragma unroll
+      for (int q = 0; q < D / 4; ++q)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ds + 16u * q), "l"(src + 4 * q) : "memory");
+    } else {                        // K = 9: rows of 108 B are only 4-byte aligned
 #pragma unroll
       for (int q = 0; q < D; ++q)
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(gs_smem_u32(dst + q)), "l"(src + q) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(ds + 4u * q), "l"(src + q) : "memory");
     }
   }
-  if ((D * 4) % 16 == 0) {
-    gs_mbar_expect_tx(&sm.full[stage], bytes);                      // arrive + bytes
-  } else {
-    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");   // the arrival
-  }
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(gs_smem_u32(&sm.full[stage])) : "memory");
 }
 
 // view of one stage: packed streams (pack pass / legacy draw API) or gathered records
@@ -167,6 +165,7 @@ __global__ void __launch_bounds__(64) blend_sh_fwd_kernel(const float4* __restri
                                                            const float* __restrict__ pS,
                                                            const GsRec* __restrict__ grec, const float* __restrict__ rgb,
                                                            const uint32_t* __restrict__ ids,
+                                                           const uint32_t* __restrict__ goff,
                                                            const int* __restrict__ tile_accum, int wp, int hp, int ntx,
                                                            float fx, float fy, const float* __restrict__ rays_o,
                                                            const float* __restrict__ lefttop,
@@ -199,7 +198,7 @@ __global__ void __launch_bounds__(64) blend_sh_fwd_kernel(const float4* __restri
   __syncthreads();
   if constexpr (GATHER) {
     for (int k = 0; k < STAGES && k < nchunks; ++k)
-      issue_sh_gather<K, NT>(sm, k, grec, rgb, ids, start + k * CH, min(CH, cnt - k * CH), tid);
+      issue_sh_gather<K, NT>(sm, k, grec, rgb, ids, goff, start + k * CH, min(CH, cnt - k * CH), tid);
   } else if (tid == 0) {
     for (int k = 0; k < STAGES && k < nchunks; ++k)
       issue_sh<K>(sm, k, pA, pB, pS, start + k * CH, min(CH, cnt - k * CH), shift);
@@ -276,7 +275,7 @@ __global__ void __launch_bounds__(64) blend_sh_fwd_kernel(const float4* __restri
     if (k + STAGES < nchunks) {
       const int kn = k + STAGES;
       if constexpr (GATHER)
-        issue_sh_gather<K, NT>(sm, stage, grec, rgb, ids, start + kn * CH, min(CH, cnt - kn * CH), tid);
+        issue_sh_gather<K, NT>(sm, stage, grec, rgb, ids, goff, start + kn * CH, min(CH, cnt - kn * CH), tid);
       else if (tid == 0)
         issue_sh<K>(sm, stage, pA, pB, pS, start + kn * CH, min(CH, cnt - kn * CH), shift);
     }
@@ -343,6 +342,7 @@ __global__ void __launch_bounds__(64) blend_sh_bwd_kernel(const float4* __restri
                                                            const float* __restrict__ pS,
                                                            const GsRec* __restrict__ grec, const float* __restrict__ rgb,
                                                            const uint32_t* __restrict__ ids,
+                                                           const uint32_t* __restrict__ goff,
                                                            const int* __restrict__ tile_accum, int wp, int hp, int ntx,
                                                            float fx, float fy, const float* __restrict__ rays_o,
                                                            const float* __restrict__ lefttop,
@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(64) blend_sh_bwd_kernel(const float4* __restri
   __syncthreads();
   if constexpr (GATHER) {
     for (int k = 0; k < STAGES && k < nchunks; ++k)
-      issue_sh_gather<K, THREADS>(sm, k, grec, rgb, ids, start + k * CH, min(CH, cnt - k * CH), tid);
+      issue_sh_gather<K, THREADS>(sm, k, grec, rgb, ids, goff, start + k * CH, min(CH, cnt - k * CH), tid);
   } else if (tid == 0) {
     for (int k = 0; k < STAGES && k < nchunks; ++k)
       issue_sh<K>(sm, k, pA, pB, pS, start + k * CH, min(CH, cnt - k * CH), shift);
@@ -530,7 +530,7 @@ __global__ void __launch_bounds__(64) blend_sh_bwd_kernel(const float4* __restri
     if (k + STAGES < nchunks) {
       const int kn = k + STAGES;
       if constexpr (GATHER)
-        issue_sh_gather<K, THREADS>(sm, stage, grec, rgb, ids, start + kn * CH, min(CH, cnt - kn * CH), tid);
+        issue_sh_gather<K, THREADS>(sm, stage, grec, rgb, ids, goff, start + kn * CH, min(CH, cnt - kn * CH), tid);
       else if (tid == 0)
         issue_sh<K>(sm, stage, pA, pB, pS, start + kn * CH, min(CH, cnt - kn * CH), shift);
     }
@@ -554,11 +554,12 @@ int gs_sh_stream_width(int d) { return d == 27 ? sh_sw(9) : sh_sw(16); }
 int gs_sh_grad_width(int d) { return d == 27 ? (sh_nv(9) + 3) / 4 * 4 : (sh_nv(16) + 3) / 4 * 4; }
 
 cudaError_t gs_launch_blend_sh_fwd(const float4* pA, const float2* pB, const float* pS, const GsRec* grec,
-                                   const float* rgb, const uint32_t* ids, int d, const int* tile_accum,
+                                   const float* rgb, const uint32_t* ids, const uint32_t* goff, int d,
+                                   const int* tile_accum,
                                    const GsFrameGeom& g, const GsRayPtrs& r, float* image, int* tile_neff,
                                    float* final_img, const GsCrop& crop, cudaStream_t st) {
 #define GS_SHF(K, GA)                                                                                               \
-  blend_sh_fwd_kernel<K, GA><<<g.n_tiles, 64, 0, st>>>(pA, pB, pS, grec, rgb, ids, tile_accum, g.wp, g.hp, g.ntx,   \
+  blend_sh_fwd_kernel<K, GA><<<g.n_tiles, 64, 0, st>>>(pA, pB, pS, grec, rgb, ids, goff, tile_accum, g.wp, g.hp, g.ntx,   \
                                                        g.fx, g.fy, r.rays_o, r.lefttop, r.dx, r.dy, image, tile_neff, \
                                                        final_img, crop)
   if (grec) {
@@ -571,13 +572,14 @@ cudaError_t gs_launch_blend_sh_fwd(const float4* pA, const float2* pB, const flo
 }
 
 cudaError_t gs_launch_blend_sh_bwd(const float4* pA, const float2* pB, const float* pS, const GsRec* grec,
-                                   const float* rgb, const uint32_t* ids, int d, const int* tile_accum,
+                                   const float* rgb, const uint32_t* ids, const uint32_t* goff, int d,
+                                   const int* tile_accum,
                                    const GsFrameGeom& g, const GsRayPtrs& r, const float* image,
                                    const float* grad_image, float* grad_inst, int grad_is_final, const GsCrop& crop,
                                    uint32_t* row_epoch, uint32_t epoch, int* tile_neff_b, cudaStream_t st) {
   if (grec && !row_epoch) return cudaErrorInvalidValue;
 #define GS_SHB(K, GA)                                                                                               \
-  blend_sh_bwd_kernel<K, GA><<<g.n_tiles, 64, 0, st>>>(pA, pB, pS, grec, rgb, ids, tile_accum, g.wp, g.hp, g.ntx,   \
+  blend_sh_bwd_kernel<K, GA><<<g.n_tiles, 64, 0, st>>>(pA, pB, pS, grec, rgb, ids, goff, tile_accum, g.wp, g.hp, g.ntx,   \
                                                        g.fx, g.fy, r.rays_o, r.lefttop, r.dx, r.dy, image, grad_image, \
                                                        grad_inst, grad_is_final, crop, row_epoch, epoch, tile_neff_b)
   if (grec) {

@@ -53,11 +53,13 @@ int gs_sh_stream_width(int d);     // floats per instance row of the SH stream (
 int gs_sh_grad_width(int d);       // floats per instance gradient row (6 geometry + d coefficients, padded)
 // grec != nullptr: gather path (records from rec[N], raw coefficients from the parameter tensor rgb[N, d])
 cudaError_t gs_launch_blend_sh_fwd(const float4* pA, const float2* pB, const float* pS, const GsRec* grec,
-                                   const float* rgb, const uint32_t* ids, int d, const int* tile_accum,
+                                   const float* rgb, const uint32_t* ids, const uint32_t* goff /*offsets_g*/, int d,
+                                   const int* tile_accum,
                                    const GsFrameGeom& g, const GsRayPtrs& r, float* image, int* tile_neff,
                                    float* final_img, const GsCrop& crop, cudaStream_t st);
 cudaError_t gs_launch_blend_sh_bwd(const float4* pA, const float2* pB, const float* pS, const GsRec* grec,
-                                   const float* rgb, const uint32_t* ids, int d, const int* tile_accum,
+                                   const float* rgb, const uint32_t* ids, const uint32_t* goff /*offsets_g*/, int d,
+                                   const int* tile_accum,
                                    const GsFrameGeom& g, const GsRayPtrs& r, const float* image,
                                    const float* grad_image, float* grad_inst, int grad_is_final, const GsCrop& crop,
                                    uint32_t* row_epoch, uint32_t epoch, int* tile_neff_b, cudaStream_t st);
@@ -109,7 +111,8 @@ cudaError_t gs_launch_blend_fwd(const float4* pA, const float2* pB, const float4
                                 int* tile_neff, float* final_img, const GsCrop& crop, cudaStream_t st);
 
 cudaError_t gs_launch_blend_bwd(const float4* pA, const float2* pB, const float4* pC, const GsRec* grec,
-                                const uint32_t* ids, const int* tile_accum, const GsFrameGeom& g, const float* image,
+                                const uint32_t* ids, const uint32_t* goff /*offsets_g (gather path)*/,
+                                const int* tile_accum, const GsFrameGeom& g, const float* image,
                                 const float* grad_image, float* grad_inst /*[M,GS_GREC] rows addressed by slot*/,
                                 int grad_is_final, const GsCrop& crop, uint32_t* row_epoch /*nullable (packed only)*/,
                                 uint32_t epoch, int* tile_neff_b /*nullable: instances the backward consumed per tile*/,

@@ -352,7 +352,7 @@ static int render_forward_impl(gs_ctx* c, const float* pos, const float* rgb, co
     GS_CUDA_TRY(c->vals_out.reserve(M * 4, st));
     // 3. instances in (depth, id) order: tile-id keys + Gaussian-id values
     GS_CUDA_TRY(gs_launch_emit_keys(c->rec.as<GsRec>(), c->perm.as<uint32_t>(), c->offsets.as<uint32_t>(),
-                                    gather ? c->offsets_g.as<uint32_t>() : nullptr, n, g.ntx, c->keys_in.p, key_bytes,
+                                    nullptr, n, g.ntx, c->keys_in.p, key_bytes,
                                     c->vals_in.as<uint32_t>(), st));
     gs_count_launch();
     // 4. stable radix sort on the tile id only -> (tile, depth, id)
@@ -407,7 +407,8 @@ static int render_forward_impl(gs_ctx* c, const float* pos, const float* rgb, co
     const float* rp = c->rays.as<float>();
     GsRayPtrs rays{rp, rp + 3, rp + 6, rp + 9};
     GS_CUDA_TRY(gs_launch_blend_sh_fwd(c->pA.as<float4>(), c->pB.as<float2>(), c->pC.as<float>(),
-                                       gather ? c->rec.as<GsRec>() : nullptr, rgb, c->vals_out.as<uint32_t>(), d,
+                                       gather ? c->rec.as<GsRec>() : nullptr, rgb, c->vals_out.as<uint32_t>(),
+                                       c->offsets_g.as<uint32_t>(), d,
                                        c->tile_accum.as<int>(), g, rays, image, c->tile_neff.as<int>(), final_img,
                                        crop, st));
   }
@@ -479,14 +480,16 @@ static int render_backward_impl(gs_ctx* c, const float* pos, const float* rgb, c
     if (d == 3) {
       GS_CUDA_TRY(gs_launch_blend_bwd(c->pA.as<float4>(), c->pB.as<float2>(), c->pC.as<float4>(),
                                       c->gather ? c->rec.as<GsRec>() : nullptr, c->vals_out.as<uint32_t>(),
-                                      c->tile_accum.as<int>(), c->geom, image, grad_image, c->grad_inst.as<float>(),
+                                      c->offsets_g.as<uint32_t>(), c->tile_accum.as<int>(), c->geom, image, grad_image,
+                                      c->grad_inst.as<float>(),
                                       grad_is_final, crop, c->row_epoch.as<uint32_t>(), c->epoch,
                                       c->tile_neff_b.as<int>(), st));
     } else {
       const float* rp = c->rays.as<float>();
       GsRayPtrs rays{rp, rp + 3, rp + 6, rp + 9};
       GS_CUDA_TRY(gs_launch_blend_sh_bwd(c->pA.as<float4>(), c->pB.as<float2>(), c->pC.as<float>(),
-                                         c->gather ? c->rec.as<GsRec>() : nullptr, rgb, c->vals_out.as<uint32_t>(), d,
+                                         c->gather ? c->rec.as<GsRec>() : nullptr, rgb, c->vals_out.as<uint32_t>(),
+                                         c->offsets_g.as<uint32_t>(), d,
                                          c->tile_accum.as<int>(), c->geom, rays, image, grad_image,
                                          c->grad_inst.as<float>(), grad_is_final, crop,
                                          c->row_epoch.as<uint32_t>(), c->epoch, c->tile_neff_b.as<int>(), st));

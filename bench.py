@@ -440,7 +440,7 @@ def run_ours(args, world, rank, local):
             "pairs_per_clk_per_sm": pairs / (k_ms * 1e-3 * sm_hz * n_sm) if k_ms and k_ms > 0 else None,
             "issue_frac": ncu.get("issue_active_frac"), "mufu_frac": ncu.get("xu_pipe_frac"),
             "fma_pipe_frac": ncu.get("fma_pipe_frac"), "warp_inst_per_launch": ncu.get("warp_inst"),
-            "thread_inst_per_pair": (ncu["warp_inst"] * 32.0 / ncu["pairs"]) if ncu.get("warp_inst") and ncu.get("pairs") else None,
+            "thread_inst_per_pair": (ncu["warp_inst"] * 32.0 / pairs) if ncu.get("warp_inst") and pairs else None,
             "ncu_source": ncu.get("source"),
             "note": "blend is instruction-issue / MUFU bound, not HBM bound (SURVEY.md §8d): the HBM fraction is reported "
                     "because the metric asks for it; issue_frac / mufu_frac come from the committed ncu capture of this "

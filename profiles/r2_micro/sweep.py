@@ -27,17 +27,12 @@ BASE = dict(fwd_kernel=0, fwd_ch=256, fwd_px=4, bwd_kernel=1, bwd_px=8, bwd_ws=0
 VARIANTS = [
     ("r1 kernels (packed, thread-0 issue, shuffle reduction)", dict(bwd_kernel=0, bwd_px=4)),
     ("packed: bwd2 px8 t0 rq4 st2 unroll2 minb16", dict()),
-    ("packed: bwd2 px8 unroll2 minb10", dict(bwd_minb=10)),
     ("packed: bwd2 px8 unroll4 minb10", dict(bwd_unroll=4, bwd_minb=10)),
-    ("packed: bwd2 px4 unroll4", dict(bwd_px=4, bwd_unroll=4, bwd_minb=1)),
-    ("gather: fwd ch256 + bwd2 px8 unroll2 minb16", dict(gather=1)),
+    ("gather(cp.async): fwd ch256 + bwd2 px8 unroll2 minb16", dict(gather=1)),
     ("gather: fwd ch128", dict(gather=1, fwd_ch=128)),
     ("gather: fwd ch64", dict(gather=1, fwd_ch=64)),
-    ("gather: fwd px8 ch128", dict(gather=1, fwd_ch=128, fwd_px=8)),
-    ("gather: bwd2 px8 unroll2 minb10", dict(gather=1, bwd_minb=10)),
     ("gather: bwd2 px8 unroll4 minb10", dict(gather=1, bwd_unroll=4, bwd_minb=10)),
     ("gather: bwd2 px8 unroll2 st3 minb16", dict(gather=1, bwd_stages=3)),
-    ("gather: bwd2 px8 unroll1 minb16", dict(gather=1, bwd_unroll=1)),
     ("gather: bwd2 px4 unroll4", dict(gather=1, bwd_px=4, bwd_unroll=4, bwd_minb=1)),
 ]
 

@@ -56,6 +56,44 @@ def full_report(path):
     return "\n".join(out)
 
 
+def ncu_metrics(path, key):
+    """{kernel family: counters per launch} from an `ncu --set full` report, for bench.py's roofline block
+    (profiles/<tag>_ncu_metrics.json, keyed by "<workload>/D<colour>")."""
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+
+    def val(r, name, scale_units=True):
+        if name not in idx or r[idx[name]] in ("", "n/a"):
+            return None
+        v = float(r[idx[name]].replace(",", ""))
+        u = units[idx[name]]
+        if scale_units:
+            v *= {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0, "ms": 1.0, "us": 1e-3, "ns": 1e-6}.get(u, 1.0)
+        return v
+
+    out = {}
+    for r in rows[2:]:
+        name = r[idx["Kernel Name"]]
+        fam = next((f for f in ("blend_sh_fwd", "blend_sh_bwd", "blend_fwd", "blend_bwd", "fused_project_bwd", "fused_project",
+                                "emit_keys", "tile_ranges", "pack_sorted") if f in name), None)
+        if fam is None or fam in out:
+            continue
+        fam = {"blend_sh_fwd": "blend_fwd", "blend_sh_bwd": "blend_bwd"}.get(fam, fam)
+        rd, wr = val(r, "dram__bytes_read.sum"), val(r, "dram__bytes_write.sum")
+        out[fam] = {
+            "kernel": name.split("(")[0][-80:], "ms": val(r, "gpu__time_duration.sum"),
+            "dram_bytes": (rd or 0) + (wr or 0), "warp_inst": val(r, "smsp__inst_executed.sum", False),
+            "issue_active_frac": (val(r, "smsp__issue_active.avg.pct_of_peak_sustained_active", False) or 0) / 100.0,
+            "xu_pipe_frac": (val(r, "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", False) or 0) / 100.0,
+            "fma_pipe_frac": (val(r, "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", False) or 0) / 100.0,
+            "dram_throughput_frac": (val(r, "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", False) or 0) / 100.0,
+            "registers": val(r, "launch__registers_per_thread", False),
+            "source": f"profiles/{os.path.basename(path)} ({key}; ncu --set full --clock-control none)"}
+    return out
+
+
 def main(src, tag):
     here = os.path.dirname(os.path.abspath(__file__))
     md = [f"# profiles — round {tag}", "",
@@ -94,6 +132,18 @@ def main(src, tag):
     if os.path.exists(rep):
         md += ["## ncu --set full, blend kernels (report kept out of git: 8 MB; regenerate with the command in "
                "gpurun_out/run_r1_profile.sh)", full_report(rep), ""]
+    metrics = {}
+    for name in sorted(os.listdir(src)):
+        if name.startswith("prof_") and name.endswith(".ncu-rep"):
+            # prof_<workload>_D<colour>[_anything].ncu-rep
+            parts = name[:-8].split("_")
+            key = f"{parts[1]}/{parts[2]}" if len(parts) >= 3 else "C3/D3"
+            rep = os.path.join(src, name)
+            md += [f"## ncu --set full: {name} ({key})", full_report(rep), ""]
+            m = ncu_metrics(rep, key)
+            metrics.setdefault(key, {}).update(m)
+    if metrics:
+        json.dump(metrics, open(os.path.join(here, f"{tag}_ncu_metrics.json"), "w"), indent=1)
     open(os.path.join(here, f"{tag}_summary.md"), "w").write("\n".join(md) + "\n")
     print("\n".join(md))
 
