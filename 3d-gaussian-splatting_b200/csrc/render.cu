@@ -46,7 +46,7 @@ static int tune_env(const char* name, int dflt) {
 }
 GsTuning& gs_tuning() {
   // shipped configuration = the best of the sweeps in profiles/r2_sweeps.md
-  static GsTuning t = {tune_env("GS_TUNE_FWD_KERNEL", 0),  tune_env("GS_TUNE_FWD_CH", 256),   tune_env("GS_TUNE_BWD_KERNEL", 1),
+  static GsTuning t = {tune_env("GS_TUNE_FWD_KERNEL", 0),  tune_env("GS_TUNE_FWD_CH", 128),   tune_env("GS_TUNE_BWD_KERNEL", 1),
                        tune_env("GS_TUNE_BWD_PX", 8),      tune_env("GS_TUNE_BWD_WS", 0),     tune_env("GS_TUNE_BWD_UNROLL", 2),
                        tune_env("GS_TUNE_BWD_STAGES", 2),  tune_env("GS_TUNE_BWD_MINB", 16),  tune_env("GS_TUNE_BWD_RQ", 4),
                        tune_env("GS_TUNE_FWD_PX", 4),      tune_env("GS_TUNE_GATHER", 1)};
