@@ -1,15 +1,19 @@
 #!/usr/bin/env python
 """Benchmark of the hot path: render + backward FPS at 1080p, 2.4M Gaussians.
 
-  python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload C2|C3|C5]
+  python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload C2|C3|C5] [--colour 3|27|48]
 
 One "step" = one forward + backward of one 1920x1080 view per GPU: raw parameters ->
 image -> gradients of all five parameter tensors for a fixed upstream image gradient
-(SURVEY.md §8d FPS_fb; no loss / optimizer inside), followed at N > 1 by the NCCL
-all-reduce of the gradient bucket (views are sharded one per GPU, Gaussians replicated:
-weak scaling).  `value` = N views / max-over-ranks step time, inputs resident in HBM.
+(SURVEY.md §8d FPS_fb; no loss / optimizer inside), followed at N > 1 by the exchange of the
+gradient bucket (views are sharded one per GPU, Gaussians replicated: weak scaling): our own
+kernels over NVLink peer memory (push fused into the projection backward) at N = 2, 4, 8, else one
+NCCL all-reduce.  `value` = N views / max-over-ranks step time, inputs resident in HBM.
 `e2e`   = the same through the public `Splatter` API with the upstream gradient coming
 from pinned HOST memory and the rendered image read back to the host every step.
+Also on the line: `stage_ms`, `roofline` (HBM fraction as the metric asks + what really binds),
+`gpu_launches` (counted by the library), at N = 1 short legs `sh` (D = 27 / 48) and `opaque_scene`, at
+N > 1 `exchange_check` (active exchange vs NCCL, bit-equality across ranks) and `per_rank`.
 
 --impl reference times the reference's own CUDA build (oracle/_ref: unmodified
 gaussian.cu + bindings.cpp + renderer.py) driven with the reference's per-frame call
