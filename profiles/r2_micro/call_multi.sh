@@ -11,9 +11,11 @@ run() { # tag, extra args
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 50 --warmup 8 "$@" > gpurun_out/m$N/bench_$tag.json 2> gpurun_out/m$N/bench_$tag.err
 }
 run push
+GS_DP_PUSH_MC=0 run push_nomc
+GS_DP_PUSH_MC=1 run push_mc
 run nccl --exchange nccl
 run c5 --workload C5 --steps 30
-python bench.py --gpus 1 --steps 50 --warmup 8 --no-cpu-baseline --no-extra-legs > gpurun_out/m$N/bench_n1.json 2> gpurun_out/m$N/bench_n1.err
+if [ "$N" != "8" ]; then python bench.py --gpus 1 --steps 50 --warmup 8 --no-cpu-baseline --no-extra-legs > gpurun_out/m$N/bench_n1.json 2> gpurun_out/m$N/bench_n1.err; fi
 tail -3 gpurun_out/m$N/pytest_exchange.log; [ -f gpurun_out/m$N/pytest_train_dp.log ] && tail -3 gpurun_out/m$N/pytest_train_dp.log
 python - <<PY
 import json,glob
