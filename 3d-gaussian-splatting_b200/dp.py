@@ -89,8 +89,8 @@ class SymmetricGradBucket:
                        slots and stores the sum to every bucket (gs_allreduce_push_finish_f32).
                        (W-1)/W bucket sizes per direction hidden under the backward + the same
                        again exposed.  The bucket is only complete after `allreduce()`.
-      mode "auto":     push (W = 2, 4, 8; its broadcast half goes through the NVSwitch with multimem.st at
-                       W >= 4 when a multicast mapping exists), else multimem / p2p.
+      mode "auto":     push (W = 2, 4, 8; GS_DP_PUSH_MC=1 sends its broadcast half through the NVSwitch with
+                       multimem.st), else multimem / p2p.
 
     Measured on B200 for the 134 MB bucket of 2.4 M Gaussians (profiles/r1_exchange.md), exchange
     alone: W = 2: p2p 0.214 ms, multimem 0.357, NCCL 0.292; W = 8: multimem 0.330, p2p 0.394,
@@ -139,9 +139,11 @@ class SymmetricGradBucket:
         if self.mode == "auto":
             push = p2p_ok
             self.mode = "p2p" if (p2p_ok or not has_mc) else "multimem"
-        # broadcast half of the pushed exchange through the NVSwitch (multimem.st) where it pays (W >= 4)
-        env_mc = os.environ.get("GS_DP_PUSH_MC")
-        self.push_mc = has_mc and (self.world >= 4 if env_mc is None else env_mc == "1")
+        # broadcast half of the pushed exchange: plain peer stores by default; GS_DP_PUSH_MC=1 sends it through
+        # the NVSwitch instead (one multimem.st per 16 bytes: each GPU sends its slice once, but the switch also
+        # loops the slice back to its owner) - measured within noise of each other at 4 and 8 GPUs
+        # (profiles/r2_scaling.md), so the simpler one ships
+        self.push_mc = has_mc and os.environ.get("GS_DP_PUSH_MC") == "1"
         if self.mode == "multimem" and not has_mc:
             raise RuntimeError("symmetric memory has no multicast mapping (NVLS unavailable)")
         if self.mode == "p2p" and not p2p_ok:

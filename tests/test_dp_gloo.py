@@ -92,7 +92,7 @@ def test_gradient_bucket_allreduce_world2():
 def test_symmetric_bucket_mode_resolution():
     """Mode selection of SymmetricGradBucket without GPUs: the symmetric-memory allocation and the
     exchange kernels are replaced by stand-ins; only the host logic (auto -> push at 2 / 4 / 8 ranks,
-    NVSwitch broadcast from 4 ranks, slice size, allocator contract) runs."""
+    optional NVSwitch broadcast, slice size, allocator contract) runs."""
     sys.path.insert(0, os.path.join(ROOT, "3d-gaussian-splatting_b200"))
     import dp
 
@@ -115,7 +115,12 @@ def test_symmetric_bucket_mode_resolution():
         return b
 
     assert make(2, "auto").mode == "push" and not make(2, "auto").push_mc
-    assert make(4, "auto").mode == "push" and make(4, "auto").push_mc          # broadcast via multimem.st at W >= 4
+    assert make(4, "auto").mode == "push" and not make(4, "auto").push_mc      # plain peer stores unless GS_DP_PUSH_MC=1
+    os.environ["GS_DP_PUSH_MC"] = "1"
+    try:
+        assert make(4, "auto").push_mc and not make(4, "auto", mc=0).push_mc
+    finally:
+        del os.environ["GS_DP_PUSH_MC"]
     assert make(8, "auto", mc=0).mode == "push" and not make(8, "auto", mc=0).push_mc
     assert make(2, "p2p").mode == "p2p" and make(4, "push").mode == "push"
     with pytest.raises(RuntimeError):
