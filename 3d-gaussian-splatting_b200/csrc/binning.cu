@@ -196,21 +196,26 @@ __global__ void __launch_bounds__(kBlock) pack_sorted_sh_kernel(const KeyT* __re
 }
 
 // Tile ranges of the sorted instance list (tile_n_point_accum semantics: accum[t] = first sorted index of
-// tile t, accum[T] = M) for the gather path, where no pack pass walks the keys.
+// tile t, accum[T] = M) for the gather path, where no pack pass walks the keys.  8 consecutive keys per thread.
 template <typename KeyT>
 __global__ void __launch_bounds__(kBlock) tile_ranges_kernel(const KeyT* __restrict__ keys, long long m, int n_tiles,
                                                               int* __restrict__ tile_accum) {
-  long long i = (long long)blockIdx.x * kBlock + threadIdx.x;
-  if (i >= m) return;
-  const uint32_t tile = keys[i];
-  if (i == 0) {
-    for (uint32_t t = 0; t <= tile; ++t) tile_accum[t] = 0;
-  } else {
-    const uint32_t prev = keys[i - 1];
-    for (uint32_t t = prev + 1; t <= tile; ++t) tile_accum[t] = (int)i;
+  const long long i0 = ((long long)blockIdx.x * kBlock + threadIdx.x) * 8;
+  if (i0 >= m) return;
+  uint32_t prev = i0 > 0 ? (uint32_t)keys[i0 - 1] : 0u;
+  if (i0 == 0) tile_accum[0] = 0;
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const long long i = i0 + u;
+    if (i >= m) break;
+    const uint32_t tile = keys[i];
+    for (uint32_t t = prev + 1; t <= tile; ++t) tile_accum[t] = (int)i;      // (empty for equal neighbours)
+    if (i == 0)
+      for (uint32_t t = 1; t <= tile; ++t) tile_accum[t] = 0;
+    prev = tile;
+    if (i == m - 1)
+      for (uint32_t t = tile + 1; t <= (uint32_t)n_tiles; ++t) tile_accum[t] = (int)m;
   }
-  if (i == m - 1)
-    for (uint32_t t = tile + 1; t <= (uint32_t)n_tiles; ++t) tile_accum[t] = (int)m;
 }
 
 __global__ void __launch_bounds__(kBlock) iota_kernel(uint32_t* out, int n) {
@@ -305,7 +310,7 @@ cudaError_t gs_launch_emit_keys(GsRec* rec, const uint32_t* perm, const uint32_t
 cudaError_t gs_launch_tile_ranges(const void* keys, int key_bytes, long long m, int n_tiles, int* tile_accum,
                                   cudaStream_t st) {
   if (m == 0) return cudaMemsetAsync(tile_accum, 0, sizeof(int) * (size_t)(n_tiles + 1), st);
-  const unsigned grid = (unsigned)((m + kBlock - 1) / kBlock);
+  const unsigned grid = (unsigned)((m + 8LL * kBlock - 1) / (8LL * kBlock));
   if (key_bytes == 2)
     tile_ranges_kernel<uint16_t><<<grid, kBlock, 0, st>>>(static_cast<const uint16_t*>(keys), m, n_tiles, tile_accum);
   else

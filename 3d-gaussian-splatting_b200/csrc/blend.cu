@@ -710,8 +710,8 @@ struct Bwd2Cfg {
   static constexpr int STAGES = STAGES_;
 };
 
-template <int PX, int STAGES, int RQ, bool GATHER>
-struct Bwd2Smem : std::conditional<GATHER, GatherRing<WS_CH, STAGES, 4>, WsRing<STAGES>>::type {
+template <int PX, int STAGES, int RQ, bool GATHER, int CH>
+struct Bwd2Smem : std::conditional<GATHER, GatherRing<CH, STAGES, 4>, WsRing<STAGES>>::type {
   float part[Bwd2Cfg<PX, STAGES, RQ>::R * Bwd2Cfg<PX, STAGES, RQ>::IS];
   float pyt[GS_TILE];
   int valid[2];
@@ -754,7 +754,7 @@ __device__ __forceinline__ void bwd_row(const float4 a, const float2 b, const fl
 
 // WS: dedicated producer warp (full / empty mbarrier ring); !WS: consumer thread 0 issues the copies at the
 // chunk boundaries (no extra warp holding registers).  UNR: instances per unrolled step of the first phase.
-template <int PX, bool WS, int UNR, int STAGES, int MINB, int RQ, bool GATHER>
+template <int PX, bool WS, int UNR, int STAGES, int MINB, int RQ, bool GATHER, int CH>
 __global__ void __launch_bounds__(256 / PX + (WS ? 32 : 0), MINB)
     blend_bwd2_kernel(const float4* __restrict__ pA, const float2* __restrict__ pB, const float4* __restrict__ pC,
                       const GsRec* __restrict__ grec, const uint32_t* __restrict__ ids,
@@ -766,14 +766,15 @@ __global__ void __launch_bounds__(256 / PX + (WS ? 32 : 0), MINB)
   constexpr int NT = Cfg::NT, TPR = Cfg::TPR, R = Cfg::R, SQ = Cfg::SQ, QS = Cfg::QS, IS = Cfg::IS, ROWS = Cfg::ROWS;
   static_assert(IS % 2 == 0 && QS % 2 == 0 && IS % 32 == 2 && QS % 32 == 32 / RQ, "partial buffer strides");
   static_assert(!(WS && GATHER), "the gather path issues its copies from all consumer threads");
-  using Smem = Bwd2Smem<PX, STAGES, RQ, GATHER>;
+  static_assert(GATHER || CH == WS_CH, "the packed ring is sized for CH instances per stage");
+  using Smem = Bwd2Smem<PX, STAGES, RQ, GATHER, CH>;
   __shared__ __align__(16) Smem sm;
   const int tile = blockIdx.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int start = tile_accum[tile];
   const int cnt = tile_accum[tile + 1] - start;
   if (cnt == 0) return;
-  const int nchunks = (cnt + WS_CH - 1) / WS_CH;
+  const int nchunks = (cnt + CH - 1) / CH;
   const int tx = tile % ntx, ty = tile / ntx;
   const int shift = start & 1;
   if (tid < GS_TILE) sm.pyt[tid] = gs_pixel_coord(ty * GS_TILE + tid, hp, fy);
@@ -792,16 +793,16 @@ __global__ void __launch_bounds__(256 / PX + (WS ? 32 : 0), MINB)
       }
     } else if (tid == 0) {
       for (int k = 0; k < STAGES && k < nchunks; ++k)
-        issue_chunk<Smem, WS_CH>(sm, k, pA, pB, pC, start + k * WS_CH, min(WS_CH, cnt - k * WS_CH), shift);
+        issue_chunk<Smem, CH>(sm, k, pA, pB, pC, start + k * CH, min(CH, cnt - k * CH), shift);
     }
   }
-  GatherIds<NT, WS_CH> gid;
+  GatherIds<NT, CH> gid;
   if constexpr (GATHER) {
     for (int k = 0; k < STAGES && k < nchunks; ++k) {
-      gid.load(ids, start + k * WS_CH, min(WS_CH, cnt - k * WS_CH), tid);
-      gather_issue<Smem, NT, WS_CH, 4>(sm, k, grec, goff, gid, min(WS_CH, cnt - k * WS_CH), tid);
+      gid.load(ids, start + k * CH, min(CH, cnt - k * CH), tid);
+      gather_issue<Smem, NT, CH, 4>(sm, k, grec, goff, gid, min(CH, cnt - k * CH), tid);
     }
-    if (STAGES < nchunks) gid.load(ids, start + STAGES * WS_CH, min(WS_CH, cnt - STAGES * WS_CH), tid);
+    if (STAGES < nchunks) gid.load(ids, start + STAGES * CH, min(CH, cnt - STAGES * CH), tid);
   }
   const int ix0 = tx * GS_TILE + (tid % TPR) * PX;
   const int iy = ty * GS_TILE + (tid / TPR);
@@ -854,7 +855,7 @@ __global__ void __launch_bounds__(256 / PX + (WS ? 32 : 0), MINB)
   for (; k < nchunks && !finished; ++k) {
     const int stage = k % STAGES;
     gs_mbar_wait(&sm.full[stage], (uint32_t)((k / STAGES) & 1));
-    const int n = min(WS_CH, cnt - k * WS_CH);
+    const int n = min(CH, cnt - k * CH);
     StageView<GATHER> sv;
     if constexpr (GATHER) {
       sv.R = sm.rec[stage];
@@ -960,7 +961,7 @@ __global__ void __launch_bounds__(256 / PX + (WS ? 32 : 0), MINB)
       if (NT == 64) gs_bar_sync(1, NT);            // the partial buffer may be overwritten now
       else __syncwarp();
       if (all_dead) {
-        consumed = min(cnt, k * WS_CH + sub + nr);
+        consumed = min(cnt, k * CH + sub + nr);
         finished = true;
         break;
       }
@@ -968,8 +969,8 @@ __global__ void __launch_bounds__(256 / PX + (WS ? 32 : 0), MINB)
     if constexpr (GATHER) {
       if (!finished && k + STAGES < nchunks) {   // every consumer is past the barrier: the stage is free
         const int kn = k + STAGES;
-        gather_issue<Smem, NT, WS_CH, 4>(sm, stage, grec, goff, gid, min(WS_CH, cnt - kn * WS_CH), tid);
-        if (kn + 1 < nchunks) gid.load(ids, start + (kn + 1) * WS_CH, min(WS_CH, cnt - (kn + 1) * WS_CH), tid);
+        gather_issue<Smem, NT, CH, 4>(sm, stage, grec, goff, gid, min(CH, cnt - kn * CH), tid);
+        if (kn + 1 < nchunks) gid.load(ids, start + (kn + 1) * CH, min(CH, cnt - (kn + 1) * CH), tid);
       }
     } else if (tid == 0) {
       if (WS) {
@@ -978,7 +979,7 @@ __global__ void __launch_bounds__(256 / PX + (WS ? 32 : 0), MINB)
         gs_mbar_arrive(&sm.empty[stage]);
       } else if (!finished && k + STAGES < nchunks) {
         const int kn = k + STAGES;               // every consumer is past the barrier: the stage is free
-        issue_chunk<Smem, WS_CH>(sm, stage, pA, pB, pC, start + kn * WS_CH, min(WS_CH, cnt - kn * WS_CH), shift);
+        issue_chunk<Smem, CH>(sm, stage, pA, pB, pC, start + kn * CH, min(CH, cnt - kn * CH), shift);
       }
     }
   }
@@ -1159,14 +1160,25 @@ cudaError_t gs_launch_blend_bwd(const float4* pA, const float2* pB, const float4
   const bool gather = grec != nullptr;
   if (gather && !row_epoch) return cudaErrorInvalidValue;
   if (tn.bwd_kernel != 0 || gather) {
-#define GS_BWD2(PX, WS, UNR, ST, MINB, RQ, GA)                                                                      \
-  blend_bwd2_kernel<PX, WS, UNR, ST, MINB, RQ, GA><<<g.n_tiles, 256 / PX + (WS ? 32 : 0), 0, st>>>(                  \
+#define GS_BWD2C(PX, WS, UNR, ST, MINB, RQ, GA, CH)                                                                 \
+  blend_bwd2_kernel<PX, WS, UNR, ST, MINB, RQ, GA, CH><<<g.n_tiles, 256 / PX + (WS ? 32 : 0), 0, st>>>(              \
       pA, pB, pC, grec, ids, goff, tile_accum, g.wp, g.hp, g.ntx, g.fx, g.fy, image, grad_image, grad_inst,          \
       grad_is_final,                                                                                                 \
       crop, row_epoch, epoch, tile_neff_b)
+#define GS_BWD2(PX, WS, UNR, ST, MINB, RQ, GA) GS_BWD2C(PX, WS, UNR, ST, MINB, RQ, GA, 64)
     // key: px | producer warp | unroll | stages | reducers per instance | min blocks (2 digits)
     const int key = ((((tn.bwd_px * 10 + tn.bwd_ws) * 10 + tn.bwd_unroll) * 10 + tn.bwd_stages) * 10 + tn.bwd_rq) * 100 +
                     tn.bwd_minb;
+    if (gather && tn.bwd_ch == 32) {
+      switch (key) {
+        case 8022416: GS_BWD2C(8, false, 2, 2, 16, 4, true, 32); break;
+        case 8023416: GS_BWD2C(8, false, 2, 3, 16, 4, true, 32); break;
+        case 8042410: GS_BWD2C(8, false, 4, 2, 10, 4, true, 32); break;
+        case 8043410: GS_BWD2C(8, false, 4, 3, 10, 4, true, 32); break;
+        default: return cudaErrorInvalidValue;
+      }
+      return cudaGetLastError();
+    }
     if (gather) {
       switch (key) {
         case 8012410: GS_BWD2(8, false, 1, 2, 10, 4, true); break;
@@ -1205,6 +1217,7 @@ cudaError_t gs_launch_blend_bwd(const float4* pA, const float2* pB, const float4
       default: return cudaErrorInvalidValue;
     }
 #undef GS_BWD2
+#undef GS_BWD2C
     return cudaGetLastError();
   }
   const int warps = tn.bwd_px == 8 ? 1 : 2;   // round-1 kernel: 1 warp x 8 px or 2 warps x 4 px

@@ -40,6 +40,7 @@ struct GsTuning {
   int bwd_minb;     // __launch_bounds__ min blocks (register cap); 1 = none
   int bwd_rq;       // reducer threads per instance in the second phase: 4 (16 instances per round) or 8 (8)
   int fwd_px;       // pixels per thread of forward kernel 0: 4 (2 warps per tile) or 8 (1 warp)
+  int bwd_ch;       // gather path: instances per staging chunk of the backward (64 or 32)
   int gather;       // RGB frame path: 1 = no pack pass, blend kernels gather records from rec[N]; 0 = packed streams
 };
 GsTuning& gs_tuning();

@@ -49,7 +49,7 @@ GsTuning& gs_tuning() {
   static GsTuning t = {tune_env("GS_TUNE_FWD_KERNEL", 0),  tune_env("GS_TUNE_FWD_CH", 128),   tune_env("GS_TUNE_BWD_KERNEL", 1),
                        tune_env("GS_TUNE_BWD_PX", 8),      tune_env("GS_TUNE_BWD_WS", 0),     tune_env("GS_TUNE_BWD_UNROLL", 2),
                        tune_env("GS_TUNE_BWD_STAGES", 2),  tune_env("GS_TUNE_BWD_MINB", 16),  tune_env("GS_TUNE_BWD_RQ", 4),
-                       tune_env("GS_TUNE_FWD_PX", 4),      tune_env("GS_TUNE_GATHER", 1)};
+                       tune_env("GS_TUNE_FWD_PX", 4),      tune_env("GS_TUNE_BWD_CH", 64),    tune_env("GS_TUNE_GATHER", 1)};
   return t;
 }
 extern "C" int gs_tune(const char* name, int value) {
@@ -60,7 +60,7 @@ extern "C" int gs_tune(const char* name, int value) {
                                              {"bwd_ws", &t.bwd_ws},         {"bwd_unroll", &t.bwd_unroll},
                                              {"bwd_stages", &t.bwd_stages}, {"bwd_minb", &t.bwd_minb},
                                              {"bwd_rq", &t.bwd_rq},         {"fwd_px", &t.fwd_px},
-                                             {"gather", &t.gather}};
+                                             {"gather", &t.gather},         {"bwd_ch", &t.bwd_ch}};
   for (auto& e : tab)
     if (!strcmp(e.k, name)) {
       *e.v = value;

@@ -22,18 +22,16 @@ sp._rctx.set_timing(True)
 go = S.make_grad_output(h, w, 0).to(dev)
 params = list(sp.gaussian_3ds.parameters())
 
-BASE = dict(fwd_kernel=0, fwd_ch=256, fwd_px=4, bwd_kernel=1, bwd_px=8, bwd_ws=0, bwd_unroll=2, bwd_stages=2, bwd_minb=16, bwd_rq=4,
-            gather=0)
+BASE = dict(fwd_kernel=0, fwd_ch=128, fwd_px=4, bwd_kernel=1, bwd_px=8, bwd_ws=0, bwd_unroll=2, bwd_stages=2, bwd_minb=16, bwd_rq=4,
+            bwd_ch=64, gather=1)
 VARIANTS = [
-    ("r1 kernels (packed, thread-0 issue, shuffle reduction)", dict(bwd_kernel=0, bwd_px=4)),
-    ("packed: bwd2 px8 t0 rq4 st2 unroll2 minb16", dict()),
-    ("packed: bwd2 px8 unroll4 minb10", dict(bwd_unroll=4, bwd_minb=10)),
-    ("gather(cp.async): fwd ch256 + bwd2 px8 unroll2 minb16", dict(gather=1)),
-    ("gather: fwd ch128", dict(gather=1, fwd_ch=128)),
-    ("gather: fwd ch64", dict(gather=1, fwd_ch=64)),
-    ("gather: bwd2 px8 unroll4 minb10", dict(gather=1, bwd_unroll=4, bwd_minb=10)),
-    ("gather: bwd2 px8 unroll2 st3 minb16", dict(gather=1, bwd_stages=3)),
-    ("gather: bwd2 px4 unroll4", dict(gather=1, bwd_px=4, bwd_unroll=4, bwd_minb=1)),
+    ("shipped: gather, fwd ch128, bwd2 px8 unroll2 st2 minb16 ch64", dict()),
+    ("bwd ch32 st2", dict(bwd_ch=32)),
+    ("bwd ch32 st3", dict(bwd_ch=32, bwd_stages=3)),
+    ("bwd ch32 st2 unroll4 minb10", dict(bwd_ch=32, bwd_unroll=4, bwd_minb=10)),
+    ("bwd ch32 st3 unroll4 minb10", dict(bwd_ch=32, bwd_unroll=4, bwd_minb=10, bwd_stages=3)),
+    ("bwd ch64 unroll4 minb10", dict(bwd_unroll=4, bwd_minb=10)),
+    ("packed: r1 kernels", dict(gather=0, fwd_ch=256, bwd_kernel=0, bwd_px=4)),
 ]
 
 
