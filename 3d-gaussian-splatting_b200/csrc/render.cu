@@ -47,9 +47,9 @@ static int tune_env(const char* name, int dflt) {
 GsTuning& gs_tuning() {
   // shipped configuration = the best of the sweeps in profiles/r2_sweeps.md
   static GsTuning t = {tune_env("GS_TUNE_FWD_KERNEL", 0),  tune_env("GS_TUNE_FWD_CH", 128),   tune_env("GS_TUNE_BWD_KERNEL", 1),
-                       tune_env("GS_TUNE_BWD_PX", 8),      tune_env("GS_TUNE_BWD_WS", 0),     tune_env("GS_TUNE_BWD_UNROLL", 2),
-                       tune_env("GS_TUNE_BWD_STAGES", 2),  tune_env("GS_TUNE_BWD_MINB", 16),  tune_env("GS_TUNE_BWD_RQ", 4),
-                       tune_env("GS_TUNE_FWD_PX", 4),      tune_env("GS_TUNE_BWD_CH", 64),    tune_env("GS_TUNE_GATHER", 1)};
+                       tune_env("GS_TUNE_BWD_PX", 8),      tune_env("GS_TUNE_BWD_WS", 0),     tune_env("GS_TUNE_BWD_UNROLL", 4),
+                       tune_env("GS_TUNE_BWD_STAGES", 3),  tune_env("GS_TUNE_BWD_MINB", 10),  tune_env("GS_TUNE_BWD_RQ", 4),
+                       tune_env("GS_TUNE_FWD_PX", 4),      tune_env("GS_TUNE_BWD_CH", 32),    tune_env("GS_TUNE_GATHER", 1)};
   return t;
 }
 extern "C" int gs_tune(const char* name, int value) {
