@@ -1175,7 +1175,7 @@ cudaError_t gs_launch_blend_bwd(const float4* pA, const float2* pB, const float4
         case 8023416: GS_BWD2C(8, false, 2, 3, 16, 4, true, 32); break;
         case 8042410: GS_BWD2C(8, false, 4, 2, 10, 4, true, 32); break;
         case 8043410: GS_BWD2C(8, false, 4, 3, 10, 4, true, 32); break;
-        default: return cudaErrorInvalidValue;
+        default: return gs_tuning().strict ? cudaErrorInvalidValue : (GS_BWD2C(8, false, 4, 3, 10, 4, true, 32), cudaGetLastError());
       }
       return cudaGetLastError();
     }
@@ -1192,7 +1192,7 @@ cudaError_t gs_launch_blend_bwd(const float4* pA, const float2* pB, const float4
         case 8013416: GS_BWD2(8, false, 1, 3, 16, 4, true); break;
         case 4012401: GS_BWD2(4, false, 1, 2, 1, 4, true); break;
         case 4042401: GS_BWD2(4, false, 4, 2, 1, 4, true); break;
-        default: return cudaErrorInvalidValue;
+        default: return gs_tuning().strict ? cudaErrorInvalidValue : (GS_BWD2(8, false, 2, 2, 16, 4, true), cudaGetLastError());
       }
       return cudaGetLastError();
     }
@@ -1214,7 +1214,9 @@ cudaError_t gs_launch_blend_bwd(const float4* pA, const float2* pB, const float4
       case 8112410: GS_BWD2(8, true, 1, 2, 10, 4, false); break;
       case 8012424: GS_BWD2(8, false, 1, 2, 24, 4, false); break;
       case 8012824: GS_BWD2(8, false, 1, 2, 24, 8, false); break;
-      default: return cudaErrorInvalidValue;
+      // the packed path (legacy draw API, gs_tune("gather", 0)) has fewer instantiated variants than the gather
+      // path: any other knob combination runs its shipped configuration (strict mode, used by the sweeps, refuses)
+      default: return gs_tuning().strict ? cudaErrorInvalidValue : (GS_BWD2(8, false, 2, 2, 16, 4, false), cudaGetLastError());
     }
 #undef GS_BWD2
 #undef GS_BWD2C

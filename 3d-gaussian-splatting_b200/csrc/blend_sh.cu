@@ -307,30 +307,46 @@ __global__ void __launch_bounds__(64) blend_sh_fwd_kernel(const float4* __restri
   if (tile_neff && tid == 0) tile_neff[tile] = consumed;
 }
 
+// reduce 8 values over the warp: afterwards lane L holds the total of value ((L >> 2) & 7)
+// (bit 4 -> +4, bit 3 -> +2, bit 2 -> +1) in v[0]; 9 SHFL instead of 40
+__device__ __forceinline__ float reduce8(float* v, int lane) {
+  {
+    const bool up = (lane & 16) != 0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float keep = up ? v[u + 4] : v[u];
+      const float send = up ? v[u] : v[u + 4];
+      v[u] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  }
+  {
+    const bool up = (lane & 8) != 0;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const float keep = up ? v[u + 2] : v[u];
+      const float send = up ? v[u] : v[u + 2];
+      v[u] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+  }
+  {
+    const bool up = (lane & 4) != 0;
+    const float keep = up ? v[1] : v[0];
+    const float send = up ? v[0] : v[1];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+  return v[0];
+}
+
 // ---------------------------------------------------------------------------------------
 // backward: 64 threads per tile, a row of 4 pixels per thread
 // grad row (GS_SH_GREC(K) floats): d/d{x, y, ca, cb, cc, l2o}, d/d coef[0..3K)
 // ---------------------------------------------------------------------------------------
-// Two-phase gradient reduction (as in blend.cu, without shuffle networks): every thread stores its 3 + 3K partial
-// sums of an instance (s0, sx, sxx over its row of 4 pixels - dy is shared by the row - and the 3K coefficient
-// gradients) as one row of the partial buffer; every R instances a second phase gives each value COLUMN to one
-// thread (K = 16: 51 columns over the 64 partials) or to two (K = 9: 30 columns, one thread per warp-half), which
-// also forms Sy, Sxy, Syy from the per-row dy.  Row stride NVS: 16-byte aligned and conflict free for the 16-byte
-// stores of a quarter warp; consecutive columns are consecutive banks for the loads.
-template <int K>
-struct ShRed {
-  static constexpr int NVT = 3 + 3 * K;
-  static constexpr int NVS = K == 9 ? 36 : 52;
-  static constexpr int R = 2;
-  static constexpr int HPV = NVT <= 32 ? 2 : 1;
-};
-
 template <int K, bool GATHER>
 struct ShBwdSmem {
   typename std::conditional<GATHER, ShGatherStage<K, 32, 2>, ShStage<K, 32, 2>>::type st;
-  float part[ShRed<K>::R * 64 * ShRed<K>::NVS];
-  float comb[ShRed<K>::R][3][32];
-  float pyt[GS_TILE];
+  float partial[2][32 * sh_nvp(K)];
 };
 
 template <int K, bool GATHER>
@@ -352,7 +368,6 @@ __global__ void __launch_bounds__(64) blend_sh_bwd_kernel(const float4* __restri
   constexpr int CH = 32, STAGES = 2, PX = 4, SW = sh_sw(K), NV = sh_nv(K), NVP = sh_nvp(K), THREADS = 64;
   constexpr int GREC = (NV + 3) / 4 * 4;
   __shared__ __align__(16) ShBwdSmem<K, GATHER> smem;
-  __shared__ int vld[2];
   auto& sm = smem.st;
   const int tile = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tx = tile % ntx, ty = tile / ntx;
@@ -395,7 +410,6 @@ __global__ void __launch_bounds__(64) blend_sh_bwd_kernel(const float4* __restri
 #pragma unroll
     for (int p = 0; p < PX; ++p) T[p] = 1.f;
   }
-  if (tid < GS_TILE) smem.pyt[tid] = gs_pixel_coord(ty * GS_TILE + tid, hp, fy);
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) gs_mbar_init(&sm.full[s], GATHER ? THREADS : 1);
     gs_fence_barrier_init();
@@ -409,13 +423,8 @@ __global__ void __launch_bounds__(64) blend_sh_bwd_kernel(const float4* __restri
       issue_sh<K>(sm, k, pA, pB, pS, start + k * CH, min(CH, cnt - k * CH), shift);
   }
 
-  constexpr int NVT = ShRed<K>::NVT, NVS = ShRed<K>::NVS, RR = ShRed<K>::R, HPV = ShRed<K>::HPV;
-  // second-phase role: value column rv, summed over the source threads of the halves [rh0, rh1)
-  const int rv = HPV == 2 ? lane : tid;
-  const int rh0 = HPV == 2 ? warp : 0, rh1 = HPV == 2 ? warp + 1 : 2;
   int consumed = cnt, k = 0;
-  bool finished = false;
-  for (; k < nchunks && !finished; ++k) {
+  for (; k < nchunks; ++k) {
     const int stage = k % STAGES;
     gs_mbar_wait(&sm.full[stage], (uint32_t)((k / STAGES) & 1));
     const int n = min(CH, cnt - k * CH);
@@ -427,156 +436,110 @@ __global__ void __launch_bounds__(64) blend_sh_bwd_kernel(const float4* __restri
       sv.B = sm.B[stage] + shift;
     }
     sv.S = sm.S[stage];
-    for (int sub = 0; sub < n; sub += RR) {
-      const int nr = min(RR, n - sub);
-      // ---- phase 1
-      int j = 0;
-      for (; j < nr; ++j) {
-        {
-          const bool dead = !(T[0] > GS_T_STOP) && !(T[1] > GS_T_STOP) && !(T[2] > GS_T_STOP) && !(T[3] > GS_T_STOP);
-          if (__all_sync(0xffffffffu, dead)) break;
-        }
-        const float4 a = sv.a(sub + j);
-        const float2 b = sv.b(sub + j);
-        float cf[3 * K];
-        {
-          const float4* c4 = reinterpret_cast<const float4*>(sv.coef(sub + j));
-#pragma unroll
-          for (int q = 0; q < (3 * K + 3) / 4; ++q) {
-            const float4 t4 = c4[q];
-            if (4 * q < 3 * K) cf[4 * q] = t4.x;
-            if (4 * q + 1 < 3 * K) cf[4 * q + 1] = t4.y;
-            if (4 * q + 2 < 3 * K) cf[4 * q + 2] = t4.z;
-            if (4 * q + 3 < 3 * K) cf[4 * q + 3] = t4.w;
-          }
-        }
-        float val[NVS];          // s0, sx, sxx, then the 3K coefficient gradients
-#pragma unroll
-        for (int u = 0; u < NVS; ++u) val[u] = 0.f;
-        const float dy = py - a.y;
-        const float m1 = a.w * dy;
-        const float ev = fmaf(-b.x * dy, dy, b.y);
-#pragma unroll
-        for (int p = 0; p < PX; ++p) {
-          const float dx = px[p] - a.x;
-          const float eu = fmaf(a.z, dx, -m1);
-          const float alpha = gs_ex2(fmaf(-dx, eu, ev));
-          if (T[p] > GS_T_STOP) {          // saturated pixels contribute exactly nothing
-            const float w = alpha * T[p];
-            float col[3];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-              float t = 0.f;
-#pragma unroll
-              for (int q = 0; q < K; ++q) t = fmaf(sh[p][q], cf[c * K + q], t);
-              col[c] = sh_sigmoid(t);
-            }
-            const float gc = fmaf(gr[p], col[0], fmaf(gg[p], col[1], gb[p] * col[2]));
-            R[p] = fmaf(-gc, w, R[p]);
-            const float rc = gs_rcp(1.0000001f - alpha);
-            const float dal = fmaf(T[p], gc, -R[p] * rc);
-            const float e = dal * alpha;
-            T[p] -= w;
-            const float ex = e * dx;
-            val[0] += e;
-            val[1] += ex;
-            val[2] = fmaf(ex, dx, val[2]);
-            // d colour_c / d coef[c*K+q] = sigma'(.) * SH_q      (gaussian.cu:666-674)
-            const float d0 = gr[p] * w * col[0] * (1.f - col[0]);
-            const float d1 = gg[p] * w * col[1] * (1.f - col[1]);
-            const float d2 = gb[p] * w * col[2] * (1.f - col[2]);
-#pragma unroll
-            for (int q = 0; q < K; ++q) {
-              val[3 + q] = fmaf(d0, sh[p][q], val[3 + q]);
-              val[3 + K + q] = fmaf(d1, sh[p][q], val[3 + K + q]);
-              val[3 + 2 * K + q] = fmaf(d2, sh[p][q], val[3 + 2 * K + q]);
-            }
-          }
-        }
-        float4* dst = reinterpret_cast<float4*>(smem.part + (size_t)(j * 64 + tid) * NVS);
-#pragma unroll
-        for (int q = 0; q < NVS / 4; ++q) dst[q] = make_float4(val[4 * q], val[4 * q + 1], val[4 * q + 2], val[4 * q + 3]);
+    float* __restrict__ part = smem.partial[warp];
+    int j = 0;
+    for (; j < n; ++j) {
+      {
+        const bool dead = !(T[0] > GS_T_STOP) && !(T[1] > GS_T_STOP) && !(T[2] > GS_T_STOP) && !(T[3] > GS_T_STOP);
+        if (__all_sync(0xffffffffu, dead)) break;
       }
-      if (lane == 0) vld[warp] = j;              // instances of this round the warp really processed (warp-uniform)
-      const bool dead = !(T[0] > GS_T_STOP) && !(T[1] > GS_T_STOP) && !(T[2] > GS_T_STOP) && !(T[3] > GS_T_STOP);
-      const int all_dead = __syncthreads_and(dead);
-      // ---- phase 2: one (K = 16) or two (K = 9) threads per value column
-      float tot[RR], wy[RR], wyy[RR];
+      const float4 a = sv.a(j);
+      const float2 b = sv.b(j);
+      float cf[3 * K];
+      {
+        const float4* c4 = reinterpret_cast<const float4*>(sv.coef(j));
 #pragma unroll
-      for (int r = 0; r < RR; ++r) {
-        tot[r] = wy[r] = wyy[r] = 0.f;
-        if (r < nr && rv < NVT) {
-          const float ay = sv.a(sub + r).y;
-          for (int h = rh0; h < rh1; ++h) {
-            if (r >= vld[h]) continue;           // that warp had no live pixel left: its rows were not written
-            const float* src = smem.part + (size_t)(r * 64 + h * 32) * NVS + rv;
-            if (rv < 2) {
-#pragma unroll 8
-              for (int sidx = 0; sidx < 32; ++sidx) {
-                const float x = src[sidx * NVS];
-                const float dyr = smem.pyt[(h * 32 + sidx) >> 2] - ay;
-                tot[r] += x;
-                wy[r] = fmaf(dyr, x, wy[r]);
-                wyy[r] = fmaf(dyr * dyr, x, wyy[r]);
-              }
-            } else {
-#pragma unroll 8
-              for (int sidx = 0; sidx < 32; ++sidx) tot[r] += src[sidx * NVS];
-            }
+        for (int q = 0; q < (3 * K + 3) / 4; ++q) {
+          const float4 t4 = c4[q];
+          if (4 * q < 3 * K) cf[4 * q] = t4.x;
+          if (4 * q + 1 < 3 * K) cf[4 * q + 1] = t4.y;
+          if (4 * q + 2 < 3 * K) cf[4 * q + 2] = t4.z;
+          if (4 * q + 3 < 3 * K) cf[4 * q + 3] = t4.w;
+        }
+      }
+      float acc[NVP];
+#pragma unroll
+      for (int u = 0; u < NVP; ++u) acc[u] = 0.f;
+      float s0 = 0.f, sx = 0.f, sxx = 0.f;
+      const float dy = py - a.y;
+      const float m1 = a.w * dy;
+      const float ev = fmaf(-b.x * dy, dy, b.y);
+#pragma unroll
+      for (int p = 0; p < PX; ++p) {
+        const float dx = px[p] - a.x;
+        const float eu = fmaf(a.z, dx, -m1);
+        const float alpha = gs_ex2(fmaf(-dx, eu, ev));
+        if (T[p] > GS_T_STOP) {          // saturated pixels contribute exactly nothing
+          const float w = alpha * T[p];
+          float col[3];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            float t = 0.f;
+#pragma unroll
+            for (int q = 0; q < K; ++q) t = fmaf(sh[p][q], cf[c * K + q], t);
+            col[c] = sh_sigmoid(t);
+          }
+          const float gc = fmaf(gr[p], col[0], fmaf(gg[p], col[1], gb[p] * col[2]));
+          R[p] = fmaf(-gc, w, R[p]);
+          const float rc = gs_rcp(1.0000001f - alpha);
+          const float dal = fmaf(T[p], gc, -R[p] * rc);
+          const float e = dal * alpha;
+          T[p] -= w;
+          const float ex = e * dx;
+          s0 += e;
+          sx += ex;
+          sxx = fmaf(ex, dx, sxx);
+          // d colour_c / d coef[c*K+q] = sigma'(.) * SH_q      (gaussian.cu:666-674)
+          const float d0 = gr[p] * w * col[0] * (1.f - col[0]);
+          const float d1 = gg[p] * w * col[1] * (1.f - col[1]);
+          const float d2 = gb[p] * w * col[2] * (1.f - col[2]);
+#pragma unroll
+          for (int q = 0; q < K; ++q) {
+            acc[6 + q] = fmaf(d0, sh[p][q], acc[6 + q]);
+            acc[6 + K + q] = fmaf(d1, sh[p][q], acc[6 + K + q]);
+            acc[6 + 2 * K + q] = fmaf(d2, sh[p][q], acc[6 + 2 * K + q]);
           }
         }
       }
-      if (HPV == 2) {                              // combine the two halves through shared memory
-        if (warp == 1) {
+      acc[0] = sx;
+      acc[1] = dy * s0;
+      acc[2] = sxx;
+      acc[3] = dy * sx;
+      acc[4] = dy * acc[1];
+      acc[5] = s0;
 #pragma unroll
-          for (int r = 0; r < RR; ++r) {
-            smem.comb[r][0][lane] = tot[r];
-            smem.comb[r][1][lane] = wy[r];
-            smem.comb[r][2][lane] = wyy[r];
-          }
-        }
-        __syncthreads();
-        if (warp == 0) {
-#pragma unroll
-          for (int r = 0; r < RR; ++r) {
-            tot[r] += smem.comb[r][0][lane];
-            wy[r] += smem.comb[r][1][lane];
-            wyy[r] += smem.comb[r][2][lane];
-          }
-        }
-      }
-#pragma unroll
-      for (int r = 0; r < RR; ++r) {
-        // column 0 = S0 (+ Sy, Syy), 1 = Sx (+ Sxy), 2 = Sxx live in lanes 0..2 of warp 0
-        const float sx_t = __shfl_sync(0xffffffffu, tot[r], 1), sxy_t = __shfl_sync(0xffffffffu, wy[r], 1);
-        const float sxx_t = __shfl_sync(0xffffffffu, tot[r], 2);
-        if (r < nr && (HPV == 1 || warp == 0)) {
-          const uint32_t slot = sv.slot(sub + r, tx, ty);
-          float* out = grad_inst + (size_t)slot * GREC;
-          if (tid == 0) {
-            const float4 a = sv.a(sub + r);
-            const float2 b = sv.b(sub + r);
-            const float S0 = tot[r], Sy = wy[r], Syy = wyy[r];
-            out[0] = GS_LN2 * (2.f * a.z * sx_t - a.w * Sy);
-            out[1] = GS_LN2 * (2.f * b.x * Sy - a.w * sx_t);
-            out[2] = -GS_LN2 * sxx_t;
-            out[3] = GS_LN2 * sxy_t;
-            out[4] = -GS_LN2 * Syy;
-            out[5] = GS_LN2 * S0;
-            if (row_epoch) row_epoch[slot] = epoch;
-          } else if (rv >= 3 && rv < NVT) {
-            out[6 + (rv - 3)] = tot[r];
-          }
-        }
-      }
-      __syncthreads();                           // the partial buffer (and comb) may be overwritten now
-      if (all_dead) {
-        consumed = min(cnt, k * CH + sub + nr);
-        finished = true;
-        break;
+      for (int blk = 0; blk < NVP / 8; ++blk) {
+        const float r = reduce8(acc + blk * 8, lane);
+        if ((lane & 3) == 0) part[j * NVP + blk * 8 + ((lane >> 2) & 7)] = r;
       }
     }
-    if (!finished && k + STAGES < nchunks) {
+    for (int z = j * NVP + lane; z < n * NVP; z += 32) part[z] = 0.f;
+    __syncthreads();
+    for (int t = tid; t < n; t += THREADS) {
+      const float* p0 = smem.partial[0] + t * NVP;
+      const float* p1 = smem.partial[1] + t * NVP;
+      const float4 a = sv.a(t);
+      const float2 b = sv.b(t);
+      const uint32_t slot = sv.slot(t, tx, ty);
+      float* out = grad_inst + (size_t)slot * GREC;
+      float s[6];
+#pragma unroll
+      for (int u = 0; u < 6; ++u) s[u] = p0[u] + p1[u];
+      out[0] = GS_LN2 * (2.f * a.z * s[0] - a.w * s[1]);
+      out[1] = GS_LN2 * (2.f * b.x * s[1] - a.w * s[0]);
+      out[2] = -GS_LN2 * s[2];
+      out[3] = GS_LN2 * s[3];
+      out[4] = -GS_LN2 * s[4];
+      out[5] = GS_LN2 * s[5];
+      for (int u = 6; u < NV; ++u) out[u] = p0[u] + p1[u];
+      if (row_epoch) row_epoch[slot] = epoch;
+    }
+    const bool dead = !(T[0] > GS_T_STOP) && !(T[1] > GS_T_STOP) && !(T[2] > GS_T_STOP) && !(T[3] > GS_T_STOP);
+    if (__syncthreads_and(dead)) {
+      consumed = min(cnt, (k + 1) * CH);
+      break;
+    }
+    if (k + STAGES < nchunks) {
       const int kn = k + STAGES;
       if constexpr (GATHER)
         issue_sh_gather<K, THREADS>(sm, stage, grec, rgb, ids, goff, start + kn * CH, min(CH, cnt - kn * CH), tid);
@@ -584,7 +547,6 @@ __global__ void __launch_bounds__(64) blend_sh_bwd_kernel(const float4* __restri
         issue_sh<K>(sm, stage, pA, pB, pS, start + kn * CH, min(CH, cnt - kn * CH), shift);
     }
   }
-  if (finished) --k;          // (the loop increment moved past the chunk that finished) chunks k+1 .. may be in flight
   if (tid == 0 && k < nchunks)
     for (int kk = k + 1; kk < nchunks && kk < k + STAGES; ++kk)
       gs_mbar_wait(&sm.full[kk % STAGES], (uint32_t)((kk / STAGES) & 1));

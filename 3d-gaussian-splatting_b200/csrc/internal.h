@@ -41,7 +41,8 @@ struct GsTuning {
   int bwd_rq;       // reducer threads per instance in the second phase: 4 (16 instances per round) or 8 (8)
   int fwd_px;       // pixels per thread of forward kernel 0: 4 (2 warps per tile) or 8 (1 warp)
   int bwd_ch;       // gather path: instances per staging chunk of the backward (64 or 32)
-  int gather;       // RGB frame path: 1 = no pack pass, blend kernels gather records from rec[N]; 0 = packed streams
+  int strict;       // 1: an un-instantiated knob combination is an error (sweeps); 0: falls back to the shipped kernel
+  int gather;       // fused frame path (RGB and SH): 1 = no pack pass, blend kernels gather records from rec[N]; 0 = packed streams
 };
 GsTuning& gs_tuning();
 
@@ -88,10 +89,8 @@ cudaError_t gs_launch_fused_project_bwd(const float* pos, const float* rgb, cons
                                         float* g_quat, float* g_scale, const GsGradPush& push, cudaStream_t st);
 
 // ---- binning.cu ------------------------------------------------------------------------
-// offsets_g != nullptr: also completes rec[g].d.x (first gradient row) for the gather path
-cudaError_t gs_launch_emit_keys(GsRec* rec, const uint32_t* perm, const uint32_t* offsets_sorted,
-                                const uint32_t* offsets_g, int n, int ntx, void* keys, int key_bytes, uint32_t* vals,
-                                cudaStream_t st);
+cudaError_t gs_launch_emit_keys(const GsRec* rec, const uint32_t* perm, const uint32_t* offsets_sorted, int n, int ntx,
+                                void* keys, int key_bytes, uint32_t* vals, cudaStream_t st);
 cudaError_t gs_launch_tile_ranges(const void* keys, int key_bytes, long long m, int n_tiles, int* tile_accum,
                                   cudaStream_t st);
 

@@ -49,7 +49,8 @@ GsTuning& gs_tuning() {
   static GsTuning t = {tune_env("GS_TUNE_FWD_KERNEL", 0),  tune_env("GS_TUNE_FWD_CH", 128),   tune_env("GS_TUNE_BWD_KERNEL", 1),
                        tune_env("GS_TUNE_BWD_PX", 8),      tune_env("GS_TUNE_BWD_WS", 0),     tune_env("GS_TUNE_BWD_UNROLL", 4),
                        tune_env("GS_TUNE_BWD_STAGES", 3),  tune_env("GS_TUNE_BWD_MINB", 10),  tune_env("GS_TUNE_BWD_RQ", 4),
-                       tune_env("GS_TUNE_FWD_PX", 4),      tune_env("GS_TUNE_BWD_CH", 32),    tune_env("GS_TUNE_GATHER", 1)};
+                       tune_env("GS_TUNE_FWD_PX", 4),      tune_env("GS_TUNE_BWD_CH", 32),    tune_env("GS_TUNE_STRICT", 0),
+                       tune_env("GS_TUNE_GATHER", 1)};
   return t;
 }
 extern "C" int gs_tune(const char* name, int value) {
@@ -60,7 +61,8 @@ extern "C" int gs_tune(const char* name, int value) {
                                              {"bwd_ws", &t.bwd_ws},         {"bwd_unroll", &t.bwd_unroll},
                                              {"bwd_stages", &t.bwd_stages}, {"bwd_minb", &t.bwd_minb},
                                              {"bwd_rq", &t.bwd_rq},         {"fwd_px", &t.fwd_px},
-                                             {"gather", &t.gather},         {"bwd_ch", &t.bwd_ch}};
+                                             {"gather", &t.gather},         {"bwd_ch", &t.bwd_ch},
+                                             {"strict", &t.strict}};
   for (auto& e : tab)
     if (!strcmp(e.k, name)) {
       *e.v = value;
@@ -351,9 +353,8 @@ static int render_forward_impl(gs_ctx* c, const float* pos, const float* rgb, co
     GS_CUDA_TRY(c->vals_in.reserve(M * 4, st));
     GS_CUDA_TRY(c->vals_out.reserve(M * 4, st));
     // 3. instances in (depth, id) order: tile-id keys + Gaussian-id values
-    GS_CUDA_TRY(gs_launch_emit_keys(c->rec.as<GsRec>(), c->perm.as<uint32_t>(), c->offsets.as<uint32_t>(),
-                                    nullptr, n, g.ntx, c->keys_in.p, key_bytes,
-                                    c->vals_in.as<uint32_t>(), st));
+    GS_CUDA_TRY(gs_launch_emit_keys(c->rec.as<GsRec>(), c->perm.as<uint32_t>(), c->offsets.as<uint32_t>(), n, g.ntx,
+                                    c->keys_in.p, key_bytes, c->vals_in.as<uint32_t>(), st));
     gs_count_launch();
     // 4. stable radix sort on the tile id only -> (tile, depth, id)
     gs_mark(c, 3, st);

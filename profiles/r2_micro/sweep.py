@@ -23,7 +23,7 @@ go = S.make_grad_output(h, w, 0).to(dev)
 params = list(sp.gaussian_3ds.parameters())
 
 BASE = dict(fwd_kernel=0, fwd_ch=128, fwd_px=4, bwd_kernel=1, bwd_px=8, bwd_ws=0, bwd_unroll=2, bwd_stages=2, bwd_minb=16, bwd_rq=4,
-            bwd_ch=64, gather=1)
+            bwd_ch=64, gather=1, strict=1)
 VARIANTS = [
     ("shipped: gather, fwd ch128, bwd2 px8 unroll2 st2 minb16 ch64", dict()),
     ("bwd ch32 st2", dict(bwd_ch=32)),

@@ -120,3 +120,40 @@ def test_argument_validation_needs_no_gpu():
     assert lib.gs_adam_step(0x1000, 0x2000, 0x3000, 0x4000, 16, ends, lrs, 1, 0.9, 0.99, 1e-8, 0, None) == -1  # step 0
     assert lib.gs_adam_step(0x1000, 0x2000, 0x3000, 0x4000, 15, ends, lrs, 1, 0.9, 0.99, 1e-8, 1, None) == -1  # n % 4
     assert lib.gs_adam_step(0x1000, 0x2000, 0x3000, 0x4000, 16, ends, lrs, 9, 0.9, 0.99, 1e-8, 1, None) == -1  # > 8 segments
+
+
+def test_round2_entry_points_validate_without_a_gpu():
+    """The entry points added in round 2 (loss, densification, tuning, push-finish through the switch, launch
+    counter) reject bad arguments before touching CUDA."""
+    lib = ctypes.CDLL(os.path.join(PKG, "libgs_b200.so"))
+    lib.gs_last_error.restype = ctypes.c_char_p
+    P, LL, I, F = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_float
+
+    def err():
+        return lib.gs_last_error().decode()
+
+    lib.gs_loss_workspace_bytes.restype = ctypes.c_size_t
+    assert lib.gs_loss_workspace_bytes(1080, 1920) >= 1080 * 1920 * 9 * 4 and lib.gs_loss_workspace_bytes(0, 5) == 0
+    lib.gs_loss_l1_ssim.argtypes = [P, P, I, I, I, F, F, F, P, P, P, ctypes.c_size_t, P]
+    assert lib.gs_loss_l1_ssim(None, None, 0, 64, 64, 0.9, -0.1, 0.1, None, None, None, 0, None) == -1 and "null" in err()
+    assert lib.gs_loss_l1_ssim(0x1000, 0x2000, 0, 8, 64, 0.9, -0.1, 0.1, None, 0x3000, 0x4000, 1 << 30, None) == -1 \
+        and "11x11" in err()
+    assert lib.gs_loss_l1_ssim(0x1000, 0x2000, 0, 64, 64, 0.9, -0.1, 0.1, None, 0x3000, 0x4000, 16, None) == -1 \
+        and "workspace" in err()
+    lib.gs_densify_workspace_bytes.restype = ctypes.c_size_t
+    assert lib.gs_densify_workspace_bytes(1000) > 0
+    lib.gs_densify_plan.argtypes = [P, P, P, I, I, F, F, F, I, F, I, I, P, P, P, ctypes.c_size_t, P]
+    assert lib.gs_densify_plan(None, None, None, -1, 0, 0.0, 1.0, 1e-4, 1, 0.1, 1, 1, None, None, None, 0, None) == -1
+    assert lib.gs_densify_plan(None, None, None, 10, 0, 0.0, 1.0, 1e-4, 1, 0.1, 1, 1, None, None, None, 0, None) == -1
+    lib.gs_densify_apply.argtypes = [P] * 5 + [I, I, P, P, P, F, P, I, I, I, I] + [P] * 6
+    assert lib.gs_densify_apply(*([None] * 5), 10, 3, None, None, None, 0.01, None, 5, 0, 2, 0, *([None] * 6)) == -1  # splits need normals
+    lib.gs_tune.argtypes = [ctypes.c_char_p, I]
+    assert lib.gs_tune(b"no_such_knob", 1) == -1 and "unknown knob" in err()
+    assert lib.gs_tune(None, 1) == -1
+    lib.gs_allreduce_push_finish_mc_f32.argtypes = [P, P, P, LL, LL, I, I, P]
+    assert lib.gs_allreduce_push_finish_mc_f32(None, 0x1000, 0x2000, 64, 32, 0, 2, None) == -1
+    assert lib.gs_allreduce_push_finish_mc_f32(0x1000, 0x2000, 0x3000, 64, 16, 0, 2, None) == -1      # 2 * per < n
+    lib.gs_kernel_launches.restype = ctypes.c_ulonglong
+    assert lib.gs_kernel_launches() == 0                                    # nothing launched in this process
+    lib.gs_frame_tile_consumed.argtypes = [P, P, P]
+    assert lib.gs_frame_tile_consumed(None, None, None) == -1
