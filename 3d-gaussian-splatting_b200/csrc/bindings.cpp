@@ -6,6 +6,7 @@
 // to the C ABI of libgs_b200.so (include/gs_b200.h).  Additive: class `RenderContext`
 // (fused frame path) used by our splatter.py.
 #include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDACachingAllocator.h>
 #include <c10/cuda/CUDAGuard.h>
 #include <torch/extension.h>
 
@@ -234,9 +235,19 @@ struct RenderContext {
                 ") since the forward being differentiated (id ", expected,
                 "); run backward before the next forward, or use one RenderContext / Splatter per in-flight frame");
   }
+  static void* torch_alloc(size_t bytes, void*, gs_stream_t stream) {
+    try {
+      return c10::cuda::CUDACachingAllocator::raw_alloc_with_stream(bytes, (cudaStream_t)stream);
+    } catch (...) {
+      return nullptr;
+    }
+  }
+  static void torch_free(void* p, void*) { c10::cuda::CUDACachingAllocator::raw_delete(p); }
   RenderContext() {
     check_rc(gs_ctx_create(&ctx), "gs_ctx_create");
     cudaGetDevice(&device);
+    // workspaces from PyTorch's stream-ordered caching allocator: growth needs no device synchronisation
+    check_rc(gs_ctx_set_allocator(ctx, &torch_alloc, &torch_free, nullptr), "gs_ctx_set_allocator");
   }
   ~RenderContext() { gs_ctx_destroy(ctx); }
   RenderContext(const RenderContext&) = delete;

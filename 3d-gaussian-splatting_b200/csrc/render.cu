@@ -77,35 +77,57 @@ void gs_count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::m
 extern "C" unsigned long long gs_kernel_launches(void) { return g_launches.load(std::memory_order_relaxed); }
 
 // ---- growable device buffer -------------------------------------------------------------
+// Workspaces come from the caller's allocator when one is installed (gs_ctx_set_allocator: the torch shim
+// passes PyTorch's stream-ordered caching allocator, so growth - e.g. after every densification - needs no
+// device synchronisation and the memory shows up in torch's accounting); else cudaMalloc / cudaFree with a
+// stream synchronisation before a buffer is replaced.
+struct GsAllocator {
+  gs_alloc_fn alloc = nullptr;
+  gs_free_fn free = nullptr;
+  void* user = nullptr;
+};
+static thread_local const GsAllocator* g_cur_alloc = nullptr;   // allocator of the context being served
+
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
-  cudaError_t reserve(size_t bytes, cudaStream_t st) {
-    if (bytes <= cap) return cudaSuccess;
-    if (p) {
-      cudaError_t e = cudaStreamSynchronize(st);
-      if (e != cudaSuccess) return e;
+  const GsAllocator* owner = nullptr;       // allocator the current block came from (nullptr: cudaMalloc)
+  void drop(cudaStream_t st, bool sync) {
+    if (!p) return;
+    if (owner && owner->free) {
+      owner->free(p, owner->user);          // stream-ordered allocator: no synchronisation needed
+    } else {
+      if (sync) cudaStreamSynchronize(st);
       cudaFree(p);
-      p = nullptr;
-      cap = 0;
     }
-    size_t want = bytes + bytes / 8 + 256;   // slack so M jitter between frames does not realloc
-    cudaError_t e = cudaMalloc(&p, want);
-    if (e != cudaSuccess) return e;
-    cap = want;
-    return cudaSuccess;
-  }
-  void release() {
-    if (p) cudaFree(p);
     p = nullptr;
     cap = 0;
   }
+  cudaError_t reserve(size_t bytes, cudaStream_t st) {
+    if (bytes <= cap) return cudaSuccess;
+    drop(st, true);
+    size_t want = bytes + bytes / 8 + 256;   // slack so M jitter between frames does not realloc
+    const GsAllocator* a = g_cur_alloc;
+    if (a && a->alloc) {
+      p = a->alloc(want, a->user, (gs_stream_t)st);
+      if (!p) return cudaErrorMemoryAllocation;
+      owner = a;
+    } else {
+      cudaError_t e = cudaMalloc(&p, want);
+      if (e != cudaSuccess) return e;
+      owner = nullptr;
+    }
+    cap = want;
+    return cudaSuccess;
+  }
+  void release() { drop(nullptr, false); }
   template <typename T>
   T* as() const { return static_cast<T*>(p); }
 };
 
 struct gs_ctx {
   int device = 0;
+  GsAllocator allocator{};
   // per Gaussian
   DevBuf rec, count, offsets, dkey_in, dkey_out, perm, iota, offsets_g;
   size_t iota_n = 0;
@@ -209,6 +231,7 @@ static int render_forward_impl(gs_ctx* c, const float* pos, const float* rgb, co
   if (!image || (n > 0 && (!pos || !rgb || !opa || !quat || !scale)))
     return gs_set_error_msg(GS_ERR_INVALID_ARG, "gs_render_forward: null tensor pointer");
   if (int rc = gs_check_device(c->device, "gs_render_forward")) return rc;
+  g_cur_alloc = &c->allocator;
   cudaStream_t st = (cudaStream_t)stream;
   c->have_forward = false;
   c->have_backward = false;
@@ -458,6 +481,7 @@ static int render_backward_impl(gs_ctx* c, const float* pos, const float* rgb, c
       (c->n > 0 && (!pos || !rgb || !opa || !quat || !scale)))
     return gs_set_error_msg(GS_ERR_INVALID_ARG, "gs_render_backward: null tensor pointer");
   if (int rc = gs_check_device(c->device, "gs_render_backward")) return rc;
+  g_cur_alloc = &c->allocator;
   cudaStream_t st = (cudaStream_t)stream;
   size_t M = (size_t)c->m;
   const int d = c->d;
@@ -466,9 +490,9 @@ static int render_backward_impl(gs_ctx* c, const float* pos, const float* rgb, c
   {
     // one u32 tag per gradient row: rows written by this backward carry `epoch`; the tails of
     // saturated tiles are never written nor read (saves ~0.2 GB of HBM writes + reads at C3)
-    void* before = c->row_epoch.p;
+    const size_t before = c->row_epoch.cap;            // (a caching allocator may hand the same address back)
     GS_CUDA_TRY(c->row_epoch.reserve(M * 4 + 16, st));
-    if (c->row_epoch.p != before || c->epoch == 0xffffffffu) {
+    if (c->row_epoch.cap != before || c->epoch == 0xffffffffu) {
       GS_CUDA_TRY(cudaMemsetAsync(c->row_epoch.p, 0, c->row_epoch.cap, st));
       c->epoch = 0;
     }
@@ -562,6 +586,15 @@ extern "C" int gs_ctx_set_grad_push(gs_ctx* c, const gs_grad_push* p) {
   return 0;
 }
 
+extern "C" int gs_ctx_set_allocator(gs_ctx* c, gs_alloc_fn alloc, gs_free_fn free_fn, void* user) {
+  if (!c || ((alloc == nullptr) != (free_fn == nullptr)))
+    return gs_set_error_msg(GS_ERR_INVALID_ARG, "gs_ctx_set_allocator: null ctx, or only one of alloc / free given");
+  c->allocator.alloc = alloc;        // blocks already held keep the allocator they came from (DevBuf::owner)
+  c->allocator.free = free_fn;
+  c->allocator.user = user;
+  return 0;
+}
+
 extern "C" long long gs_frame_instances(gs_ctx* c) { return (c && c->have_forward) ? c->m : -1; }
 
 extern "C" int gs_frame_stats(gs_ctx* c, gs_frame_info* out, gs_stream_t stream) {
@@ -638,6 +671,7 @@ extern "C" int gs_render_forward_backward_host(gs_ctx* c, const float* pos, cons
   if (cam->width <= 0 || cam->height <= 0)
     return gs_set_error_msg(GS_ERR_INVALID_ARG, "gs_render_forward_backward_host: bad camera");
   cudaStream_t st = (cudaStream_t)stream;
+  g_cur_alloc = &c->allocator;
   int wp = (cam->width + GS_TILE - 1) / GS_TILE * GS_TILE, hp = (cam->height + GS_TILE - 1) / GS_TILE * GS_TILE;
   size_t img_bytes = (size_t)wp * hp * 3 * sizeof(float);
   DevBuf& img_dev = c->img_dev;

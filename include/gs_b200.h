@@ -143,6 +143,14 @@ typedef struct gs_frame_info {
 #define GS_SCALE_EXP 1
 
 int gs_ctx_create(gs_ctx** out);           /* binds to the current CUDA device            */
+/* Optional: workspaces of this context come from the caller's allocator instead of cudaMalloc / cudaFree
+ * (which synchronise the stream when a buffer has to grow, e.g. after every densification).  `alloc` returns
+ * device memory usable on `stream` (NULL = out of memory), `free_fn` releases it stream-ordered (the caller's
+ * allocator must keep the block alive until the work already enqueued on that stream has finished - PyTorch's
+ * caching allocator does; the torch shim installs it).  Pass NULL, NULL to go back to cudaMalloc. */
+typedef void* (*gs_alloc_fn)(size_t bytes, void* user, gs_stream_t stream);
+typedef void (*gs_free_fn)(void* ptr, void* user);
+int gs_ctx_set_allocator(gs_ctx* ctx, gs_alloc_fn alloc, gs_free_fn free_fn, void* user);
 void gs_ctx_destroy(gs_ctx* ctx);          /* frees workspaces (synchronises the device)  */
 
 /* Raw parameters (splatter.py:399-406): pos[n,3], rgb[n,d] (logits if d==3, SH coefficients

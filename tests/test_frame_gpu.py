@@ -610,3 +610,37 @@ def test_densification_kernel_vs_oracle(gs, cuda, act, agg, sh):
     info2 = sp.gaussian_3ds.adaptive_control(torch.zeros(n1, 3, device=cuda), taus=tau, delete_thresh=1.5,
                                              scale_activation=act, use_clone=False, use_split=False)
     assert info2["cloned"] == 0 and info2["split"] == 0 and info2["total"] == n1 - info2["deleted"]
+
+
+def test_workspaces_come_from_the_torch_allocator_and_grow(gs, cuda):
+    """gs_ctx_set_allocator: the torch shim hands PyTorch's caching allocator to the context, so the frame's
+    workspaces are visible in torch's accounting and a growing scene (densification) re-allocates without
+    cudaMalloc / a device synchronisation; results stay identical to a fresh context."""
+    import splatter
+    torch.cuda.synchronize()
+    g1, v, cam = scene(3000, 160, 96, k=0)
+    g2, _, _ = scene(30000, 160, 96, seed=3, k=0)
+    vd = [dict(width=v.width, height=v.height, focal_x=v.fx, focal_y=v.fy, rot=v.rot, tran=v.tran)]
+    sp = splatter.Splatter.from_tensors(g1, vd, device=cuda)
+    m0 = torch.cuda.memory_allocated(cuda)
+    img = sp(0)
+    img.sum().backward()
+    m1 = torch.cuda.memory_allocated(cuda)
+    assert m1 - m0 > 3000 * 64                       # at least the record array lives in torch's pool now
+    # the same context serves a 10x larger scene (what adaptive_control does to a Splatter) ...
+    with torch.no_grad():
+        for name in ("pos", "rgb", "opa", "quat", "scale"):
+            setattr(sp.gaussian_3ds, name, torch.nn.Parameter(g2[name].to(cuda)))
+    go = S.make_grad_output(96, 160, 0).to(cuda) * (96 * 160)
+    img2 = sp(0)
+    img2.backward(go)
+    assert torch.cuda.memory_allocated(cuda) > m1
+    # ... with the same result as a fresh context
+    sp_f = splatter.Splatter.from_tensors(g2, vd, device=cuda)
+    img3 = sp_f(0)
+    img3.backward(go)
+    assert torch.equal(img2, img3)
+    for a, b in zip(sp.gaussian_3ds.parameters(), sp_f.gaussian_3ds.parameters()):
+        assert torch.equal(a.grad, b.grad)
+    del sp, sp_f, img, img2, img3
+    torch.cuda.synchronize()
