@@ -518,7 +518,7 @@ def sh_legs(dev):
         torch.cuda.empty_cache()
         if D == 27:
             try:
-                ref_ms = reference_ms("C3", 27, dev, steps=3, warmup=1)
+                ref_ms = reference_ms("C3", 27, dev, steps=5, warmup=2)
                 if ref_ms:
                     leg["reference_ms_per_step"] = ref_ms
                     leg["vs_reference"] = ref_ms / ms
