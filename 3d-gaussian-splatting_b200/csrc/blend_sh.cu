@@ -9,58 +9,11 @@
 #include <type_traits>
 
 #include "internal.h"
+#include "sh_common.cuh"
 
 namespace {
 
-__host__ __device__ constexpr int sh_sw(int K) { return (3 * K + 1 + 3) / 4 * 4; }       // floats per pS row
-__host__ __device__ constexpr int sh_nv(int K) { return 6 + 3 * K; }                     // reduced values
-__host__ __device__ constexpr int sh_nvp(int K) { return (sh_nv(K) + 7) / 8 * 8; }       // padded to blocks of 8
-
-constexpr float SH_C0 = 0.28209479177387814f;
-constexpr float SH_C1 = 0.4886025119029199f;
-constexpr float SH_C2_0 = 1.0925484305920792f, SH_C2_1 = -1.0925484305920792f, SH_C2_2 = 0.31539156525252005f,
-                SH_C2_3 = -1.0925484305920792f, SH_C2_4 = 0.5462742152960396f;
-constexpr float SH_C3_0 = -0.5900435899266435f, SH_C3_1 = 2.890611442640554f, SH_C3_2 = -0.4570457994644658f,
-                SH_C3_3 = 0.3731763325901154f, SH_C3_4 = -0.4570457994644658f, SH_C3_5 = 1.445305721320277f,
-                SH_C3_6 = -0.5900435899266435f;
-
-template <int K>
-__device__ __forceinline__ void sh_basis(float x, float y, float z, float* out) {
-  out[0] = SH_C0;
-  out[1] = -SH_C1 * y;
-  out[2] = SH_C1 * z;
-  out[3] = -SH_C1 * x;
-  const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-  out[4] = SH_C2_0 * xy;
-  out[5] = SH_C2_1 * yz;
-  out[6] = SH_C2_2 * (2.0f * zz - xx - yy);
-  out[7] = SH_C2_3 * xz;
-  out[8] = SH_C2_4 * (xx - yy);
-  if (K > 9) {
-    out[9] = SH_C3_0 * y * (3.f * xx - yy);
-    out[10] = SH_C3_1 * xy * z;
-    out[11] = SH_C3_2 * y * (4.f * zz - xx - yy);
-    out[12] = SH_C3_3 * z * (2.f * zz - 3.f * xx - 3.f * yy);
-    out[13] = SH_C3_4 * x * (4.f * zz - xx - yy);
-    out[14] = SH_C3_5 * z * (xx - yy);
-    out[15] = SH_C3_6 * x * (xx - 3.f * yy);
-  }
-}
-
-// ray direction of padded pixel (ix, iy): gaussian.cu:849-860
-template <int K>
-__device__ __forceinline__ void pixel_sh(int ix, int iy, const float* __restrict__ rays_o,
-                                         const float* __restrict__ lefttop, const float* __restrict__ vdx,
-                                         const float* __restrict__ vdy, float* out) {
-  float d[3], nn = 0.f;
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    d[i] = __ldg(lefttop + i) + (float)ix * __ldg(vdx + i) + (float)iy * __ldg(vdy + i) - __ldg(rays_o + i);
-    nn += d[i] * d[i];
-  }
-  const float inv = 1.f / (sqrtf(nn) + 1e-7f);
-  sh_basis<K>(d[0] * inv, d[1] * inv, d[2] * inv, out);
-}
+using namespace gs_sh;
 
 template <int K, int CH, int STAGES>
 struct ShStage {
@@ -154,8 +107,6 @@ struct ShView<K, true> {
     return __float_as_uint(R[4 * j + 3].x) + ((uint32_t)ty - (rxy >> 16)) * (rwh & 0xffffu) + ((uint32_t)tx - (rxy & 0xffffu));
   }
 };
-
-__device__ __forceinline__ float sh_sigmoid(float x) { return gs_rcp(1.f + gs_ex2(-x * GS_LOG2E)); }
 
 // ---------------------------------------------------------------------------------------
 // forward: 64 threads per tile, a row of 4 pixels per thread
@@ -574,6 +525,8 @@ cudaError_t gs_launch_blend_sh_fwd(const float4* pA, const float2* pB, const flo
   blend_sh_fwd_kernel<K, GA><<<g.n_tiles, 64, 0, st>>>(pA, pB, pS, grec, rgb, ids, goff, tile_accum, g.wp, g.hp, g.ntx,   \
                                                        g.fx, g.fy, r.rays_o, r.lefttop, r.dx, r.dy, image, tile_neff, \
                                                        final_img, crop)
+  if (grec && (gs_tuning().sh_tc & 1))
+    return gs_launch_blend_sh_fwd_tc(grec, rgb, ids, d, tile_accum, g, r, image, tile_neff, final_img, crop, st);
   if (grec) {
     if (d == 27) GS_SHF(9, true); else GS_SHF(16, true);
   } else {

@@ -1,0 +1,273 @@
+// Tile blend with per-pixel SH colour on the 5th-generation tensor cores (tcgen05, accumulators in TMEM).
+//
+// The two dense contractions of the SH path (reference gaussian.cu:936-948 forward colour, :665-689 backward)
+//   logit[pixel, (instance, channel)] = sum_q SH_q(pixel) * coef[instance, channel, q]                  (forward + backward)
+//   d coef[(instance, channel), q]    = sum_pixel d logit[pixel, (instance, channel)] * SH_q(pixel)     (backward)
+// are the only GEMM-shaped work of the rasterizer: 2 * 3K (forward) + 4 * 3K (backward) FMAs of the 57 / 137
+// instructions the scalar kernels (blend_sh.cu) spend per (pixel, instance).  Here ONE THREAD OWNS ONE PIXEL:
+//   * a tile is 256 pixels = two M = 128 accumulator blocks; the SH basis of the tile is written once to shared
+//     memory as bf16 hi + lo parts (x = hi + lo to 2^-17) in the no-swizzle canonical layout, whose image is at the
+//     same time the K-major A operand of the first and the MN-major B operand of the second contraction;
+//   * per round of 16 instances the raw coefficients (gathered by cp.async, as in blend_sh.cu) are split into
+//     bf16 hi / lo K-major B operands [48 x 16] (pre-multiplied by -log2 e), three MMAs per block
+//     (hi*hi + hi*lo + lo*hi, fp32 accumulate: logits to ~2e-5 relative) leave the logits of 16 instances x 3
+//     channels in 48 TMEM columns of the lane (= pixel) that blends them: tcgen05.ld 32x32b hands every thread
+//     its own pixel's row, so the front-to-back recurrence stays a plain sequential loop;
+//   * backward: the per-(pixel, instance) logit gradients are written back to shared memory as the MN-major A
+//     operand [96 rows = (hi | lo) x 3 channels x 16 instances, K = 256 pixels] and contracted with the basis
+//     image (N = 32 = hi | lo) by 16 K = 16 MMAs; the six geometry sums per instance keep the warp-shuffle reduction.
+// Layouts / descriptor encodings: tc_common.cuh (validated by profiles/r2_micro/umma_probe.cu).
+#include "internal.h"
+#include "sh_common.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+using namespace gs_sh;
+using namespace gs_tc;
+
+constexpr int TC_J = 16;     // instances per round
+constexpr int TC_NT = 256;   // threads per CTA = pixels per tile
+
+template <int K, int STAGES>
+struct TcStage {
+  float4 R[STAGES][TC_J * 4];
+  float S[STAGES][TC_J * sh_sw(K)];
+  uint64_t full[STAGES];
+};
+
+// 16 threads per instance: record (3 x 16 B), first gradient row (backward), raw coefficients
+template <int K, int STAGES, bool BWD>
+__device__ __forceinline__ void tc_gather(TcStage<K, STAGES>& sm, int stage, const GsRec* __restrict__ grec,
+                                          const float* __restrict__ rgb, const uint32_t* __restrict__ ids,
+                                          const uint32_t* __restrict__ goff, int base, int n, int tid) {
+  constexpr int SW = sh_sw(K), D = 3 * K;
+  const int i = tid >> 4, l = tid & 15;
+  if (i < n) {
+    const uint32_t id = ids[base + i];
+    const uint32_t dr = gs_smem_u32(&sm.R[stage][i * 4]);
+    if (l < 3) {
+      const float4* src4 = reinterpret_cast<const float4*>(grec + id) + l;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dr + 16u * l), "l"(src4) : "memory");
+    } else if (BWD && l == 3) {
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dr + 48u), "l"(goff + id) : "memory");
+    }
+    const float* src = rgb + (size_t)id * D;
+    const uint32_t ds = gs_smem_u32(&sm.S[stage][i * SW]);
+    if ((D * 4) % 16 == 0) {
+      for (int q = l; q < D / 4; q += 16)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ds + 16u * q), "l"(src + 4 * q) : "memory");
+    } else {
+      for (int q = l; q < D; q += 16)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(ds + 4u * q), "l"(src + q) : "memory");
+    }
+  }
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(gs_smem_u32(&sm.full[stage])) : "memory");
+}
+
+// raw coefficients of one round -> K-major bf16 operands [n = channel * 16 + instance][q], scaled by -log2 e
+// (the blend needs 2^(-logit * log2 e)); element (n, q) lives in 16-byte unit (q / 8) * 48 + n.  q >= K stays 0.
+template <int K>
+__device__ __forceinline__ void tc_split_coefs(const float* __restrict__ S, uint4* __restrict__ bc_hi,
+                                               uint4* __restrict__ bc_lo, int tid) {
+  constexpr int SW = sh_sw(K);
+  if (tid < 96) {
+    const int n = tid % 48, g = tid / 48, c = n >> 4, j = n & 15;
+    const float* src = S + j * SW + c * K + g * 8;
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const float v0 = (g * 8 + 2 * w < K) ? -GS_LOG2E * src[2 * w] : 0.f;
+      const float v1 = (g * 8 + 2 * w + 1 < K) ? -GS_LOG2E * src[2 * w + 1] : 0.f;
+      split_bf16x2(v0, v1, h[w], l[w]);
+    }
+    bc_hi[g * 48 + n] = make_uint4(h[0], h[1], h[2], h[3]);
+    bc_lo[g * 48 + n] = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+
+// SH basis of this thread's pixel -> bf16 hi / lo operand image: 16-byte unit (q / 8) * 256 + pixel
+template <int K>
+__device__ __forceinline__ void tc_store_basis(const float* sh, uint4* __restrict__ img_hi, uint4* __restrict__ img_lo,
+                                               int pixel) {
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const float v0 = (g * 8 + 2 * w < K) ? sh[g * 8 + 2 * w] : 0.f;
+      const float v1 = (g * 8 + 2 * w + 1 < K) ? sh[g * 8 + 2 * w + 1] : 0.f;
+      split_bf16x2(v0, v1, h[w], l[w]);
+    }
+    img_hi[g * 256 + pixel] = make_uint4(h[0], h[1], h[2], h[3]);
+    img_lo[g * 256 + pixel] = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+
+// logits of one round: D[block][pixel, n] = basis[pixel, :] . coef[n, :]   (3 MMAs per 128-pixel block)
+__device__ __forceinline__ void tc_issue_logits(uint32_t tm, const uint4* img_hi, const uint4* img_lo, const uint4* bc_hi,
+                                                const uint4* bc_lo, uint64_t* bar) {
+  constexpr uint32_t idesc = idesc_bf16(0, 0, 128, 48);
+  const uint64_t b_hi = smem_desc(gs_smem_u32(bc_hi), 768, 128), b_lo = smem_desc(gs_smem_u32(bc_lo), 768, 128);
+#pragma unroll
+  for (int b = 0; b < 2; ++b) {
+    const uint64_t a_hi = smem_desc(gs_smem_u32(img_hi) + b * 2048, 4096, 128);
+    const uint64_t a_lo = smem_desc(gs_smem_u32(img_lo) + b * 2048, 4096, 128);
+    mma_bf16(tm + b * 48, a_hi, b_hi, idesc, 0);
+    mma_bf16(tm + b * 48, a_hi, b_lo, idesc, 1);
+    mma_bf16(tm + b * 48, a_lo, b_hi, idesc, 1);
+  }
+  mma_commit(bar);
+}
+
+// three sigmoids from v_c = -logit_c * log2 e with ONE reciprocal (see blend_sh.cu)
+__device__ __forceinline__ void tc_colours(float v0, float v1, float v2, float* col) {
+  const float d0 = 1.f + gs_ex2(fminf(v0, 40.f)), d1 = 1.f + gs_ex2(fminf(v1, 40.f)), d2 = 1.f + gs_ex2(fminf(v2, 40.f));
+  const float d01 = d0 * d1;
+  const float r = gs_rcp(d01 * d2);
+  col[2] = r * d01;
+  const float r2 = r * d2;
+  col[0] = r2 * d1;
+  col[1] = r2 * d0;
+}
+
+// ---------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------
+template <int K>
+struct TcFwdSmem {
+  uint4 img_hi[2 * 256];
+  uint4 img_lo[2 * 256];
+  uint4 bc_hi[2 * 48];
+  uint4 bc_lo[2 * 48];
+  TcStage<K, 4> st;
+  uint64_t mma_bar;
+  uint32_t tmem_base;
+};
+
+template <int K>
+__global__ void __launch_bounds__(TC_NT) blend_sh_fwd_tc_kernel(const GsRec* __restrict__ grec, const float* __restrict__ rgb,
+                                                                const uint32_t* __restrict__ ids,
+                                                                const int* __restrict__ tile_accum, int wp, int hp, int ntx,
+                                                                float fx, float fy, const float* __restrict__ rays_o,
+                                                                const float* __restrict__ lefttop,
+                                                                const float* __restrict__ vdx, const float* __restrict__ vdy,
+                                                                float* __restrict__ image, int* __restrict__ tile_neff,
+                                                                float* __restrict__ final_img, GsCrop crop) {
+  constexpr int STAGES = 4, TCOLS = 128;
+  __shared__ __align__(128) TcFwdSmem<K> sm;
+  const int tile = blockIdx.x, tid = threadIdx.x, warp = tid >> 5;
+  const int tx = tile % ntx, ty = tile / ntx;
+  const int ix = tx * GS_TILE + (tid & 15), iy = ty * GS_TILE + (tid >> 4);
+  const int start = tile_accum[tile];
+  const int cnt = tile_accum[tile + 1] - start;
+  float T = 1.f, cr = 0.f, cg = 0.f, cb = 0.f;
+  int consumed = cnt;
+  if (cnt > 0) {                                              // uniform over the CTA
+    const int nchunks = (cnt + TC_J - 1) / TC_J;
+    if (tid == 0) {
+      for (int s = 0; s < STAGES; ++s) gs_mbar_init(&sm.st.full[s], TC_NT);
+      gs_mbar_init(&sm.mma_bar, 1);
+      gs_fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc<TCOLS>(&sm.tmem_base);
+    {
+      float sh[16];
+      pixel_sh<K>(ix, iy, rays_o, lefttop, vdx, vdy, sh);
+      tc_store_basis<K>(sh, sm.img_hi, sm.img_lo, tid);
+    }
+    if (tid < 96) {                                           // q >= K columns of the coefficient operand stay zero
+      sm.bc_hi[tid] = make_uint4(0, 0, 0, 0);
+      sm.bc_lo[tid] = make_uint4(0, 0, 0, 0);
+    }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tm = sm.tmem_base;
+    const uint32_t trow = tm + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(warp >> 2) * 48u;
+    const float px = gs_pixel_coord(ix, wp, fx), py = gs_pixel_coord(iy, hp, fy);
+    for (int k = 0; k < STAGES - 1 && k < nchunks; ++k)
+      tc_gather<K, STAGES, false>(sm.st, k, grec, rgb, ids, nullptr, start + k * TC_J, min(TC_J, cnt - k * TC_J), tid);
+
+    for (int k = 0; k < nchunks; ++k) {
+      const int stage = k % STAGES;
+      gs_mbar_wait(&sm.st.full[stage], (uint32_t)((k / STAGES) & 1));
+      const int n = min(TC_J, cnt - k * TC_J);
+      tc_split_coefs<K>(sm.st.S[stage], sm.bc_hi, sm.bc_lo, tid);
+      fence_smem_to_async();
+      fence_before_sync();
+      // every thread has finished round k - 1 (its TMEM reads, its staged rows); all pixels saturated -> done
+      if (__syncthreads_and(!(T > GS_T_STOP))) {
+        consumed = k * TC_J;
+        break;
+      }
+      if (warp == 0) {
+        if (elect_one()) {
+          fence_after_sync();
+          tc_issue_logits(tm, sm.img_hi, sm.img_lo, sm.bc_hi, sm.bc_lo, &sm.mma_bar);
+        }
+        __syncwarp();
+      }
+      if (k + STAGES - 1 < nchunks) {
+        const int kn = k + STAGES - 1;
+        tc_gather<K, STAGES, false>(sm.st, kn % STAGES, grec, rgb, ids, nullptr, start + kn * TC_J,
+                                    min(TC_J, cnt - kn * TC_J), tid);
+      }
+      gs_mbar_wait(&sm.mma_bar, (uint32_t)(k & 1));
+      fence_after_sync();
+      const float4* R = sm.st.R[stage];
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        if (h * 8 >= n) break;
+        if (__all_sync(0xffffffffu, !(T > GS_T_STOP))) break;
+        float lr[8], lg[8], lb[8];
+        tmem_ld8x3(trow + h * 8, trow + 16 + h * 8, trow + 32 + h * 8, lr, lg, lb);
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          const int j = h * 8 + jj;
+          if (j < n) {
+            const float4 a = R[4 * j];
+            const float4 b4 = R[4 * j + 1];
+            const float dx = px - a.x, dy = py - a.y;
+            const float eu = fmaf(a.z, dx, -a.w * dy);
+            const float ev = fmaf(-b4.x * dy, dy, b4.y);
+            const float alpha = gs_ex2(fmaf(-dx, eu, ev));
+            if (T > GS_T_STOP) {
+              const float w = alpha * T;
+              float col[3];
+              tc_colours(lr[jj], lg[jj], lb[jj], col);
+              cr = fmaf(col[0], w, cr);
+              cg = fmaf(col[1], w, cg);
+              cb = fmaf(col[2], w, cb);
+              T -= w;
+            }
+          }
+        }
+      }
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<TCOLS>(tm);
+  }
+  float* o = image + ((size_t)iy * wp + ix) * 3;
+  o[0] = cr;
+  o[1] = cg;
+  o[2] = cb;
+  if (final_img) gs_store_final(final_img, ix, iy, crop.left, crop.top, crop.width, crop.height, cr, cg, cb);
+  if (tile_neff && tid == 0) tile_neff[tile] = consumed;
+}
+
+}  // namespace
+
+cudaError_t gs_launch_blend_sh_fwd_tc(const GsRec* grec, const float* rgb, const uint32_t* ids, int d,
+                                      const int* tile_accum, const GsFrameGeom& g, const GsRayPtrs& r, float* image,
+                                      int* tile_neff, float* final_img, const GsCrop& crop, cudaStream_t st) {
+#define GS_SHF_TC(K)                                                                                                  \
+  blend_sh_fwd_tc_kernel<K><<<g.n_tiles, TC_NT, 0, st>>>(grec, rgb, ids, tile_accum, g.wp, g.hp, g.ntx, g.fx, g.fy,     \
+                                                         r.rays_o, r.lefttop, r.dx, r.dy, image, tile_neff, final_img, \
+                                                         crop)
+  if (d == 27) GS_SHF_TC(9); else GS_SHF_TC(16);
+#undef GS_SHF_TC
+  return cudaGetLastError();
+}

@@ -43,6 +43,7 @@ struct GsTuning {
   int bwd_ch;       // gather path: instances per staging chunk of the backward (64 or 32)
   int strict;       // 1: an un-instantiated knob combination is an error (sweeps); 0: falls back to the shipped kernel
   int gather;       // fused frame path (RGB and SH): 1 = no pack pass, blend kernels gather records from rec[N]; 0 = packed streams
+  int sh_tc;        // SH blend on the tensor cores (blend_sh_tc.cu, gather path only): bit 0 = forward, bit 1 = backward
 };
 GsTuning& gs_tuning();
 
@@ -65,6 +66,11 @@ cudaError_t gs_launch_blend_sh_bwd(const float4* pA, const float2* pB, const flo
                                    const GsFrameGeom& g, const GsRayPtrs& r, const float* image,
                                    const float* grad_image, float* grad_inst, int grad_is_final, const GsCrop& crop,
                                    uint32_t* row_epoch, uint32_t epoch, int* tile_neff_b, cudaStream_t st);
+
+// ---- blend_sh_tc.cu (tcgen05 / TMEM) -----------------------------------------------------
+cudaError_t gs_launch_blend_sh_fwd_tc(const GsRec* grec, const float* rgb, const uint32_t* ids, int d,
+                                      const int* tile_accum, const GsFrameGeom& g, const GsRayPtrs& r, float* image,
+                                      int* tile_neff, float* final_img, const GsCrop& crop, cudaStream_t st);
 
 // ---- project.cu ------------------------------------------------------------------------
 cudaError_t gs_launch_fused_project(const float* pos, const float* rgb, const float* opa, const float* quat,

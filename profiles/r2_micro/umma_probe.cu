@@ -1,0 +1,298 @@
+// Probe of tcgen05.mma (cta_group::1) with the no-swizzle canonical shared-memory layouts that the SH
+// blend kernels use: checks descriptor encodings, the TMEM lane mapping of M = 64 / 128 accumulators
+// and the cost of short MMA batches.  Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o umma_probe
+// umma_probe.cu ; run `umma_probe <test>` on the B200 box (every wait is bounded: a wrong descriptor
+// reports, it does not hang).
+//   test 1: tf32, A K-major [128 x 16], B K-major [48 x 16]          (colour logits: pixels x (inst,ch))
+//   test 2: tf32, A MN-major [M x 128], B MN-major [16 x 128], M=128 (coefficient gradients)
+//   test 3: same as 2 with M = 64 (prints the lane of every row)
+//   test 4: bf16, A MN-major [M=128 x 128], B MN-major [16 x 128], K = 16 per instruction
+//   test 5: timing of batches (6 x m128n48k8 tf32; 16 x m128n16k8; 16 x m64n16k8; 8 x bf16 m128n16k16)
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cstdio>
+#include <cstdint>
+#include <cstdlib>
+#include <cmath>
+#include <vector>
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ int g_swap = 0;   // probe variant: exchange the leading / stride byte offsets
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+  if (g_swap) { const uint32_t t = lbo; lbo = sbo; sbo = t; }
+  const uint32_t lo = ((addr & 0x3FFFFu) >> 4) | ((lbo >> 4) << 16);
+  const uint32_t hi = (sbo >> 4) | (1u << 14);                    // version 1 (sm_100), no swizzle, base offset 0
+  return ((uint64_t)hi << 32) | lo;
+}
+__host__ __device__ constexpr uint32_t make_idesc(int fmt, int a_mn, int b_mn, int M, int N) {
+  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_tf32(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+               :: "r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void mma_f16(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+               :: "r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int n) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(n) : "memory");
+}
+__device__ __forceinline__ bool mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  for (int spin = 0; spin < (1 << 22) && !ok; ++spin)
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t addr, float* v) {
+  uint32_t r[16];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n\t"
+               "tcgen05.wait::ld.sync.aligned;"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(addr) : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+#ifdef ELECT
+#define ISSUER (warp == 0 && elect_one())
+#else
+#define ISSUER (tid == 0)
+#endif
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__host__ __device__ inline float aval(int m, int k) { return k == 0 ? m * 0.125f : (float)(((m * 7 + k * 3) % 17) - 8) * 0.125f; }
+__host__ __device__ inline float bval(int n, int k) { return (float)(((n * 5 + k * 11) % 13) - 6) * 0.25f; }
+
+constexpr int SMEM_BYTES = 160 * 1024;
+
+// out: [128 lanes][ncols] raw TMEM dump; flag: 0 ok, 1 = mbarrier timeout
+__global__ void __launch_bounds__(128) probe(int test, float* out, int* flag, long long* clk, int reps) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base)), "r"(64));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = tmem_base;
+  float* A = reinterpret_cast<float*>(smem);
+  float* B = reinterpret_cast<float*>(smem + 96 * 1024);
+  uint32_t parity = 0;
+  int ncols = 0;
+
+  const bool skip_ld = test == 6, skip_mma = test == 7;
+  if (test == 6 || test == 7) test = 1;
+  if (test == 1) {
+    // K-major: (r, k) -> (r%8)*16 + (r/8)*128 + (k/4)*LBO + (k%4)*4 bytes ; LBO = rows*16
+    for (int i = tid; i < 128 * 16; i += 128) {
+      const int r = i / 16, k = i % 16;
+      A[((r % 8) * 16 + (r / 8) * 128 + (k / 4) * 2048 + (k % 4) * 4) / 4] = aval(r, k);
+    }
+    for (int i = tid; i < 48 * 16; i += 128) {
+      const int r = i / 16, k = i % 16;
+      B[((r % 8) * 16 + (r / 8) * 128 + (k / 4) * 768 + (k % 4) * 4) / 4] = bval(r, k);
+    }
+    fence_async_smem();
+    __syncthreads();
+    if (tid == 0 && skip_mma) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(&bar)) : "memory"); }
+    if (!skip_mma && ISSUER) {
+      tc_fence_after();
+      const uint32_t idesc = make_idesc(2, 0, 0, 128, 48);
+      for (int s = 0; s < 2; ++s)
+        mma_tf32(tm, make_desc(smem_u32(A) + s * 2 * 2048, 2048, 128), make_desc(smem_u32(B) + s * 2 * 768, 768, 128),
+                 idesc, s > 0);
+      mma_commit(&bar);
+    }
+    ncols = 48;
+  } else if (test == 2 || test == 3) {
+    // MN-major: (m, k) -> (k/8)*128 + (m/4)*SBO + (k%8)*16 + (m%4)*4 ; SBO = (K/8)*128 = 2048
+    const int M = test == 2 ? 128 : 64;
+    for (int i = tid; i < M * 128; i += 128) {
+      const int m = i / 128, k = i % 128;
+      A[((k / 8) * 128 + (m / 4) * 2048 + (k % 8) * 16 + (m % 4) * 4) / 4] = aval(m, k);
+    }
+    for (int i = tid; i < 16 * 128; i += 128) {
+      const int n = i / 128, k = i % 128;
+      B[((k / 8) * 128 + (n / 4) * 2048 + (k % 8) * 16 + (n % 4) * 4) / 4] = bval(n, k);
+    }
+    fence_async_smem();
+    __syncthreads();
+    if (ISSUER) {
+      tc_fence_after();
+      const uint32_t idesc = make_idesc(2, 1, 1, M, 16);
+      for (int s = 0; s < 16; ++s)
+        mma_tf32(tm, make_desc(smem_u32(A) + s * 128, 128, 2048), make_desc(smem_u32(B) + s * 128, 128, 2048), idesc, s > 0);
+      mma_commit(&bar);
+    }
+    ncols = 16;
+  } else if (test == 4) {
+    // bf16 MN-major: (m, k) -> (k/8)*128 + (m/8)*SBO + (k%8)*16 + (m%8)*2 ; SBO = (K/8)*128 ; LBO = 128 ; K = 16 / MMA
+    __nv_bfloat16* Ah = reinterpret_cast<__nv_bfloat16*>(A);
+    __nv_bfloat16* Bh = reinterpret_cast<__nv_bfloat16*>(B);
+    for (int i = tid; i < 128 * 128; i += 128) {
+      const int m = i / 128, k = i % 128;
+      Ah[((k / 8) * 128 + (m / 8) * 2048 + (k % 8) * 16 + (m % 8) * 2) / 2] = __float2bfloat16(aval(m, k));
+    }
+    for (int i = tid; i < 16 * 128; i += 128) {
+      const int n = i / 128, k = i % 128;
+      Bh[((k / 8) * 128 + (n / 8) * 2048 + (k % 8) * 16 + (n % 8) * 2) / 2] = __float2bfloat16(bval(n, k));
+    }
+    fence_async_smem();
+    __syncthreads();
+    if (ISSUER) {
+      tc_fence_after();
+      const uint32_t idesc = make_idesc(1, 1, 1, 128, 16);
+      for (int s = 0; s < 8; ++s)
+        mma_f16(tm, make_desc(smem_u32(A) + s * 256, 128, 2048), make_desc(smem_u32(B) + s * 256, 128, 2048), idesc, s > 0);
+      mma_commit(&bar);
+    }
+    ncols = 16;
+  } else {
+    // timing: smem contents do not matter
+    for (int i = tid; i < 24 * 1024; i += 128) { A[i] = 0.f; }
+    for (int i = tid; i < 4 * 1024; i += 128) { B[i] = 0.f; }
+    fence_async_smem();
+    __syncthreads();
+    for (int mode = 0; mode < 8; ++mode) {
+      const bool sync_each = (mode & 1) == 0;
+      const int kind = mode >> 1;
+      __syncthreads();
+      const long long t0 = clock64();
+      for (int r = 0; r < reps; ++r) {
+        if (tid == 0) {
+          tc_fence_after();
+          if (kind == 0) {
+            const uint32_t idesc = make_idesc(2, 0, 0, 128, 48);
+            for (int s = 0; s < 6; ++s)
+              mma_tf32(tm, make_desc(smem_u32(A) + (s & 1) * 4096, 2048, 128), make_desc(smem_u32(B) + (s & 1) * 1536, 768, 128), idesc, s > 0);
+          } else if (kind == 1 || kind == 2) {
+            const uint32_t idesc = make_idesc(2, 1, 1, kind == 1 ? 128 : 64, 16);
+            for (int s = 0; s < 16; ++s)
+              mma_tf32(tm, make_desc(smem_u32(A) + s * 128, 128, 2048), make_desc(smem_u32(B) + s * 128, 128, 2048), idesc, s > 0);
+          } else {
+            const uint32_t idesc = make_idesc(1, 1, 1, 128, 16);
+            for (int s = 0; s < 8; ++s)
+              mma_f16(tm, make_desc(smem_u32(A) + s * 256, 128, 2048), make_desc(smem_u32(B) + s * 256, 128, 2048), idesc, s > 0);
+          }
+          if (sync_each || r == reps - 1 || (r & 7) == 7) mma_commit(&bar);
+        }
+        if (sync_each || r == reps - 1 || (r & 7) == 7) {
+          if (!mbar_wait_bounded(&bar, parity)) { if (tid == 0) *flag = 1; }
+          parity ^= 1;
+        }
+      }
+      const long long t1 = clock64();
+      if (tid == 0 && blockIdx.x == 0) clk[mode] = t1 - t0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tm), "r"(64));
+    return;
+  }
+  if (tid == 0 || tid == 33) printf("tid %d tm=0x%x before wait\n", tid, tm);
+  const bool ok = mbar_wait_bounded(&bar, 0);
+  if (!ok && tid == 0) *flag = 1;
+  tc_fence_after();
+  if (blockIdx.x == 0 && !skip_ld) {
+    for (int c0 = 0; c0 < ncols; c0 += 16) {
+      float v[16];
+      tmem_ld16(tm + ((uint32_t)(warp * 32) << 16) + c0, v);
+      for (int i = 0; i < 16; ++i) out[tid * 64 + c0 + i] = v[i];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (tid == 0 || tid == 33) printf("tid %d tm=0x%x tmem_base=0x%x before dealloc\n", tid, tm, tmem_base);
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tm), "r"(64));
+}
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); return 2; } } while (0)
+
+int main(int argc, char** argv) {
+  const int test = argc > 1 ? atoi(argv[1]) : 1;
+  float* out; int* flag; long long* clk;
+  CK(cudaMalloc(&out, 128 * 64 * 4)); CK(cudaMalloc(&flag, 4)); CK(cudaMalloc(&clk, 64));
+  CK(cudaMemset(out, 0xff, 128 * 64 * 4)); CK(cudaMemset(flag, 0, 4)); CK(cudaMemset(clk, 0, 64));
+  CK(cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  if (test == 5) {
+    const int reps = 2000;
+    for (int grid : {1, 148, 148 * 2, 148 * 4}) {
+      // several CTAs per SM need less shared memory: the timing test touches the first 112 KB only
+      const int smem = grid <= 148 ? SMEM_BYTES : (grid == 296 ? 112 * 1024 : 0);
+      if (smem == 0) continue;
+      cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+      probe<<<grid, 128, smem>>>(5, out, flag, clk, 10);
+      CK(cudaDeviceSynchronize());
+      cudaEventRecord(e0);
+      probe<<<grid, 128, smem>>>(5, out, flag, clk, reps);
+      cudaEventRecord(e1);
+      CK(cudaDeviceSynchronize());
+      float ms; cudaEventElapsedTime(&ms, e0, e1);
+      long long h[8]; int f;
+      CK(cudaMemcpy(h, clk, 64, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(&f, flag, 4, cudaMemcpyDeviceToHost));
+      printf("grid %4d  total %.3f ms  timeout_flag %d\n", grid, ms, f);
+      const char* names[4] = {"6 x tf32 m128n48k8 (K-major)", "16 x tf32 m128n16k8 (MN-major)", "16 x tf32 m64n16k8 (MN-major)", "8 x bf16 m128n16k16 (MN-major)"};
+      for (int m = 0; m < 8; ++m)
+        printf("   %-34s %-18s %8.1f clk / batch\n", names[m >> 1], (m & 1) ? "commit every 8" : "commit+wait each", (double)h[m] / reps);
+    }
+    return 0;
+  }
+  const int variant = argc > 2 ? atoi(argv[2]) : 0;
+  CK(cudaMemcpyToSymbol(g_swap, &variant, 4));
+  probe<<<1, 128, SMEM_BYTES>>>(test, out, flag, clk, 0);
+  CK(cudaDeviceSynchronize());
+  std::vector<float> h(128 * 64); int f;
+  CK(cudaMemcpy(h.data(), out, 128 * 64 * 4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(&f, flag, 4, cudaMemcpyDeviceToHost));
+  const int M = test == 3 ? 64 : 128, N = test == 1 ? 48 : 16, K = test == 1 ? 16 : 128;
+  std::vector<float> ref(M * N);
+  for (int m = 0; m < M; ++m)
+    for (int n = 0; n < N; ++n) {
+      float s = 0.f;
+      for (int k = 0; k < K; ++k) s += aval(m, k) * bval(n, k);
+      ref[m * N + n] = s;
+    }
+  printf("test %d variant %d timeout_flag %d\n", test, variant, f);
+  // find for every row of the reference the TMEM lane that holds it
+  int matched = 0, identity = 0;
+  for (int m = 0; m < M; ++m) {
+    int found = -1;
+    for (int lane = 0; lane < 128 && found < 0; ++lane) {
+      bool eq = true;
+      for (int n = 0; n < N && eq; ++n) eq = h[lane * 64 + n] == ref[m * N + n];
+      if (eq) found = lane;
+    }
+    if (found >= 0) ++matched;
+    if (found == m) ++identity;
+    if (test == 3 || found != m) { if (m < 70) printf("  row %3d -> lane %d\n", m, found); }
+  }
+  printf("rows matched %d / %d, identity mapping %d\n", matched, M, identity);
+  printf("lane0: ");
+  for (int n = 0; n < 8; ++n) printf("%g ", h[n]);
+  printf("| ref row0: ");
+  for (int n = 0; n < 8; ++n) printf("%g ", ref[n]);
+  printf("\n");
+  return matched == M ? 0 : 1;
+}
