@@ -258,38 +258,6 @@ __global__ void __launch_bounds__(64) blend_sh_fwd_kernel(const float4* __restri
   if (tile_neff && tid == 0) tile_neff[tile] = consumed;
 }
 
-// reduce 8 values over the warp: afterwards lane L holds the total of value ((L >> 2) & 7)
-// (bit 4 -> +4, bit 3 -> +2, bit 2 -> +1) in v[0]; 9 SHFL instead of 40
-__device__ __forceinline__ float reduce8(float* v, int lane) {
-  {
-    const bool up = (lane & 16) != 0;
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const float keep = up ? v[u + 4] : v[u];
-      const float send = up ? v[u] : v[u + 4];
-      v[u] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-    }
-  }
-  {
-    const bool up = (lane & 8) != 0;
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const float keep = up ? v[u + 2] : v[u];
-      const float send = up ? v[u] : v[u + 2];
-      v[u] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-    }
-  }
-  {
-    const bool up = (lane & 4) != 0;
-    const float keep = up ? v[1] : v[0];
-    const float send = up ? v[0] : v[1];
-    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-  }
-  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
-  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
-  return v[0];
-}
-
 // ---------------------------------------------------------------------------------------
 // backward: 64 threads per tile, a row of 4 pixels per thread
 // grad row (GS_SH_GREC(K) floats): d/d{x, y, ca, cb, cc, l2o}, d/d coef[0..3K)
@@ -543,6 +511,9 @@ cudaError_t gs_launch_blend_sh_bwd(const float4* pA, const float2* pB, const flo
                                    const float* grad_image, float* grad_inst, int grad_is_final, const GsCrop& crop,
                                    uint32_t* row_epoch, uint32_t epoch, int* tile_neff_b, cudaStream_t st) {
   if (grec && !row_epoch) return cudaErrorInvalidValue;
+  if (grec && (gs_tuning().sh_tc & 2))
+    return gs_launch_blend_sh_bwd_tc(grec, rgb, ids, goff, d, tile_accum, g, r, image, grad_image, grad_inst, grad_is_final,
+                                     crop, row_epoch, epoch, tile_neff_b, st);
 #define GS_SHB(K, GA)                                                                                               \
   blend_sh_bwd_kernel<K, GA><<<g.n_tiles, 64, 0, st>>>(pA, pB, pS, grec, rgb, ids, goff, tile_accum, g.wp, g.hp, g.ntx,   \
                                                        g.fx, g.fy, r.rays_o, r.lefttop, r.dx, r.dy, image, grad_image, \

@@ -258,6 +258,267 @@ __global__ void __launch_bounds__(TC_NT) blend_sh_fwd_tc_kernel(const GsRec* __r
   if (tile_neff && tid == 0) tile_neff[tile] = consumed;
 }
 
+// ---------------------------------------------------------------------------------------
+// backward
+// grad row (GS_SH_GREC(K) floats): d/d{x, y, ca, cb, cc, l2o}, d/d coef[0..3K)
+// ---------------------------------------------------------------------------------------
+template <int K>
+struct TcBwdSmem {
+  // A operand of the coefficient-gradient contraction, MN-major: 16-byte unit G * 256 + pixel holds the 8 rows
+  // (instances 8h .. 8h+7 of channel c, hi or lo part) G = part * 6 + c * 2 + h of that pixel.  The M = 128
+  // instruction reads 16 groups: the last four fall into img_hi / img_lo, which MUST follow (their rows are unused).
+  uint4 dct[12 * 256];
+  uint4 img_hi[2 * 256];
+  uint4 img_lo[2 * 256];
+  uint4 bc_hi[2 * 48];
+  uint4 bc_lo[2 * 48];
+  TcStage<K, 4> st;
+  float part[8][TC_J][8];      // per-warp sums of the six geometry values
+  float epi[48][17];           // (lo part) . basis, staged for the thread that owns the hi row
+  uint64_t mma_bar, mma2_bar;
+  uint32_t tmem_base;
+};
+
+template <int K>
+__global__ void __launch_bounds__(TC_NT) blend_sh_bwd_tc_kernel(const GsRec* __restrict__ grec, const float* __restrict__ rgb,
+                                                                const uint32_t* __restrict__ ids,
+                                                                const uint32_t* __restrict__ goff,
+                                                                const int* __restrict__ tile_accum, int wp, int hp, int ntx,
+                                                                float fx, float fy, const float* __restrict__ rays_o,
+                                                                const float* __restrict__ lefttop,
+                                                                const float* __restrict__ vdx, const float* __restrict__ vdy,
+                                                                const float* __restrict__ image,
+                                                                const float* __restrict__ grad_image,
+                                                                float* __restrict__ grad_inst, int grad_is_final, GsCrop crop,
+                                                                uint32_t* __restrict__ row_epoch, uint32_t epoch,
+                                                                int* __restrict__ tile_neff_b) {
+  constexpr int STAGES = 4, TCOLS = 256, NV = sh_nv(K), GREC = (NV + 3) / 4 * 4;
+  constexpr uint32_t D2COL = 96;                            // logits: columns [0, 96); gradient accumulators: 2 x 32
+  extern __shared__ __align__(128) uint8_t tc_smem_raw[];
+  TcBwdSmem<K>& sm = *reinterpret_cast<TcBwdSmem<K>*>(tc_smem_raw);
+  const int tile = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tx = tile % ntx, ty = tile / ntx;
+  const int ix = tx * GS_TILE + (tid & 15), iy = ty * GS_TILE + (tid >> 4);
+  const int start = tile_accum[tile];
+  const int cnt = tile_accum[tile + 1] - start;
+  if (cnt == 0) return;
+  const int nchunks = (cnt + TC_J - 1) / TC_J;
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) gs_mbar_init(&sm.st.full[s], TC_NT);
+    gs_mbar_init(&sm.mma_bar, 1);
+    gs_mbar_init(&sm.mma2_bar, 1);
+    gs_fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<TCOLS>(&sm.tmem_base);
+  {
+    float sh[16];
+    pixel_sh<K>(ix, iy, rays_o, lefttop, vdx, vdy, sh);
+    tc_store_basis<K>(sh, sm.img_hi, sm.img_lo, tid);
+  }
+  if (tid < 96) {
+    sm.bc_hi[tid] = make_uint4(0, 0, 0, 0);
+    sm.bc_lo[tid] = make_uint4(0, 0, 0, 0);
+  }
+  float T = 1.f, R, gr, gg, gb;
+  {
+    const size_t off = ((size_t)iy * wp + ix) * 3;
+    const float raw[3] = {image[off], image[off + 1], image[off + 2]};
+    if (!grad_is_final) {
+      gr = grad_image[off];
+      gg = grad_image[off + 1];
+      gb = grad_image[off + 2];
+    } else {
+      gs_load_final_grad(grad_image, raw, ix, iy, crop.left, crop.top, crop.width, crop.height, gr, gg, gb);
+    }
+    R = gr * raw[0] + gg * raw[1] + gb * raw[2];
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tm = sm.tmem_base;
+  const uint32_t tlane = (uint32_t)((warp & 3) * 32) << 16;
+  const uint32_t trow = tm + tlane + (uint32_t)(warp >> 2) * 48u;
+  const float px = gs_pixel_coord(ix, wp, fx), py = gs_pixel_coord(iy, hp, fy);
+  for (int k = 0; k < STAGES - 1 && k < nchunks; ++k)
+    tc_gather<K, STAGES, true>(sm.st, k, grec, rgb, ids, goff, start + k * TC_J, min(TC_J, cnt - k * TC_J), tid);
+
+  int consumed = cnt;
+  for (int k = 0; k < nchunks; ++k) {
+    const int stage = k % STAGES;
+    gs_mbar_wait(&sm.st.full[stage], (uint32_t)((k / STAGES) & 1));
+    const int n = min(TC_J, cnt - k * TC_J);
+    tc_split_coefs<K>(sm.st.S[stage], sm.bc_hi, sm.bc_lo, tid);
+    fence_smem_to_async();
+    fence_before_sync();
+    if (__syncthreads_and(!(T > GS_T_STOP))) {              // round k - 1 is complete everywhere
+      consumed = k * TC_J;
+      break;
+    }
+    if (warp == 0) {
+      if (elect_one()) {
+        fence_after_sync();
+        tc_issue_logits(tm, sm.img_hi, sm.img_lo, sm.bc_hi, sm.bc_lo, &sm.mma_bar);
+      }
+      __syncwarp();
+    }
+    if (k + STAGES - 1 < nchunks) {
+      const int kn = k + STAGES - 1;
+      tc_gather<K, STAGES, true>(sm.st, kn % STAGES, grec, rgb, ids, goff, start + kn * TC_J, min(TC_J, cnt - kn * TC_J),
+                                 tid);
+    }
+    gs_mbar_wait(&sm.mma_bar, (uint32_t)(k & 1));
+    fence_after_sync();
+    const float4* Rr = sm.st.R[stage];
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+      if (h * 8 >= n) break;
+      uint32_t hw[3][4], lw[3][4];
+      if (__all_sync(0xffffffffu, !(T > GS_T_STOP))) {
+        // nothing left to blend in this warp: the rows of this half round are zeros
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          sm.dct[(c * 2 + h) * 256 + tid] = make_uint4(0, 0, 0, 0);
+          sm.dct[(6 + c * 2 + h) * 256 + tid] = make_uint4(0, 0, 0, 0);
+        }
+        sm.part[warp][h * 8 + (lane >> 2)][lane & 3] = 0.f;
+        sm.part[warp][h * 8 + (lane >> 2)][4 + (lane & 3)] = 0.f;
+        continue;
+      }
+      float lr[8], lg[8], lb[8];
+      tmem_ld8x3(trow + h * 8, trow + 16 + h * 8, trow + 32 + h * 8, lr, lg, lb);
+#pragma unroll
+      for (int jp = 0; jp < 4; ++jp) {
+        float dc[2][3];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int jj = 2 * jp + u, j = h * 8 + jj;
+          float v[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) v[q] = 0.f;
+          dc[u][0] = dc[u][1] = dc[u][2] = 0.f;
+          if (j < n) {
+            const float4 a = Rr[4 * j];
+            const float4 b4 = Rr[4 * j + 1];
+            const float dx = px - a.x, dy = py - a.y;
+            const float eu = fmaf(a.z, dx, -a.w * dy);
+            const float ev = fmaf(-b4.x * dy, dy, b4.y);
+            const float alpha = gs_ex2(fmaf(-dx, eu, ev));
+            if (T > GS_T_STOP) {                            // saturated pixels contribute exactly nothing
+              const float w = alpha * T;
+              float col[3];
+              tc_colours(lr[jj], lg[jj], lb[jj], col);
+              const float gc = fmaf(gr, col[0], fmaf(gg, col[1], gb * col[2]));
+              R = fmaf(-gc, w, R);
+              const float rc = gs_rcp(1.0000001f - alpha);
+              const float dal = fmaf(T, gc, -R * rc);
+              const float e = dal * alpha;
+              T -= w;
+              const float ex = e * dx, ey = e * dy;
+              v[0] = ex;
+              v[1] = ey;
+              v[2] = ex * dx;
+              v[3] = ex * dy;
+              v[4] = ey * dy;
+              v[5] = e;
+              // d colour_c / d logit_c = sigma'(.)      (gaussian.cu:666-674)
+              dc[u][0] = gr * w * col[0] * (1.f - col[0]);
+              dc[u][1] = gg * w * col[1] * (1.f - col[1]);
+              dc[u][2] = gb * w * col[2] * (1.f - col[2]);
+            }
+            const float r = reduce8(v, lane);
+            if ((lane & 3) == 0) sm.part[warp][j][(lane >> 2) & 7] = r;
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) split_bf16x2(dc[0][c], dc[1][c], hw[c][jp], lw[c][jp]);
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        sm.dct[(c * 2 + h) * 256 + tid] = make_uint4(hw[c][0], hw[c][1], hw[c][2], hw[c][3]);
+        sm.dct[(6 + c * 2 + h) * 256 + tid] = make_uint4(lw[c][0], lw[c][1], lw[c][2], lw[c][3]);
+      }
+    }
+    fence_smem_to_async();
+    fence_before_sync();
+    __syncthreads();                                        // gradient operand + geometry partials complete
+    if (warp == 0) {
+      if (elect_one()) {
+        fence_after_sync();
+        constexpr uint32_t idesc2 = idesc_bf16(1, 1, 128, 32);
+        const uint32_t a0 = gs_smem_u32(sm.dct), b0 = gs_smem_u32(sm.img_hi);
+#pragma unroll
+        for (int s = 0; s < 16; ++s)
+          mma_bf16(tm + D2COL + (uint32_t)(s & 1) * 32u, smem_desc(a0 + s * 256, 128, 4096), smem_desc(b0 + s * 256, 128, 4096),
+                   idesc2, s >= 2);
+        mma_commit(&sm.mma2_bar);
+      }
+      __syncwarp();
+    }
+    // geometry rows (while the tensor core contracts): threads 128 .. 143, one instance each
+    if (tid >= 128 && tid < 128 + n) {
+      const int j = tid - 128;
+      float s[6];
+#pragma unroll
+      for (int u = 0; u < 6; ++u) {
+        float t = 0.f;
+#pragma unroll
+        for (int w8 = 0; w8 < 8; ++w8) t += sm.part[w8][j][u];
+        s[u] = t;
+      }
+      const float4 a = Rr[4 * j];
+      const float4 b4 = Rr[4 * j + 1];
+      const float4 cc = Rr[4 * j + 2];
+      const uint32_t rxy = __float_as_uint(cc.z), rwh = __float_as_uint(cc.w);
+      const uint32_t slot = __float_as_uint(Rr[4 * j + 3].x) + ((uint32_t)ty - (rxy >> 16)) * (rwh & 0xffffu) +
+                            ((uint32_t)tx - (rxy & 0xffffu));
+      float* out = grad_inst + (size_t)slot * GREC;
+      out[0] = GS_LN2 * (2.f * a.z * s[0] - a.w * s[1]);
+      out[1] = GS_LN2 * (2.f * b4.x * s[1] - a.w * s[0]);
+      out[2] = -GS_LN2 * s[2];
+      out[3] = GS_LN2 * s[3];
+      out[4] = -GS_LN2 * s[4];
+      out[5] = GS_LN2 * s[5];
+      row_epoch[slot] = epoch;
+    }
+    gs_mbar_wait(&sm.mma2_bar, (uint32_t)(k & 1));
+    fence_after_sync();
+    float val[16];
+    if (warp < 3) {                                         // rows 0 .. 95 live in TMEM lanes 0 .. 95
+      float a0[16], a1[16], b0[16], b1[16];
+      tmem_ld16(tm + tlane + D2COL, a0);
+      tmem_ld16(tm + tlane + D2COL + 16, a1);
+      tmem_ld16(tm + tlane + D2COL + 32, b0);
+      tmem_ld16(tm + tlane + D2COL + 48, b1);
+      if (tid < 48) {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) val[q] = (a0[q] + b0[q]) + (a1[q] + b1[q]);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) sm.epi[tid - 48][q] = a0[q] + b0[q];
+      }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (tid < 48) {
+      const int c = tid >> 4, j = tid & 15;
+      if (j < n) {
+        const float4 cc = Rr[4 * j + 2];
+        const uint32_t rxy = __float_as_uint(cc.z), rwh = __float_as_uint(cc.w);
+        const uint32_t slot = __float_as_uint(Rr[4 * j + 3].x) + ((uint32_t)ty - (rxy >> 16)) * (rwh & 0xffffu) +
+                              ((uint32_t)tx - (rxy & 0xffffu));
+        float* out = grad_inst + (size_t)slot * GREC + 6 + c * K;
+#pragma unroll
+        for (int q = 0; q < K; ++q) out[q] = val[q] + sm.epi[tid][q];
+      }
+    }
+  }
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<TCOLS>(tm);
+  if (tile_neff_b && tid == 0) tile_neff_b[tile] = consumed;
+}
+
 }  // namespace
 
 cudaError_t gs_launch_blend_sh_fwd_tc(const GsRec* grec, const float* rgb, const uint32_t* ids, int d,
@@ -269,5 +530,28 @@ cudaError_t gs_launch_blend_sh_fwd_tc(const GsRec* grec, const float* rgb, const
                                                          crop)
   if (d == 27) GS_SHF_TC(9); else GS_SHF_TC(16);
 #undef GS_SHF_TC
+  return cudaGetLastError();
+}
+
+cudaError_t gs_launch_blend_sh_bwd_tc(const GsRec* grec, const float* rgb, const uint32_t* ids, const uint32_t* goff, int d,
+                                      const int* tile_accum, const GsFrameGeom& g, const GsRayPtrs& r, const float* image,
+                                      const float* grad_image, float* grad_inst, int grad_is_final, const GsCrop& crop,
+                                      uint32_t* row_epoch, uint32_t epoch, int* tile_neff_b, cudaStream_t st) {
+  if (!row_epoch) return cudaErrorInvalidValue;   // unprocessed rows are left stale: the consumer needs the epoch tags
+#define GS_SHB_TC(K)                                                                                                  \
+  do {                                                                                                                \
+    static bool attr_done = false;                                                                                    \
+    if (!attr_done) {                                                                                                 \
+      cudaError_t e = cudaFuncSetAttribute(blend_sh_bwd_tc_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                           (int)sizeof(TcBwdSmem<K>));                                                \
+      if (e != cudaSuccess) return e;                                                                                 \
+      attr_done = true;                                                                                               \
+    }                                                                                                                 \
+    blend_sh_bwd_tc_kernel<K><<<g.n_tiles, TC_NT, sizeof(TcBwdSmem<K>), st>>>(                                          \
+        grec, rgb, ids, goff, tile_accum, g.wp, g.hp, g.ntx, g.fx, g.fy, r.rays_o, r.lefttop, r.dx, r.dy, image,       \
+        grad_image, grad_inst, grad_is_final, crop, row_epoch, epoch, tile_neff_b);                                   \
+  } while (0)
+  if (d == 27) GS_SHB_TC(9); else GS_SHB_TC(16);
+#undef GS_SHB_TC
   return cudaGetLastError();
 }

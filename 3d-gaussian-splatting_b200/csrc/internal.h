@@ -71,6 +71,10 @@ cudaError_t gs_launch_blend_sh_bwd(const float4* pA, const float2* pB, const flo
 cudaError_t gs_launch_blend_sh_fwd_tc(const GsRec* grec, const float* rgb, const uint32_t* ids, int d,
                                       const int* tile_accum, const GsFrameGeom& g, const GsRayPtrs& r, float* image,
                                       int* tile_neff, float* final_img, const GsCrop& crop, cudaStream_t st);
+cudaError_t gs_launch_blend_sh_bwd_tc(const GsRec* grec, const float* rgb, const uint32_t* ids, const uint32_t* goff, int d,
+                                      const int* tile_accum, const GsFrameGeom& g, const GsRayPtrs& r, const float* image,
+                                      const float* grad_image, float* grad_inst, int grad_is_final, const GsCrop& crop,
+                                      uint32_t* row_epoch, uint32_t epoch, int* tile_neff_b, cudaStream_t st);
 
 // ---- project.cu ------------------------------------------------------------------------
 cudaError_t gs_launch_fused_project(const float* pos, const float* rgb, const float* opa, const float* quat,
