@@ -71,7 +71,7 @@ template <int K>
 __device__ __forceinline__ void tc_split_coefs(const float* __restrict__ S, uint4* __restrict__ bc_hi,
                                                uint4* __restrict__ bc_lo, int tid) {
   constexpr int SW = sh_sw(K);
-  if (tid < 96) {
+  if ((unsigned)tid < 96u) {
     const int n = tid % 48, g = tid / 48, c = n >> 4, j = n & 15;
     const float* src = S + j * SW + c * K + g * 8;
     uint32_t h[4], l[4];
@@ -273,8 +273,9 @@ struct TcBwdSmem {
   uint4 bc_hi[2 * 48];
   uint4 bc_lo[2 * 48];
   TcStage<K, 4> st;
-  float part[8][TC_J][8];      // per-warp sums of the six geometry values
+  float part[2][8][TC_J][8];   // per-warp sums of the six geometry values (by round parity)
   float epi[48][17];           // (lo part) . basis, staged for the thread that owns the hi row
+  uint32_t slot[TC_J];         // gradient rows of the round whose coefficient gradients are still in TMEM
   uint64_t mma_bar, mma2_bar;
   uint32_t tmem_base;
 };
@@ -342,108 +343,166 @@ __global__ void __launch_bounds__(TC_NT) blend_sh_bwd_tc_kernel(const GsRec* __r
   for (int k = 0; k < STAGES - 1 && k < nchunks; ++k)
     tc_gather<K, STAGES, true>(sm.st, k, grec, rgb, ids, goff, start + k * TC_J, min(TC_J, cnt - k * TC_J), tid);
 
-  int consumed = cnt;
+  // coefficient-gradient rows of the previous round: its contraction ran while this round's operands were prepared.
+  // Rows 0 .. 95 of the accumulators live in TMEM lanes 0 .. 95 (warps 0 .. 2): (hi part) x (basis hi | lo) in rows
+  // 0 .. 47, (lo part) x basis hi in rows 48 .. 95, summed by the thread that owns the hi row.
+  auto epilogue = [&](int np) {
+    if (warp < 3) {
+      float a[32], b[32];
+      tmem_ld32(tm + tlane + D2COL, a);
+      tmem_ld32(tm + tlane + D2COL + 32, b);
+      if (tid >= 48) {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) sm.epi[tid - 48][q] = a[q] + b[q];
+      }
+      gs_bar_sync(1, 96);
+      if (tid < 48) {
+        const int c = tid >> 4, j = tid & 15;
+        if (j < np) {
+          float* out = grad_inst + (size_t)sm.slot[j] * GREC + 6 + c * K;
+#pragma unroll
+          for (int q = 0; q < K; ++q) out[q] = ((a[q] + b[q]) + (a[16 + q] + b[16 + q])) + sm.epi[tid][q];
+        }
+      }
+    }
+  };
+
+  // one (pixel, instance) pair: blend state update, logit gradients dc[3], geometry values v[0..5]
+  auto pair = [&](const float4 a, const float4 b4, float l0, float l1, float l2, float* dc, float* v) {
+    const float dx = px - a.x, dy = py - a.y;
+    const float eu = fmaf(a.z, dx, -a.w * dy);
+    const float ev = fmaf(-b4.x * dy, dy, b4.y);
+    const float alpha = gs_ex2(fmaf(-dx, eu, ev));
+    const bool live = T > GS_T_STOP;                        // saturated pixels contribute exactly nothing
+    const float w = live ? alpha * T : 0.f;
+    float col[3];
+    tc_colours(l0, l1, l2, col);
+    const float gc = fmaf(gr, col[0], fmaf(gg, col[1], gb * col[2]));
+    R = fmaf(-gc, w, R);
+    const float rc = gs_rcp(1.0000001f - alpha);
+    const float dal = fmaf(T, gc, -R * rc);
+    const float e = live ? dal * alpha : 0.f;
+    T -= w;
+    const float ex = e * dx, ey = e * dy;
+    v[0] = ex;
+    v[1] = ey;
+    v[2] = ex * dx;
+    v[3] = ex * dy;
+    v[4] = ey * dy;
+    v[5] = e;
+    v[6] = 0.f;
+    v[7] = 0.f;
+    // d colour_c / d logit_c = sigma'(.)      (gaussian.cu:666-674)
+    dc[0] = gr * w * col[0] * (1.f - col[0]);
+    dc[1] = gg * w * col[1] * (1.f - col[1]);
+    dc[2] = gb * w * col[2] * (1.f - col[2]);
+  };
+
+  // Schedule of round k (ONE CTA-wide barrier per round; the tensor core works one step ahead / behind):
+  //   wait logits(k)  ->  [96 threads: split the coefficients of round k + 1]  ->  first 8 instances  ->
+  //   wait contraction(k - 1) (it read sm.dct)  ->  store their rows  ->  [warps 0-2: coefficient rows of round k - 1]
+  //   ->  second 8 instances  ->  barrier + "all pixels saturated" vote  ->  issue logits(k + 1), then contraction(k)
+  //   ->  [warp 4: geometry rows of round k]  ->  gather round k + 3.
+  int consumed = cnt, n_prev = 0;
+  uint32_t par_prev = 0;
+  gs_mbar_wait(&sm.st.full[0], 0);
+  tc_split_coefs<K>(sm.st.S[0], sm.bc_hi, sm.bc_lo, tid);
+  fence_smem_to_async();
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) {
+    if (elect_one()) {
+      fence_after_sync();
+      tc_issue_logits(tm, sm.img_hi, sm.img_lo, sm.bc_hi, sm.bc_lo, &sm.mma_bar);
+    }
+    __syncwarp();
+  }
   for (int k = 0; k < nchunks; ++k) {
     const int stage = k % STAGES;
-    gs_mbar_wait(&sm.st.full[stage], (uint32_t)((k / STAGES) & 1));
     const int n = min(TC_J, cnt - k * TC_J);
-    tc_split_coefs<K>(sm.st.S[stage], sm.bc_hi, sm.bc_lo, tid);
-    fence_smem_to_async();
-    fence_before_sync();
-    if (__syncthreads_and(!(T > GS_T_STOP))) {              // round k - 1 is complete everywhere
-      consumed = k * TC_J;
-      break;
-    }
-    if (warp == 0) {
-      if (elect_one()) {
-        fence_after_sync();
-        tc_issue_logits(tm, sm.img_hi, sm.img_lo, sm.bc_hi, sm.bc_lo, &sm.mma_bar);
-      }
-      __syncwarp();
-    }
-    if (k + STAGES - 1 < nchunks) {
-      const int kn = k + STAGES - 1;
-      tc_gather<K, STAGES, true>(sm.st, kn % STAGES, grec, rgb, ids, goff, start + kn * TC_J, min(TC_J, cnt - kn * TC_J),
-                                 tid);
-    }
+    gs_mbar_wait(&sm.st.full[stage], (uint32_t)((k / STAGES) & 1));   // records of this round
     gs_mbar_wait(&sm.mma_bar, (uint32_t)(k & 1));
     fence_after_sync();
+    if (k + 1 < nchunks) {                                  // logits(k) are complete: the coefficient operand is free
+      gs_mbar_wait(&sm.st.full[(k + 1) % STAGES], (uint32_t)(((k + 1) / STAGES) & 1));
+      tc_split_coefs<K>(sm.st.S[(k + 1) % STAGES], sm.bc_hi, sm.bc_lo, tid - 160);   // warps 5 .. 7
+    }
     const float4* Rr = sm.st.R[stage];
+    float(*part)[8] = sm.part[k & 1][warp];
 #pragma unroll 1
     for (int h = 0; h < 2; ++h) {
-      if (h * 8 >= n) break;
       uint32_t hw[3][4], lw[3][4];
-      if (__all_sync(0xffffffffu, !(T > GS_T_STOP))) {
-        // nothing left to blend in this warp: the rows of this half round are zeros
+      const bool have = h * 8 < n;                          // uniform
+      const bool idle = have && __all_sync(0xffffffffu, !(T > GS_T_STOP));
+      if (have && !idle) {
+        float lr[8], lg[8], lb[8];
+        tmem_ld8x3(trow + h * 8, trow + 16 + h * 8, trow + 32 + h * 8, lr, lg, lb);
+        const float4* Rh = Rr + 32 * h;
+        float* ph = &part[h * 8][(lane >> 2) & 7];
+        if (h * 8 + 8 <= n) {                               // all eight instances exist: no per-instance tests
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          sm.dct[(c * 2 + h) * 256 + tid] = make_uint4(0, 0, 0, 0);
-          sm.dct[(6 + c * 2 + h) * 256 + tid] = make_uint4(0, 0, 0, 0);
-        }
-        sm.part[warp][h * 8 + (lane >> 2)][lane & 3] = 0.f;
-        sm.part[warp][h * 8 + (lane >> 2)][4 + (lane & 3)] = 0.f;
-        continue;
-      }
-      float lr[8], lg[8], lb[8];
-      tmem_ld8x3(trow + h * 8, trow + 16 + h * 8, trow + 32 + h * 8, lr, lg, lb);
+          for (int jp = 0; jp < 4; ++jp) {
+            float dc[2][3];
 #pragma unroll
-      for (int jp = 0; jp < 4; ++jp) {
-        float dc[2][3];
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int jj = 2 * jp + u, j = h * 8 + jj;
-          float v[8];
-#pragma unroll
-          for (int q = 0; q < 8; ++q) v[q] = 0.f;
-          dc[u][0] = dc[u][1] = dc[u][2] = 0.f;
-          if (j < n) {
-            const float4 a = Rr[4 * j];
-            const float4 b4 = Rr[4 * j + 1];
-            const float dx = px - a.x, dy = py - a.y;
-            const float eu = fmaf(a.z, dx, -a.w * dy);
-            const float ev = fmaf(-b4.x * dy, dy, b4.y);
-            const float alpha = gs_ex2(fmaf(-dx, eu, ev));
-            if (T > GS_T_STOP) {                            // saturated pixels contribute exactly nothing
-              const float w = alpha * T;
-              float col[3];
-              tc_colours(lr[jj], lg[jj], lb[jj], col);
-              const float gc = fmaf(gr, col[0], fmaf(gg, col[1], gb * col[2]));
-              R = fmaf(-gc, w, R);
-              const float rc = gs_rcp(1.0000001f - alpha);
-              const float dal = fmaf(T, gc, -R * rc);
-              const float e = dal * alpha;
-              T -= w;
-              const float ex = e * dx, ey = e * dy;
-              v[0] = ex;
-              v[1] = ey;
-              v[2] = ex * dx;
-              v[3] = ex * dy;
-              v[4] = ey * dy;
-              v[5] = e;
-              // d colour_c / d logit_c = sigma'(.)      (gaussian.cu:666-674)
-              dc[u][0] = gr * w * col[0] * (1.f - col[0]);
-              dc[u][1] = gg * w * col[1] * (1.f - col[1]);
-              dc[u][2] = gb * w * col[2] * (1.f - col[2]);
+            for (int u = 0; u < 2; ++u) {
+              const int jj = 2 * jp + u;
+              float v[8];
+              pair(Rh[4 * jj], Rh[4 * jj + 1], lr[jj], lg[jj], lb[jj], dc[u], v);
+              const float r = reduce8(v, lane);
+              if ((lane & 3) == 0) ph[jj * 8] = r;
             }
-            const float r = reduce8(v, lane);
-            if ((lane & 3) == 0) sm.part[warp][j][(lane >> 2) & 7] = r;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) split_bf16x2(dc[0][c], dc[1][c], hw[c][jp], lw[c][jp]);
+          }
+        } else {
+#pragma unroll
+          for (int jp = 0; jp < 4; ++jp) {
+            float dc[2][3];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int jj = 2 * jp + u;
+              dc[u][0] = dc[u][1] = dc[u][2] = 0.f;
+              if (h * 8 + jj < n) {
+                float v[8];
+                pair(Rh[4 * jj], Rh[4 * jj + 1], lr[jj], lg[jj], lb[jj], dc[u], v);
+                const float r = reduce8(v, lane);
+                if ((lane & 3) == 0) ph[jj * 8] = r;
+              }
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) split_bf16x2(dc[0][c], dc[1][c], hw[c][jp], lw[c][jp]);
           }
         }
+      } else if (idle) {
+        // nothing left to blend in this warp: the rows of this half round are zeros
 #pragma unroll
-        for (int c = 0; c < 3; ++c) split_bf16x2(dc[0][c], dc[1][c], hw[c][jp], lw[c][jp]);
-      }
+        for (int c = 0; c < 3; ++c)
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        sm.dct[(c * 2 + h) * 256 + tid] = make_uint4(hw[c][0], hw[c][1], hw[c][2], hw[c][3]);
-        sm.dct[(6 + c * 2 + h) * 256 + tid] = make_uint4(lw[c][0], lw[c][1], lw[c][2], lw[c][3]);
+          for (int q = 0; q < 4; ++q) hw[c][q] = lw[c][q] = 0u;
+        part[h * 8 + (lane >> 2)][lane & 3] = 0.f;
+        part[h * 8 + (lane >> 2)][4 + (lane & 3)] = 0.f;
       }
+      if (h == 0 && n_prev > 0) {                           // the previous contraction has read sm.dct
+        gs_mbar_wait(&sm.mma2_bar, par_prev);
+        fence_after_sync();
+      }
+      if (have) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          sm.dct[(c * 2 + h) * 256 + tid] = make_uint4(hw[c][0], hw[c][1], hw[c][2], hw[c][3]);
+          sm.dct[(6 + c * 2 + h) * 256 + tid] = make_uint4(lw[c][0], lw[c][1], lw[c][2], lw[c][3]);
+        }
+      }
+      if (h == 0 && n_prev > 0) epilogue(n_prev);
     }
     fence_smem_to_async();
     fence_before_sync();
-    __syncthreads();                                        // gradient operand + geometry partials complete
+    const bool done = __syncthreads_and(!(T > GS_T_STOP)) != 0;   // operands of both contractions complete
+    const bool more = !done && k + 1 < nchunks;
     if (warp == 0) {
       if (elect_one()) {
         fence_after_sync();
+        if (more) tc_issue_logits(tm, sm.img_hi, sm.img_lo, sm.bc_hi, sm.bc_lo, &sm.mma_bar);
         constexpr uint32_t idesc2 = idesc_bf16(1, 1, 128, 32);
         const uint32_t a0 = gs_smem_u32(sm.dct), b0 = gs_smem_u32(sm.img_hi);
 #pragma unroll
@@ -462,7 +521,7 @@ __global__ void __launch_bounds__(TC_NT) blend_sh_bwd_tc_kernel(const GsRec* __r
       for (int u = 0; u < 6; ++u) {
         float t = 0.f;
 #pragma unroll
-        for (int w8 = 0; w8 < 8; ++w8) t += sm.part[w8][j][u];
+        for (int w8 = 0; w8 < 8; ++w8) t += sm.part[k & 1][w8][j][u];
         s[u] = t;
       }
       const float4 a = Rr[4 * j];
@@ -471,6 +530,7 @@ __global__ void __launch_bounds__(TC_NT) blend_sh_bwd_tc_kernel(const GsRec* __r
       const uint32_t rxy = __float_as_uint(cc.z), rwh = __float_as_uint(cc.w);
       const uint32_t slot = __float_as_uint(Rr[4 * j + 3].x) + ((uint32_t)ty - (rxy >> 16)) * (rwh & 0xffffu) +
                             ((uint32_t)tx - (rxy & 0xffffu));
+      sm.slot[j] = slot;                                    // for the coefficient rows, written one round later
       float* out = grad_inst + (size_t)slot * GREC;
       out[0] = GS_LN2 * (2.f * a.z * s[0] - a.w * s[1]);
       out[1] = GS_LN2 * (2.f * b4.x * s[1] - a.w * s[0]);
@@ -480,37 +540,24 @@ __global__ void __launch_bounds__(TC_NT) blend_sh_bwd_tc_kernel(const GsRec* __r
       out[5] = GS_LN2 * s[5];
       row_epoch[slot] = epoch;
     }
-    gs_mbar_wait(&sm.mma2_bar, (uint32_t)(k & 1));
+    n_prev = n;
+    par_prev = (uint32_t)(k & 1);
+    if (done) {
+      consumed = min(cnt, (k + 1) * TC_J);
+      break;
+    }
+    // stage (k + 3) % 4 held round k - 1, whose records were last read before this round's barrier
+    if (k + STAGES - 1 < nchunks) {
+      const int kn = k + STAGES - 1;
+      tc_gather<K, STAGES, true>(sm.st, kn % STAGES, grec, rgb, ids, goff, start + kn * TC_J, min(TC_J, cnt - kn * TC_J),
+                                 tid);
+    }
+  }
+  __syncthreads();                                          // sm.slot of the last round (written by warp 4)
+  if (n_prev > 0) {
+    gs_mbar_wait(&sm.mma2_bar, par_prev);
     fence_after_sync();
-    float val[16];
-    if (warp < 3) {                                         // rows 0 .. 95 live in TMEM lanes 0 .. 95
-      float a0[16], a1[16], b0[16], b1[16];
-      tmem_ld16(tm + tlane + D2COL, a0);
-      tmem_ld16(tm + tlane + D2COL + 16, a1);
-      tmem_ld16(tm + tlane + D2COL + 32, b0);
-      tmem_ld16(tm + tlane + D2COL + 48, b1);
-      if (tid < 48) {
-#pragma unroll
-        for (int q = 0; q < 16; ++q) val[q] = (a0[q] + b0[q]) + (a1[q] + b1[q]);
-      } else {
-#pragma unroll
-        for (int q = 0; q < 16; ++q) sm.epi[tid - 48][q] = a0[q] + b0[q];
-      }
-    }
-    fence_before_sync();
-    __syncthreads();
-    if (tid < 48) {
-      const int c = tid >> 4, j = tid & 15;
-      if (j < n) {
-        const float4 cc = Rr[4 * j + 2];
-        const uint32_t rxy = __float_as_uint(cc.z), rwh = __float_as_uint(cc.w);
-        const uint32_t slot = __float_as_uint(Rr[4 * j + 3].x) + ((uint32_t)ty - (rxy >> 16)) * (rwh & 0xffffu) +
-                              ((uint32_t)tx - (rxy & 0xffffu));
-        float* out = grad_inst + (size_t)slot * GREC + 6 + c * K;
-#pragma unroll
-        for (int q = 0; q < K; ++q) out[q] = val[q] + sm.epi[tid][q];
-      }
-    }
+    epilogue(n_prev);
   }
   asm volatile("cp.async.wait_all;" ::: "memory");
   fence_before_sync();

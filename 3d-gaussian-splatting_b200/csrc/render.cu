@@ -50,7 +50,7 @@ GsTuning& gs_tuning() {
                        tune_env("GS_TUNE_BWD_PX", 8),      tune_env("GS_TUNE_BWD_WS", 0),     tune_env("GS_TUNE_BWD_UNROLL", 4),
                        tune_env("GS_TUNE_BWD_STAGES", 3),  tune_env("GS_TUNE_BWD_MINB", 10),  tune_env("GS_TUNE_BWD_RQ", 4),
                        tune_env("GS_TUNE_FWD_PX", 4),      tune_env("GS_TUNE_BWD_CH", 32),    tune_env("GS_TUNE_STRICT", 0),
-                       tune_env("GS_TUNE_GATHER", 1),      tune_env("GS_TUNE_SH_TC", 0)};
+                       tune_env("GS_TUNE_GATHER", 1),      tune_env("GS_TUNE_SH_TC", 3)};
   return t;
 }
 extern "C" int gs_tune(const char* name, int value) {

@@ -53,6 +53,7 @@ __device__ __forceinline__ bool mbar_wait_bounded(uint64_t* bar, uint32_t parity
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t addr, float* v) {
   uint32_t r[16];
+  __syncwarp();
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n\t"
                "tcgen05.wait::ld.sync.aligned;"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
@@ -148,7 +149,7 @@ __global__ void __launch_bounds__(128) probe(int test, float* out, int* flag, lo
       mma_commit(&bar);
     }
     ncols = 16;
-  } else if (test == 4) {
+  } else if (test == 4 || test == 8) {
     // bf16 MN-major: (m, k) -> (k/8)*128 + (m/8)*SBO + (k%8)*16 + (m%8)*2 ; SBO = (K/8)*128 ; LBO = 128 ; K = 16 / MMA
     __nv_bfloat16* Ah = reinterpret_cast<__nv_bfloat16*>(A);
     __nv_bfloat16* Bh = reinterpret_cast<__nv_bfloat16*>(B);
@@ -164,12 +165,57 @@ __global__ void __launch_bounds__(128) probe(int test, float* out, int* flag, lo
     __syncthreads();
     if (ISSUER) {
       tc_fence_after();
-      const uint32_t idesc = make_idesc(1, 1, 1, 128, 16);
+      const uint32_t idesc = make_idesc(1, 1, 1, test == 8 ? 64 : 128, 16);
       for (int s = 0; s < 8; ++s)
         mma_f16(tm, make_desc(smem_u32(A) + s * 256, 128, 2048), make_desc(smem_u32(B) + s * 256, 128, 2048), idesc, s > 0);
       mma_commit(&bar);
     }
     ncols = 16;
+  } else if (test == 9) {
+    // throughput: batches of MMAs into INDEPENDENT accumulators (4 x 16 columns), K-major bf16 m128 / MN-major
+    for (int i = tid; i < 24 * 1024; i += 128) { A[i] = 0.f; }
+    for (int i = tid; i < 4 * 1024; i += 128) { B[i] = 0.f; }
+    fence_async_smem();
+    __syncthreads();
+    for (int mode = 0; mode < 6; ++mode) {
+      __syncthreads();
+      const long long t0 = clock64();
+      for (int r = 0; r < reps; ++r) {
+        if (tid == 0) {
+          tc_fence_after();
+          if (mode < 3) {              // m128 n{16,32,48} k16 MN-major bf16: 16 MMAs round-robin over 1 / 2 / 4 accumulators
+            const uint32_t idesc = make_idesc(1, 1, 1, 128, 16);
+            const int nacc = mode == 0 ? 1 : (mode == 1 ? 2 : 4);
+            for (int s = 0; s < 16; ++s)
+              mma_f16(tm + (s % nacc) * 16, make_desc(smem_u32(A) + (s & 7) * 256, 128, 2048), make_desc(smem_u32(B) + (s & 7) * 256, 128, 2048), idesc, s >= nacc);
+          } else {                     // m128 n48 k16 K-major bf16 (logits): 6 MMAs, chain of 6 / two chains of 3 / m64 n32 x 16 on 4 acc
+            if (mode == 3) {
+              const uint32_t idesc = make_idesc(1, 0, 0, 128, 48);
+              for (int s = 0; s < 6; ++s)
+                mma_f16(tm, make_desc(smem_u32(A), 4096, 128), make_desc(smem_u32(B), 768, 128), idesc, s > 0);
+            } else if (mode == 4) {
+              const uint32_t idesc = make_idesc(1, 0, 0, 128, 16);
+              for (int s = 0; s < 6; ++s)
+                mma_f16(tm + (s & 1) * 16, make_desc(smem_u32(A), 4096, 128), make_desc(smem_u32(B), 768, 128), idesc, s > 1);
+            } else {
+              const uint32_t idesc = make_idesc(1, 1, 1, 64, 16);
+              for (int s = 0; s < 16; ++s)
+                mma_f16(tm + (s & 3) * 16, make_desc(smem_u32(A) + (s & 7) * 256, 128, 2048), make_desc(smem_u32(B) + (s & 7) * 256, 128, 2048), idesc, s >= 4);
+            }
+          }
+          mma_commit(&bar);
+        }
+        if (!mbar_wait_bounded(&bar, parity)) { if (tid == 0) *flag = 1; }
+        parity ^= 1;
+      }
+      const long long t1 = clock64();
+      if (tid == 0 && blockIdx.x == 0) clk[mode] = t1 - t0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    __syncwarp();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tm), "r"(64));
+    return;
   } else {
     // timing: smem contents do not matter
     for (int i = tid; i < 24 * 1024; i += 128) { A[i] = 0.f; }
@@ -212,7 +258,6 @@ __global__ void __launch_bounds__(128) probe(int test, float* out, int* flag, lo
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tm), "r"(64));
     return;
   }
-  if (tid == 0 || tid == 33) printf("tid %d tm=0x%x before wait\n", tid, tm);
   const bool ok = mbar_wait_bounded(&bar, 0);
   if (!ok && tid == 0) *flag = 1;
   tc_fence_after();
@@ -225,7 +270,7 @@ __global__ void __launch_bounds__(128) probe(int test, float* out, int* flag, lo
   }
   tc_fence_before();
   __syncthreads();
-  if (tid == 0 || tid == 33) printf("tid %d tm=0x%x tmem_base=0x%x before dealloc\n", tid, tm, tmem_base);
+  __syncwarp();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tm), "r"(64));
 }
 
@@ -237,6 +282,20 @@ int main(int argc, char** argv) {
   CK(cudaMalloc(&out, 128 * 64 * 4)); CK(cudaMalloc(&flag, 4)); CK(cudaMalloc(&clk, 64));
   CK(cudaMemset(out, 0xff, 128 * 64 * 4)); CK(cudaMemset(flag, 0, 4)); CK(cudaMemset(clk, 0, 64));
   CK(cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  if (test == 9) {
+    const int reps = 2000;
+    probe<<<1, 128, SMEM_BYTES>>>(9, out, flag, clk, 10);
+    CK(cudaDeviceSynchronize());
+    probe<<<1, 128, SMEM_BYTES>>>(9, out, flag, clk, reps);
+    CK(cudaDeviceSynchronize());
+    long long h[8]; int f;
+    CK(cudaMemcpy(h, clk, 64, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(&f, flag, 4, cudaMemcpyDeviceToHost));
+    const char* names[6] = {"16 x bf16 m128n16k16, 1 accumulator", "16 x bf16 m128n16k16, 2 accumulators", "16 x bf16 m128n16k16, 4 accumulators",
+                            "6 x bf16 m128n48k16 K-major, 1 chain", "6 x bf16 m128n16k16 K-major, 2 chains", "16 x bf16 m64n16k16, 4 accumulators"};
+    printf("timeout_flag %d\n", f);
+    for (int m = 0; m < 6; ++m) printf("   %-42s %8.1f clk / batch (commit + wait each)\n", names[m], (double)h[m] / reps);
+    return 0;
+  }
   if (test == 5) {
     const int reps = 2000;
     for (int grid : {1, 148, 148 * 2, 148 * 4}) {
@@ -266,7 +325,7 @@ int main(int argc, char** argv) {
   CK(cudaDeviceSynchronize());
   std::vector<float> h(128 * 64); int f;
   CK(cudaMemcpy(h.data(), out, 128 * 64 * 4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(&f, flag, 4, cudaMemcpyDeviceToHost));
-  const int M = test == 3 ? 64 : 128, N = test == 1 ? 48 : 16, K = test == 1 ? 16 : 128;
+  const int M = (test == 3 || test == 8) ? 64 : 128, N = test == 1 ? 48 : 16, K = test == 1 ? 16 : 128;
   std::vector<float> ref(M * N);
   for (int m = 0; m < M; ++m)
     for (int n = 0; n < N; ++n) {
@@ -286,7 +345,7 @@ int main(int argc, char** argv) {
     }
     if (found >= 0) ++matched;
     if (found == m) ++identity;
-    if (test == 3 || found != m) { if (m < 70) printf("  row %3d -> lane %d\n", m, found); }
+    if (test == 3 || test == 8 || found != m) { if (m < 70) printf("  row %3d -> lane %d\n", m, found); }
   }
   printf("rows matched %d / %d, identity mapping %d\n", matched, M, identity);
   printf("lane0: ");

@@ -62,18 +62,25 @@ def test_fused_frame_vs_oracle(gs, cuda, n, w, h, k, opa):
     assert torch.equal(idx.cpu().long(), aux["gauss_idx"])
 
 
+@pytest.mark.parametrize("sh_tc", [3, 0], ids=["tensor-core", "scalar"])
 @pytest.mark.parametrize("sh_dim,opa", [(27, (0.005, 0.05)), (27, (0.3, 0.95)), (48, (0.05, 0.9))])
-def test_fused_frame_sh_vs_oracle(gs, cuda, sh_dim, opa):
+def test_fused_frame_sh_vs_oracle(gs, cuda, sh_dim, opa, sh_tc):
+    """Both SH blend kernel families (blend_sh_tc.cu: tcgen05 contractions with bf16 hi/lo operands, the default;
+    blend_sh.cu: scalar fp32) against the fp64 oracle, at the tolerances of BASELINE.json's north_star."""
     n, w, h = 2500, 112, 80
     g, v, cam = scene(n, w, h, k=1, sh_dim=sh_dim, opa_range=opa)
     go = S.make_grad_output(h, w, 0) * (h * w)
     oimg, ograds, aux = _oracle_frame(g, cam, go, use_sh_coeff=True)
-    sp = _splatter(g, [v], cuda, use_sh_coeff=True)
-    img = sp(0)
-    assert abs_err(img, oimg) < IMG_ATOL
-    img.backward(go.to(cuda))
-    for name in ("pos", "rgb", "opa", "quat", "scale"):
-        assert rel_err(getattr(sp.gaussian_3ds, name).grad, ograds[name]) < GRAD_RTOL, name
+    gs[0].tune("sh_tc", sh_tc)
+    try:
+        sp = _splatter(g, [v], cuda, use_sh_coeff=True)
+        img = sp(0)
+        assert abs_err(img, oimg) < IMG_ATOL
+        img.backward(go.to(cuda))
+        for name in ("pos", "rgb", "opa", "quat", "scale"):
+            assert rel_err(getattr(sp.gaussian_3ds, name).grad, ograds[name]) < GRAD_RTOL, name
+    finally:
+        gs[0].tune("sh_tc", 3)
 
 
 def test_fused_frame_vs_reference_pipeline(gs, ref, cuda):
