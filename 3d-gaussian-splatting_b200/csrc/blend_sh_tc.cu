@@ -222,26 +222,28 @@ __global__ void __launch_bounds__(TC_NT) blend_sh_fwd_tc_kernel(const GsRec* __r
         if (__all_sync(0xffffffffu, !(T > GS_T_STOP))) break;
         float lr[8], lg[8], lb[8];
         tmem_ld8x3(trow + h * 8, trow + 16 + h * 8, trow + 32 + h * 8, lr, lg, lb);
+        const float4* Rh = R + 32 * h;
+        // one (pixel, instance) pair; a saturated pixel blends nothing (w = 0), without a divergent branch
+        auto pair = [&](const float4 a, const float4 b4, float l0, float l1, float l2) {
+          const float dx = px - a.x, dy = py - a.y;
+          const float eu = fmaf(a.z, dx, -a.w * dy);
+          const float ev = fmaf(-b4.x * dy, dy, b4.y);
+          const float alpha = gs_ex2(fmaf(-dx, eu, ev));
+          const float w = (T > GS_T_STOP) ? alpha * T : 0.f;
+          float col[3];
+          tc_colours(l0, l1, l2, col);
+          cr = fmaf(col[0], w, cr);
+          cg = fmaf(col[1], w, cg);
+          cb = fmaf(col[2], w, cb);
+          T -= w;
+        };
+        if (h * 8 + 8 <= n) {
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
-          const int j = h * 8 + jj;
-          if (j < n) {
-            const float4 a = R[4 * j];
-            const float4 b4 = R[4 * j + 1];
-            const float dx = px - a.x, dy = py - a.y;
-            const float eu = fmaf(a.z, dx, -a.w * dy);
-            const float ev = fmaf(-b4.x * dy, dy, b4.y);
-            const float alpha = gs_ex2(fmaf(-dx, eu, ev));
-            if (T > GS_T_STOP) {
-              const float w = alpha * T;
-              float col[3];
-              tc_colours(lr[jj], lg[jj], lb[jj], col);
-              cr = fmaf(col[0], w, cr);
-              cg = fmaf(col[1], w, cg);
-              cb = fmaf(col[2], w, cb);
-              T -= w;
-            }
-          }
+          for (int jj = 0; jj < 8; ++jj) pair(Rh[4 * jj], Rh[4 * jj + 1], lr[jj], lg[jj], lb[jj]);
+        } else {
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj)
+            if (h * 8 + jj < n) pair(Rh[4 * jj], Rh[4 * jj + 1], lr[jj], lg[jj], lb[jj]);
         }
       }
     }
