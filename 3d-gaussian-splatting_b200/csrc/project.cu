@@ -150,13 +150,16 @@ __global__ void __launch_bounds__(kBlock) fused_project_bwd_kernel(
     float* __restrict__ g_rgb, float* __restrict__ g_opa, float* __restrict__ g_quat, float* __restrict__ g_scale,
     GsGradPush push) {
   int i = blockIdx.x * kBlock + threadIdx.x;
-  if (i >= n) return;
+  // SH colour on one GPU: the warp writes its coefficient gradients together (below), so threads past n stay
+  constexpr bool kStagedRgb = (D != 3) && (W == 0);
+  const bool valid = i < n;
+  if (!valid && !kStagedRgb) return;
   float gp[3] = {0.f, 0.f, 0.f}, gq_raw[4] = {0.f, 0.f, 0.f, 0.f}, gs_raw[3] = {0.f, 0.f, 0.f};
   float go = 0.f;
   float acc[GW];
 #pragma unroll
   for (int k = 0; k < GW; ++k) acc[k] = 0.f;
-  const uint32_t cnt = count[i];
+  const uint32_t cnt = valid ? count[i] : 0u;
   if (cnt > 0) {
     const uint32_t o0 = offsets_g[i], o1 = o0 + cnt;   // this Gaussian's contiguous gradient rows
     // issue the parameter loads BEFORE the row loop so that both round trips to HBM overlap
@@ -222,13 +225,42 @@ __global__ void __launch_bounds__(kBlock) fused_project_bwd_kernel(
     }
   }
   if (W == 0) {
+    if constexpr (kStagedRgb) {
+      // The 32 Gaussians of a warp own 32 * D contiguous floats of g_rgb.  One strided 4-byte store per coefficient
+      // makes every store a partial-sector write (read-modify-write under ECC: 8x the bytes; 0.45 / 0.91 ms at
+      // D = 27 / 48 against 0.17 ms for RGB): the rows go through shared memory and leave as whole sectors.
+      // D = 48: two passes of 24 floats (96-byte, sector-aligned pieces); D = 27: the whole 32 x 108-byte span.
+      constexpr int HW = (D % 8 == 0) ? D / 2 : D;
+      __shared__ float stage[kBlock / 32][32][HW + 1];
+      const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+      const int i0 = blockIdx.x * kBlock + warp * 32;
+      const int nrow = min(32, n - i0);
+#pragma unroll
+      for (int pass = 0; pass < D / HW; ++pass) {
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < HW; ++k) stage[warp][lane][k] = acc[6 + pass * HW + k];
+        __syncwarp();
+        if (HW == D) {
+          float* dst = g_rgb + (size_t)i0 * D;
+          for (int t = lane; t < nrow * D; t += 32) dst[t] = stage[warp][t / D][t % D];
+        } else {
+          for (int t = lane; t < nrow * HW; t += 32) {
+            const int g = t / HW, c = t % HW;
+            g_rgb[(size_t)(i0 + g) * D + pass * HW + c] = stage[warp][g][c];
+          }
+        }
+      }
+      if (!valid) return;
+    } else {
+#pragma unroll
+      for (int k = 0; k < D; ++k) g_rgb[(size_t)i * D + k] = acc[6 + k];
+    }
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       g_pos[3 * i + k] = gp[k];
       g_scale[3 * i + k] = gs_raw[k];
     }
-#pragma unroll
-    for (int k = 0; k < D; ++k) g_rgb[(size_t)i * D + k] = acc[6 + k];
     reinterpret_cast<float4*>(g_quat)[i] = make_float4(gq_raw[0], gq_raw[1], gq_raw[2], gq_raw[3]);
     g_opa[i] = go;
   } else {
