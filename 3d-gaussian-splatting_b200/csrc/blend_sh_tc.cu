@@ -877,16 +877,12 @@ cudaError_t gs_launch_blend_sh_bwd_tc(const GsRec* grec, const float* rgb, const
   const bool two_px = (gs_tuning().sh_tc & 4) != 0;   // two pixels per thread (128 threads per tile)
 #define GS_SHB_TC(K)                                                                                                  \
   do {                                                                                                                \
-    static bool attr_done = false;                                                                                    \
-    if (!attr_done) {                                                                                                 \
-      cudaError_t e = cudaFuncSetAttribute(blend_sh_bwd_tc_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
-                                           (int)sizeof(TcBwdSmem<K>));                                                \
-      if (e != cudaSuccess) return e;                                                                                 \
-      e = cudaFuncSetAttribute(blend_sh_bwd_tc2_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,               \
-                               (int)sizeof(TcBwdSmem<K>));                                                            \
-      if (e != cudaSuccess) return e;                                                                                 \
-      attr_done = true;                                                                                               \
-    }                                                                                                                 \
+    /* per device and cheap: set on every launch rather than cached in a process-wide flag */                        \
+    cudaError_t e = two_px ? cudaFuncSetAttribute(blend_sh_bwd_tc2_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                                  (int)sizeof(TcBwdSmem<K>))                                          \
+                           : cudaFuncSetAttribute(blend_sh_bwd_tc_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                                  (int)sizeof(TcBwdSmem<K>));                                         \
+    if (e != cudaSuccess) return e;                                                                                   \
     if (two_px)                                                                                                       \
       blend_sh_bwd_tc2_kernel<K><<<g.n_tiles, 128, sizeof(TcBwdSmem<K>), st>>>(                                        \
           grec, rgb, ids, goff, tile_accum, g.wp, g.hp, g.ntx, g.fx, g.fy, r.rays_o, r.lefttop, r.dx, r.dy, image,     \
