@@ -3,8 +3,9 @@
 // The two dense contractions of the SH path (reference gaussian.cu:936-948 forward colour, :665-689 backward)
 //   logit[pixel, (instance, channel)] = sum_q SH_q(pixel) * coef[instance, channel, q]                  (forward + backward)
 //   d coef[(instance, channel), q]    = sum_pixel d logit[pixel, (instance, channel)] * SH_q(pixel)     (backward)
-// are the only GEMM-shaped work of the rasterizer: 2 * 3K (forward) + 4 * 3K (backward) FMAs of the 57 / 137
-// instructions the scalar kernels (blend_sh.cu) spend per (pixel, instance).  Here ONE THREAD OWNS ONE PIXEL:
+// are the only GEMM-shaped work of the rasterizer: 3K (forward) / 2 * 3K (backward) FMAs per (pixel, instance), i.e.
+// 27 of the 57 and 54 of the 137 instructions the scalar kernels (blend_sh.cu) issue per warp and 32 pairs at K = 9.
+// Here ONE THREAD OWNS ONE PIXEL:
 //   * a tile is 256 pixels = two M = 128 accumulator blocks; the SH basis of the tile is written once to shared
 //     memory as bf16 hi + lo parts (x = hi + lo to 2^-17) in the no-swizzle canonical layout, whose image is at the
 //     same time the K-major A operand of the first and the MN-major B operand of the second contraction;
@@ -278,7 +279,6 @@ struct TcBwdSmem {
   TcStage<K, 4> st;
   float part[2][8][TC_J][8];   // per-warp sums of the six geometry values (by round parity)
   float epi[48][17];           // (lo part) . basis, staged for the thread that owns the hi row
-  uint32_t slot[TC_J];         // gradient rows of the round whose coefficient gradients are still in TMEM
   uint64_t mma_bar, mma2_bar;
   uint32_t tmem_base;
 };
@@ -349,7 +349,8 @@ __global__ void __launch_bounds__(TC_NT) blend_sh_bwd_tc_kernel(const GsRec* __r
   // coefficient-gradient rows of the previous round: its contraction ran while this round's operands were prepared.
   // Rows 0 .. 95 of the accumulators live in TMEM lanes 0 .. 95 (warps 0 .. 2): (hi part) x (basis hi | lo) in rows
   // 0 .. 47, (lo part) x basis hi in rows 48 .. 95, summed by the thread that owns the hi row.
-  auto epilogue = [&](int np) {
+  // (np, Rp: instance count and staged records of THAT round - its stage is not refilled before the next barrier)
+  auto epilogue = [&](int np, const float4* Rp) {
     if (warp < 3) {
       float a[32], b[32];
       tmem_ld32(tm + tlane + D2COL, a);
@@ -362,7 +363,11 @@ __global__ void __launch_bounds__(TC_NT) blend_sh_bwd_tc_kernel(const GsRec* __r
       if (tid < 48) {
         const int c = tid >> 4, j = tid & 15;
         if (j < np) {
-          float* out = grad_inst + (size_t)sm.slot[j] * GREC + 6 + c * K;
+          const float4 cc = Rp[4 * j + 2];
+          const uint32_t rxy = __float_as_uint(cc.z), rwh = __float_as_uint(cc.w);
+          const uint32_t slot = __float_as_uint(Rp[4 * j + 3].x) + ((uint32_t)ty - (rxy >> 16)) * (rwh & 0xffffu) +
+                                ((uint32_t)tx - (rxy & 0xffffu));
+          float* out = grad_inst + (size_t)slot * GREC + 6 + c * K;
 #pragma unroll
           for (int q = 0; q < K; ++q) out[q] = ((a[q] + b[q]) + (a[16 + q] + b[16 + q])) + sm.epi[tid][q];
         }
@@ -406,7 +411,7 @@ __global__ void __launch_bounds__(TC_NT) blend_sh_bwd_tc_kernel(const GsRec* __r
   //   wait contraction(k - 1) (it read sm.dct)  ->  store their rows  ->  [warps 0-2: coefficient rows of round k - 1]
   //   ->  second 8 instances  ->  barrier + "all pixels saturated" vote  ->  issue logits(k + 1), then contraction(k)
   //   ->  [warp 4: geometry rows of round k]  ->  gather round k + 3.
-  int consumed = cnt, n_prev = 0;
+  int consumed = cnt, n_prev = 0, st_prev = 0;
   uint32_t par_prev = 0;
   gs_mbar_wait(&sm.st.full[0], 0);
   tc_split_coefs<K>(sm.st.S[0], sm.bc_hi, sm.bc_lo, tid);
@@ -496,7 +501,7 @@ __global__ void __launch_bounds__(TC_NT) blend_sh_bwd_tc_kernel(const GsRec* __r
           sm.dct[(6 + c * 2 + h) * 256 + tid] = make_uint4(lw[c][0], lw[c][1], lw[c][2], lw[c][3]);
         }
       }
-      if (h == 0 && n_prev > 0) epilogue(n_prev);
+      if (h == 0 && n_prev > 0) epilogue(n_prev, sm.st.R[(k - 1) % STAGES]);
     }
     fence_smem_to_async();
     fence_before_sync();
@@ -533,7 +538,6 @@ __global__ void __launch_bounds__(TC_NT) blend_sh_bwd_tc_kernel(const GsRec* __r
       const uint32_t rxy = __float_as_uint(cc.z), rwh = __float_as_uint(cc.w);
       const uint32_t slot = __float_as_uint(Rr[4 * j + 3].x) + ((uint32_t)ty - (rxy >> 16)) * (rwh & 0xffffu) +
                             ((uint32_t)tx - (rxy & 0xffffu));
-      sm.slot[j] = slot;                                    // for the coefficient rows, written one round later
       float* out = grad_inst + (size_t)slot * GREC;
       out[0] = GS_LN2 * (2.f * a.z * s[0] - a.w * s[1]);
       out[1] = GS_LN2 * (2.f * b4.x * s[1] - a.w * s[0]);
@@ -545,6 +549,7 @@ __global__ void __launch_bounds__(TC_NT) blend_sh_bwd_tc_kernel(const GsRec* __r
     }
     n_prev = n;
     par_prev = (uint32_t)(k & 1);
+    st_prev = stage;
     if (done) {
       consumed = min(cnt, (k + 1) * TC_J);
       break;
@@ -556,11 +561,11 @@ __global__ void __launch_bounds__(TC_NT) blend_sh_bwd_tc_kernel(const GsRec* __r
                                  tid);
     }
   }
-  __syncthreads();                                          // sm.slot of the last round (written by warp 4)
+  __syncthreads();
   if (n_prev > 0) {
     gs_mbar_wait(&sm.mma2_bar, par_prev);
     fence_after_sync();
-    epilogue(n_prev);
+    epilogue(n_prev, sm.st.R[st_prev]);
   }
   asm volatile("cp.async.wait_all;" ::: "memory");
   fence_before_sync();
@@ -645,7 +650,8 @@ __global__ void __launch_bounds__(128) blend_sh_bwd_tc2_kernel(const GsRec* __re
   for (int k = 0; k < STAGES - 1 && k < nchunks; ++k)
     tc_gather<K, STAGES, true, NT>(sm.st, k, grec, rgb, ids, goff, start + k * TC_J, min(TC_J, cnt - k * TC_J), tid);
 
-  auto epilogue = [&](int np) {
+  // (np, Rp: instance count and staged records of THAT round - its stage is not refilled before the next barrier)
+  auto epilogue = [&](int np, const float4* Rp) {
     if (warp < 3) {
       float a[32], b[32];
       tmem_ld32(tm + tlane + D2COL, a);
@@ -658,7 +664,11 @@ __global__ void __launch_bounds__(128) blend_sh_bwd_tc2_kernel(const GsRec* __re
       if (tid < 48) {
         const int c = tid >> 4, j = tid & 15;
         if (j < np) {
-          float* out = grad_inst + (size_t)sm.slot[j] * GREC + 6 + c * K;
+          const float4 cc = Rp[4 * j + 2];
+          const uint32_t rxy = __float_as_uint(cc.z), rwh = __float_as_uint(cc.w);
+          const uint32_t slot = __float_as_uint(Rp[4 * j + 3].x) + ((uint32_t)ty - (rxy >> 16)) * (rwh & 0xffffu) +
+                                ((uint32_t)tx - (rxy & 0xffffu));
+          float* out = grad_inst + (size_t)slot * GREC + 6 + c * K;
 #pragma unroll
           for (int q = 0; q < K; ++q) out[q] = ((a[q] + b[q]) + (a[16 + q] + b[16 + q])) + sm.epi[tid][q];
         }
@@ -706,7 +716,7 @@ __global__ void __launch_bounds__(128) blend_sh_bwd_tc2_kernel(const GsRec* __re
     v[7] = 0.f;
   };
 
-  int consumed = cnt, n_prev = 0;
+  int consumed = cnt, n_prev = 0, st_prev = 0;
   uint32_t par_prev = 0;
   gs_mbar_wait(&sm.st.full[0], 0);
   tc_split_coefs<K>(sm.st.S[0], sm.bc_hi, sm.bc_lo, tid);
@@ -788,7 +798,7 @@ __global__ void __launch_bounds__(128) blend_sh_bwd_tc2_kernel(const GsRec* __re
             sm.dct[(6 + c * 2 + h) * 256 + tid + 128 * p] = make_uint4(lw[p][c][0], lw[p][c][1], lw[p][c][2], lw[p][c][3]);
           }
       }
-      if (h == 0 && n_prev > 0) epilogue(n_prev);
+      if (h == 0 && n_prev > 0) epilogue(n_prev, sm.st.R[(k - 1) % STAGES]);
     }
     fence_smem_to_async();
     fence_before_sync();
@@ -820,7 +830,6 @@ __global__ void __launch_bounds__(128) blend_sh_bwd_tc2_kernel(const GsRec* __re
       const uint32_t rxy = __float_as_uint(cc.z), rwh = __float_as_uint(cc.w);
       const uint32_t slot = __float_as_uint(Rr[4 * j + 3].x) + ((uint32_t)ty - (rxy >> 16)) * (rwh & 0xffffu) +
                             ((uint32_t)tx - (rxy & 0xffffu));
-      sm.slot[j] = slot;
       float* out = grad_inst + (size_t)slot * GREC;
       out[0] = GS_LN2 * (2.f * a.z * s[0] - a.w * s[1]);
       out[1] = GS_LN2 * (2.f * b4.x * s[1] - a.w * s[0]);
@@ -832,6 +841,7 @@ __global__ void __launch_bounds__(128) blend_sh_bwd_tc2_kernel(const GsRec* __re
     }
     n_prev = n;
     par_prev = (uint32_t)(k & 1);
+    st_prev = stage;
     if (done) {
       consumed = min(cnt, (k + 1) * TC_J);
       break;
@@ -846,7 +856,7 @@ __global__ void __launch_bounds__(128) blend_sh_bwd_tc2_kernel(const GsRec* __re
   if (n_prev > 0) {
     gs_mbar_wait(&sm.mma2_bar, par_prev);
     fence_after_sync();
-    epilogue(n_prev);
+    epilogue(n_prev, sm.st.R[st_prev]);
   }
   asm volatile("cp.async.wait_all;" ::: "memory");
   fence_before_sync();

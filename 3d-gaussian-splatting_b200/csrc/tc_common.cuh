@@ -63,17 +63,8 @@ __device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence
 // generic-proxy shared-memory writes -> visible to the tensor core's (async proxy) operand reads
 __device__ __forceinline__ void fence_smem_to_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// lane L of the warp reads columns [col, col + 8) of TMEM lane (warp % 4) * 32 + L; blocks until the data is there
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
-  uint32_t r[8];
-  __syncwarp();
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n\t"
-               "tcgen05.wait::ld.sync.aligned;"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "r"(taddr) : "memory");
-#pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
-}
+// tcgen05.ld.32x32b: lane L of the warp reads consecutive columns of TMEM lane (warp % 4) * 32 + L; the helpers block
+// until the data is there (tcgen05.wait::ld).
 // three column blocks of 8 (one per colour channel) with a single wait
 __device__ __forceinline__ void tmem_ld8x3(uint32_t t0, uint32_t t1, uint32_t t2, float* v0, float* v1, float* v2) {
   uint32_t r[24];
@@ -93,18 +84,6 @@ __device__ __forceinline__ void tmem_ld8x3(uint32_t t0, uint32_t t1, uint32_t t2
     v2[i] = __uint_as_float(r[16 + i]);
   }
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-  uint32_t r[16];
-  __syncwarp();
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n\t"
-               "tcgen05.wait::ld.sync.aligned;"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-               : "r"(taddr) : "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   uint32_t r[32];
   __syncwarp();

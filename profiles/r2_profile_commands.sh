@@ -15,5 +15,5 @@ python bench.py --colour 27 --impl reference --steps 5 --warmup 2 > gpurun_out/r
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-extra-legs > gpurun_out/r2/ncu_launches.log 2>&1
 # full sets: all six kernels of OUR frame (second frame), RGB and SH-27
 ncu --set full --clock-control none --import-source on -k regex:"blend_|fused_project|emit_keys|tile_ranges" -s 6 -c 6 -o gpurun_out/r2/prof_C3_D3 -f python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-extra-legs > gpurun_out/r2/ncu_full_d3.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"blend_sh" -s 2 -c 2 -o gpurun_out/r2/prof_C3_D27 -f python bench.py --colour 27 --steps 2 --warmup 1 --no-cpu-baseline --no-extra-legs > gpurun_out/r2/ncu_full_d27.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"blend_sh|fused_project_bwd" -s 3 -c 3 -o gpurun_out/r2/prof_C3_D27 -f python bench.py --colour 27 --steps 2 --warmup 1 --no-cpu-baseline --no-extra-legs > gpurun_out/r2/ncu_full_d27.log 2>&1
 ls -la gpurun_out/r2
