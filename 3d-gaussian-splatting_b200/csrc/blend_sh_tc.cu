@@ -411,6 +411,17 @@ __global__ void __launch_bounds__(TC_NT) blend_sh_bwd_tc_kernel(const GsRec* __r
   //   wait contraction(k - 1) (it read sm.dct)  ->  store their rows  ->  [warps 0-2: coefficient rows of round k - 1]
   //   ->  second 8 instances  ->  barrier + "all pixels saturated" vote  ->  issue logits(k + 1), then contraction(k)
   //   ->  [warp 4: geometry rows of round k]  ->  gather round k + 3.
+  // What orders every producer / consumer pair (B(k) = the barrier of round k):
+  //   staged records / coefficients   cp.async -> stage mbarrier (full[s]) -> every reader waits on it; a stage is refilled
+  //                                   (round k + 3 into the stage of round k - 1) after B(k), its last readers (blend of
+  //                                   k - 1, geometry rows, coefficient rows of k - 1) all run before B(k)
+  //   bc_hi / bc_lo                   written (warps 5-7) after their wait on logits(k); read by logits(k + 1), issued after B(k)
+  //   TMEM logits                     written by logits(k + 1) after B(k); all tcgen05.ld of round k precede B(k)
+  //   sm.dct                          written after the wait on contraction(k - 1); read by contraction(k), issued after B(k)
+  //   TMEM gradient accumulators      written by contraction(k) after B(k); read (warps 0-2) in round k + 1 after its mbarrier,
+  //                                   before B(k + 1), after which contraction(k + 1) overwrites them
+  //   sm.part[k & 1]                  written in round k; read by warp 4 after B(k); rewritten in round k + 2, after B(k + 1)
+  //   sm.epi                          warps 0-2 only, named barrier 1; the next use lies behind B(k)
   int consumed = cnt, n_prev = 0, st_prev = 0;
   uint32_t par_prev = 0;
   gs_mbar_wait(&sm.st.full[0], 0);
