@@ -1,13 +1,20 @@
 // Probe of tcgen05.mma (cta_group::1) with the no-swizzle canonical shared-memory layouts that the SH
 // blend kernels use: checks descriptor encodings, the TMEM lane mapping of M = 64 / 128 accumulators
-// and the cost of short MMA batches.  Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o umma_probe
-// umma_probe.cu ; run `umma_probe <test>` on the B200 box (every wait is bounded: a wrong descriptor
-// reports, it does not hang).
+// and the cost of short MMA batches.  Build: nvcc [-DELECT] -gencode arch=compute_100a,code=sm_100a -O3 -o umma_probe
+// umma_probe.cu ; run `umma_probe <test> [variant]` on the B200 box (every wait is bounded: a wrong descriptor
+// reports, it does not hang; variant 1 exchanges the leading / stride byte offsets of every descriptor).
 //   test 1: tf32, A K-major [128 x 16], B K-major [48 x 16]          (colour logits: pixels x (inst,ch))
-//   test 2: tf32, A MN-major [M x 128], B MN-major [16 x 128], M=128 (coefficient gradients)
-//   test 3: same as 2 with M = 64 (prints the lane of every row)
-//   test 4: bf16, A MN-major [M=128 x 128], B MN-major [16 x 128], K = 16 per instruction
-//   test 5: timing of batches (6 x m128n48k8 tf32; 16 x m128n16k8; 16 x m64n16k8; 8 x bf16 m128n16k16)
+//   test 2: tf32, A MN-major [M x 128], B MN-major [16 x 128], M=128 (result: all zeros - not usable without swizzle)
+//   test 3: same as 2 with M = 64
+//   test 4: bf16, A MN-major [M=128 x 128], B MN-major [16 x 128], K = 16 per instruction (coefficient gradients)
+//   test 5: timing of dependent batches (6 x m128n48k8 tf32; 16 x m128n16k8; 16 x m64n16k8; 8 x bf16 m128n16k16), 1 .. 2 CTAs/SM
+//   test 6 / 7: test 1 without the TMEM read / without the MMA (used to isolate a trap: see below)
+//   test 8: test 4 with M = 64 (prints the TMEM lane of every row: r -> (r / 16) * 32 + r % 16)
+//   test 9: 16 MMAs round-robin over 1 / 2 / 4 accumulators (no overlap inside one CTA), the logits batch, m64
+// Lesson kept in tc_common.cuh: .sync.aligned tcgen05 instructions (alloc, dealloc, ld) need a reconverged warp; after
+// `if (tid == 0) { issue }` or an mbarrier spin the first build executed tcgen05.dealloc once for lane 0 and once for
+// the other 31 lanes ("unallocated columns being dealloced" trap) - __syncwarp() first, and issue from an elected lane
+// of a warp-uniform branch (-DELECT).
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <cstdio>
