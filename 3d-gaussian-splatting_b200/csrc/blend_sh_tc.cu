@@ -18,6 +18,8 @@
 //     operand [96 rows = (hi | lo) x 3 channels x 16 instances, K = 256 pixels] and contracted with the basis
 //     image (N = 32 = hi | lo) by 16 K = 16 MMAs; the six geometry sums per instance keep the warp-shuffle reduction.
 // Layouts / descriptor encodings: tc_common.cuh (validated by profiles/r2_micro/umma_probe.cu).
+#include <cstddef>
+
 #include "internal.h"
 #include "sh_common.cuh"
 #include "tc_common.cuh"
@@ -298,6 +300,8 @@ __global__ void __launch_bounds__(TC_NT) blend_sh_bwd_tc_kernel(const GsRec* __r
                                                                 int* __restrict__ tile_neff_b) {
   constexpr int STAGES = 4, TCOLS = 256, NV = sh_nv(K), GREC = (NV + 3) / 4 * 4;
   constexpr uint32_t D2COL = 96;                            // logits: columns [0, 96); gradient accumulators: 2 x 32
+  static_assert(offsetof(TcBwdSmem<K>, img_hi) == 12 * 256 * 16 && offsetof(TcBwdSmem<K>, img_lo) == 14 * 256 * 16,
+                "the basis image must follow the gradient operand: descriptors address both as one region");
   extern __shared__ __align__(128) uint8_t tc_smem_raw[];
   TcBwdSmem<K>& sm = *reinterpret_cast<TcBwdSmem<K>*>(tc_smem_raw);
   const int tile = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
